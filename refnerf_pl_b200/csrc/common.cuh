@@ -1,0 +1,125 @@
+// Shared device helpers for the refnerf_pl_b200 CUDA kernels (sm_100a).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/refnerf_b200.h"
+
+#define RN_EPS32 1.1920928955078125e-07f
+#define RN_FULL 0xffffffffu
+
+#define RN_CUDA_CHECK_LAUNCH()                       \
+  do {                                               \
+    cudaError_t e__ = cudaGetLastError();            \
+    if (e__ != cudaSuccess) return rn_set_cuda_error(e__, __FILE__, __LINE__); \
+  } while (0)
+
+int rn_set_cuda_error(cudaError_t e, const char* file, int line);
+int rn_set_error(int code, const char* msg);
+
+// ------------------------------------------------------------------------------------------
+// Activation buffers: [rows, ld] matrices that feed / leave the GEMMs.
+//   RN_PREC_FP32   : hi = float*            (exact-parity SIMT path)
+//   RN_PREC_BF16   : hi = bf16*             (throughput tensor path)
+//   RN_PREC_BF16X3 : hi, lo = bf16*         (split-bf16 tensor path: x ~= hi + lo, 16-bit mantissa)
+// ------------------------------------------------------------------------------------------
+struct ActBuf {
+  void* hi;
+  void* lo;
+  int ld;  // elements
+};
+
+__device__ __forceinline__ float bf16_bits_to_float(uint16_t b) { return __uint_as_float(((uint32_t)b) << 16); }
+
+__device__ __forceinline__ uint16_t float_to_bf16_bits(float x) {
+  return __bfloat16_as_ushort(__float2bfloat16_rn(x));
+}
+
+// pack two floats into hi (and lo residual) bf16 pairs
+__device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t& lo) {
+  uint16_t ha = float_to_bf16_bits(a), hb = float_to_bf16_bits(b);
+  hi = (uint32_t)ha | ((uint32_t)hb << 16);
+  float ra = a - bf16_bits_to_float(ha), rb = b - bf16_bits_to_float(hb);
+  lo = (uint32_t)float_to_bf16_bits(ra) | ((uint32_t)float_to_bf16_bits(rb) << 16);
+}
+
+// store 8 consecutive columns (col % 8 == 0) of one row
+template <int PREC>
+__device__ __forceinline__ void act_store8(const ActBuf& b, size_t row, int col, const float* v) {
+  if (PREC == RN_PREC_FP32) {
+    float4* p = reinterpret_cast<float4*>(reinterpret_cast<float*>(b.hi) + row * b.ld + col);
+    p[0] = make_float4(v[0], v[1], v[2], v[3]);
+    p[1] = make_float4(v[4], v[5], v[6], v[7]);
+  } else {
+    uint32_t h[4], l[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) split2(v[2 * i], v[2 * i + 1], h[i], l[i]);
+    *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(b.hi) + row * b.ld + col) = make_uint4(h[0], h[1], h[2], h[3]);
+    if (PREC == RN_PREC_BF16X3)
+      *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(b.lo) + row * b.ld + col) = make_uint4(l[0], l[1], l[2], l[3]);
+  }
+}
+
+// load 8 consecutive columns of one row as floats (hi + lo)
+template <int PREC>
+__device__ __forceinline__ void act_load8(const ActBuf& b, size_t row, int col, float* v) {
+  if (PREC == RN_PREC_FP32) {
+    const float4* p = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(b.hi) + row * b.ld + col);
+    float4 a = p[0], c = p[1];
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = c.x; v[5] = c.y; v[6] = c.z; v[7] = c.w;
+  } else {
+    uint4 h = *reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(b.hi) + row * b.ld + col);
+    uint32_t hh[4] = {h.x, h.y, h.z, h.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      v[2 * i] = __uint_as_float(hh[i] << 16);
+      v[2 * i + 1] = __uint_as_float(hh[i] & 0xffff0000u);
+    }
+    if (PREC == RN_PREC_BF16X3) {
+      uint4 l = *reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(b.lo) + row * b.ld + col);
+      uint32_t ll[4] = {l.x, l.y, l.z, l.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        v[2 * i] += __uint_as_float(ll[i] << 16);
+        v[2 * i + 1] += __uint_as_float(ll[i] & 0xffff0000u);
+      }
+    }
+  }
+}
+
+// sign bits only (relu mask): positive iff hi > 0 (lo never flips the sign of a nonzero hi)
+template <int PREC>
+__device__ __forceinline__ void act_load8_hi(const ActBuf& b, size_t row, int col, float* v) {
+  if (PREC == RN_PREC_FP32) {
+    act_load8<RN_PREC_FP32>(b, row, col, v);
+  } else {
+    act_load8<RN_PREC_BF16>(b, row, col, v);
+  }
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(RN_FULL, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(RN_FULL, v, o));
+  return v;
+}
+// inclusive prefix sum across the warp
+__device__ __forceinline__ float warp_scan_incl(float v, int lane) {
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    float t = __shfl_up_sync(RN_FULL, v, o);
+    if (lane >= o) v += t;
+  }
+  return v;
+}
+
+__device__ __forceinline__ float softplus_f(float x) {
+  // torch.nn.functional.softplus, beta=1, threshold=20
+  return x > 20.f ? x : log1pf(expf(x));
+}
+__device__ __forceinline__ float sigmoid_f(float x) { return 1.f / (1.f + expf(-x)); }

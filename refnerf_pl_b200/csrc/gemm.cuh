@@ -1,0 +1,90 @@
+// GEMM building blocks of the NerfMLP chain: argument structs and launchers (definitions in
+// gemm_simt.cu and gemm_tc.cu).
+#pragma once
+#include "common.cuh"
+
+namespace rn {
+
+// Epilogue shared by the SIMT and tcgen05 kernels; applied to 8 consecutive columns of one row.
+struct GemmEpilogue {
+  const float* bias = nullptr;  // [n]
+  int relu = 0;
+  ActBuf mask = {nullptr, nullptr, 0};  // if set: v = (mask[row, col] > 0) ? v : 0   (ReLU backward)
+  ActBuf out = {nullptr, nullptr, 0};   // columns [0, out_cols) in activation format
+  int out_cols = 0;
+  float* f32 = nullptr;                 // columns [f32_col0, f32_col0 + f32_cols) -> f32[row*f32_ld + col - f32_col0]
+  int f32_ld = 0, f32_col0 = 0, f32_cols = 0, f32_accum = 0;
+};
+
+struct GemmArgs {
+  int prec = RN_PREC_FP32;
+  int impl = 0;        // 0 = tcgen05 (bf16 modes) / SIMT (fp32); 1 = force SIMT
+  int64_t m = 0;       // rows
+  int n = 0;           // output columns, multiple of 16, <= 256
+  ActBuf a1 = {nullptr, nullptr, 0};
+  int k1 = 0;          // multiple of 64
+  int a1_valid = 0;    // valid columns of a1 (columns beyond read as zero), multiple of 8
+  ActBuf a2 = {nullptr, nullptr, 0};
+  int k2 = 0, a2_valid = 0;
+  const void* b_hi = nullptr;  // weights [n, k1+k2] K-major in `prec` format
+  const void* b_lo = nullptr;
+  int b_ld = 0;
+  GemmEpilogue epi;
+};
+
+// dW[n0 + i, j] += sum_r dY[r, n0 + i] * X[r, j]   for i < 128, j < kx  (guards: n0+i < n_real, j < k_real)
+struct WgradArgs {
+  int prec = RN_PREC_FP32;
+  int impl = 0;
+  int64_t m = 0;
+  ActBuf dy = {nullptr, nullptr, 0};
+  int dy_valid = 0;   // valid columns of dy
+  int n0 = 0;         // first dy column of this 128-wide slab
+  int n_real = 0;     // rows of dW that exist
+  ActBuf x = {nullptr, nullptr, 0};
+  int x_valid = 0;
+  int kx = 0;         // multiple of 64, <= 256
+  int k_real = 0;
+  float* out = nullptr;  // dW (fp32), row-major [.., out_ld], element (n, j) at out[n*out_ld + j]
+  int out_ld = 0;
+};
+
+int launch_gemm(const GemmArgs& g, cudaStream_t st);
+int launch_wgrad(const WgradArgs& g, cudaStream_t st);
+
+int launch_gemm_simt(const GemmArgs& g, cudaStream_t st);
+int launch_wgrad_simt(const WgradArgs& g, cudaStream_t st);
+int launch_gemm_tc(const GemmArgs& g, cudaStream_t st);
+int launch_wgrad_tc(const WgradArgs& g, cudaStream_t st);
+
+// ---- epilogue device code (shared) ------------------------------------------------------------
+template <int PREC>
+__device__ __forceinline__ void epi_store8(const GemmEpilogue& e, size_t row, int col, float* v) {
+  if (e.bias) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] += e.bias[col + i];
+  }
+  if (e.relu) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i], 0.f);
+  }
+  if (e.mask.hi) {
+    float mk[8];
+    act_load8_hi<PREC>(e.mask, row, col, mk);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = mk[i] > 0.f ? v[i] : 0.f;
+  }
+  if (e.out.hi && col < e.out_cols) act_store8<PREC>(e.out, row, col, v);
+  if (e.f32 && col + 8 > e.f32_col0 && col < e.f32_col0 + e.f32_cols) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int c = col + i - e.f32_col0;
+      if (c >= 0 && c < e.f32_cols) {
+        float* p = e.f32 + row * e.f32_ld + c;
+        *p = e.f32_accum ? (*p + v[i]) : v[i];
+      }
+    }
+  }
+}
+
+}  // namespace rn

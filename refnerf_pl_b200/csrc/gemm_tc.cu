@@ -1,0 +1,510 @@
+// tcgen05 / TMEM / TMA GEMMs for sm_100a.
+//
+//   gemm_tc_kernel : C[128-row tile, n<=256] = A[., k] * B[n, k]^T, both operands K-major bf16 staged by
+//                    TMA (128B swizzle) into a multi-stage shared-memory ring; one elected thread issues
+//                    tcgen05.mma (kind::f16, M=128, N=n, K=16) into a double-buffered fp32 TMEM
+//                    accumulator; four epilogue warps drain TMEM with tcgen05.ld and apply
+//                    bias / ReLU / ReLU-mask / format conversion while the next tile's MMAs run.
+//                    SPLIT=3 issues hi*hi + lo*hi + hi*lo per K step (split-bf16, ~16-bit mantissa).
+//   wgrad_tc_kernel: dW[128 x kx] += dY^T X over a row range: both operands are MN-major views of the
+//                    row-major [rows, features] buffers (same TMA boxes, transposed descriptors), split
+//                    over rows across CTAs, reduced into fp32 with red.global.add.
+//
+// Persistent warp-specialised layout (256 threads): warp 0 TMA producer, warp 1 MMA issuer,
+// warp 2 TMEM allocator, warps 4-7 epilogue (warp%4 = TMEM lane quadrant).
+#include <cuda.h>
+
+#include "gemm.cuh"
+
+namespace rn {
+namespace {
+
+constexpr int kBM = 128;      // rows per tile (UMMA M)
+constexpr int kBK = 64;       // K elements per stage (= one 128B swizzle atom of bf16)
+constexpr int kUmmaK = 16;
+constexpr uint32_t kTmemCols = 512;
+constexpr int kSpinLimit = 1 << 22;   // bounded mbarrier spin: trap instead of hanging the GPU
+
+// ---------------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  for (int spin = 0; spin < kSpinLimit; ++spin) {
+    uint32_t done;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (done) return;
+  }
+  __trap();
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(cols));
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols));
+}
+// D[tmem] (+)= A[smem] * B[smem]
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accum)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// Shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout), 128B swizzle:
+//   [0,14) start>>4 | [16,30) LBO>>4 | [32,46) SBO>>4 | [46,48) version=1 | [61,64) layout=2 (SWIZZLE_128B)
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3fff);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3fff) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3fff) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// Instruction descriptor (cute::UMMA::InstrDescriptor): c=f32, a=b=bf16, M=128, N=n
+__device__ __forceinline__ uint32_t make_idesc(int n, int a_mn_major, int b_mn_major) {
+  uint32_t d = 0;
+  d |= 1u << 4;                       // c_format = F32
+  d |= 1u << 7;                       // a_format = BF16
+  d |= 1u << 10;                      // b_format = BF16
+  d |= (uint32_t)a_mn_major << 15;
+  d |= (uint32_t)b_mn_major << 16;
+  d |= (uint32_t)(n >> 3) << 17;
+  d |= (uint32_t)(kBM >> 4) << 24;
+  return d;
+}
+
+struct TcMaps {
+  CUtensorMap a1_hi, a1_lo, a2_hi, a2_lo, b_hi, b_lo;
+};
+
+template <int SPLIT>
+struct Cfg {
+  static constexpr int kPlanes = SPLIT == 3 ? 2 : 1;
+  static constexpr int kStages = SPLIT == 3 ? 2 : 4;
+  static constexpr int kABytes = kBM * kBK * 2;        // 16 KB
+  static constexpr int kBBytes = 256 * kBK * 2;        // 32 KB (n <= 256)
+  static constexpr int kStageBytes = kPlanes * (kABytes + kBBytes);
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+};
+
+// ---------------------------------------------------------------------------------------------
+// forward / dgrad GEMM
+// ---------------------------------------------------------------------------------------------
+template <int SPLIT>
+__global__ void __launch_bounds__(256, 1)
+gemm_tc_kernel(const __grid_constant__ TcMaps maps, int64_t m, int n, int kb1, int kb2, GemmEpilogue epi) {
+  using C = Cfg<SPLIT>;
+  constexpr int PREC = SPLIT == 3 ? RN_PREC_BF16X3 : RN_PREC_BF16;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::kStages * C::kStageBytes);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + C::kStages;
+  uint64_t* tfull = bars + 2 * C::kStages;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t num_tiles = (m + kBM - 1) / kBM;
+  const int kbt = kb1 + kb2;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&maps.a1_hi);
+    tma_prefetch_desc(&maps.b_hi);
+    for (int i = 0; i < C::kStages; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull[i], 1);
+      mbar_init(&tempty[i], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0 && lane == 0) {
+    // ===== TMA producer =====
+    const uint32_t stage_tx = (uint32_t)C::kPlanes * (uint32_t)(C::kABytes + n * kBK * 2);
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m0 = (int)(tile * kBM);
+      for (int kb = 0; kb < kbt; ++kb) {
+        mbar_wait(&empty[stage], phase ^ 1);
+        uint8_t* sbase = smem + stage * C::kStageBytes;
+        mbar_arrive_expect_tx(&full[stage], stage_tx);
+        const bool first = kb < kb1;
+        const int ka = (first ? kb : kb - kb1) * kBK;
+        tma_load_2d(sbase, first ? &maps.a1_hi : &maps.a2_hi, &full[stage], ka, m0);
+        tma_load_2d(sbase + C::kPlanes * C::kABytes, &maps.b_hi, &full[stage], kb * kBK, 0);
+        if (SPLIT == 3) {
+          tma_load_2d(sbase + C::kABytes, first ? &maps.a1_lo : &maps.a2_lo, &full[stage], ka, m0);
+          tma_load_2d(sbase + 2 * C::kABytes + C::kBBytes, &maps.b_lo, &full[stage], kb * kBK, 0);
+        }
+        if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ===== MMA issuer =====
+    const uint32_t idesc = make_idesc(n, 0, 0);
+    int stage = 0;
+    uint32_t phase = 0;
+    int buf = 0;
+    uint32_t tphase = 0;
+    for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      mbar_wait(&tempty[buf], tphase ^ 1);
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + (uint32_t)buf * 256u;
+      for (int kb = 0; kb < kbt; ++kb) {
+        mbar_wait(&full[stage], phase);
+        tc_fence_after();
+        const uint32_t sa_hi = smem_u32(smem + stage * C::kStageBytes);
+        const uint32_t sb_hi = sa_hi + C::kPlanes * C::kABytes;
+        const uint32_t sa_lo = sa_hi + C::kABytes;
+        const uint32_t sb_lo = sb_hi + C::kBBytes;
+#pragma unroll
+        for (int kk = 0; kk < kBK / kUmmaK; ++kk) {
+          const uint32_t koff = kk * kUmmaK * 2;  // bytes inside the 128B swizzle atom
+          const uint64_t da = make_desc(sa_hi + koff, 16, 1024);
+          const uint64_t db = make_desc(sb_hi + koff, 16, 1024);
+          umma_bf16(tmem_d, da, db, idesc, (kb | kk) ? 1u : 0u);
+          if (SPLIT == 3) {
+            const uint64_t dal = make_desc(sa_lo + koff, 16, 1024);
+            const uint64_t dbl = make_desc(sb_lo + koff, 16, 1024);
+            umma_bf16(tmem_d, dal, db, idesc, 1u);
+            umma_bf16(tmem_d, da, dbl, idesc, 1u);
+          }
+        }
+        umma_commit(&empty[stage]);  // frees the smem slot once the MMAs above have read it
+        if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+      }
+      umma_commit(&tfull[buf]);      // accumulator complete
+      if (++buf == 2) { buf = 0; tphase ^= 1; }
+    }
+  } else if (warp >= 4) {
+    // ===== epilogue =====
+    const int q = warp - 4;
+    int buf = 0;
+    uint32_t tphase = 0;
+    for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      mbar_wait(&tfull[buf], tphase);
+      tc_fence_after();
+      const int64_t row = tile * kBM + q * 32 + lane;
+      const uint32_t taddr = tmem_base + (uint32_t)buf * 256u + ((uint32_t)(q * 32) << 16);
+      for (int c0 = 0; c0 < n; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld32(taddr + (uint32_t)c0, r);
+        tmem_ld_wait();
+        if (row < m) {
+#pragma unroll
+          for (int g8 = 0; g8 < 4; ++g8) {
+            if (c0 + g8 * 8 < n) {
+              float v[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(r[g8 * 8 + e]);
+              epi_store8<PREC>(epi, (size_t)row, c0 + g8 * 8, v);
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[buf]);
+      if (++buf == 2) { buf = 0; tphase ^= 1; }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, kTmemCols);
+}
+
+// ---------------------------------------------------------------------------------------------
+// wgrad: dW[n0+i, j] += sum_r dY[r, n0+i] * X[r, j]
+// ---------------------------------------------------------------------------------------------
+struct WgMaps {
+  CUtensorMap dy_hi, dy_lo, x_hi, x_lo;
+};
+
+template <int SPLIT>
+__global__ void __launch_bounds__(256, 1)
+wgrad_tc_kernel(const __grid_constant__ WgMaps maps, int64_t m, int64_t rows_per_cta, int n0, int n_real, int kx,
+                int k_real, float* __restrict__ out, int out_ld) {
+  using C = Cfg<SPLIT>;
+  constexpr int kRowBlk = 64;                       // rows (reduction) per stage
+  constexpr int kBoxBytes = kRowBlk * 128;          // one [64 rows x 64 features] TMA box = 8 KB
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::kStages * C::kStageBytes);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + C::kStages;
+  uint64_t* tfull = bars + 2 * C::kStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tfull + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t r_begin = (int64_t)blockIdx.x * rows_per_cta;
+  const int64_t r_end = min(m, r_begin + rows_per_cta);
+  const int nblk = r_end > r_begin ? (int)((r_end - r_begin + kRowBlk - 1) / kRowBlk) : 0;
+  const int xboxes = kx / 64;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&maps.dy_hi);
+    tma_prefetch_desc(&maps.x_hi);
+    for (int i = 0; i < C::kStages; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    mbar_init(&tfull[0], 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, 256);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  if (nblk > 0) {
+    if (warp == 0 && lane == 0) {
+      const uint32_t stage_tx = (uint32_t)C::kPlanes * (uint32_t)(2 + xboxes) * kBoxBytes;
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int b = 0; b < nblk; ++b) {
+        mbar_wait(&empty[stage], phase ^ 1);
+        uint8_t* sbase = smem + stage * C::kStageBytes;
+        mbar_arrive_expect_tx(&full[stage], stage_tx);
+        const int r0 = (int)(r_begin + (int64_t)b * kRowBlk);
+        // layout per stage: dY_hi (2 boxes) | dY_lo | X_hi (4 boxes) | X_lo
+        for (int i = 0; i < 2; ++i) tma_load_2d(sbase + i * kBoxBytes, &maps.dy_hi, &full[stage], n0 + i * 64, r0);
+        for (int i = 0; i < xboxes; ++i)
+          tma_load_2d(sbase + C::kPlanes * C::kABytes + i * kBoxBytes, &maps.x_hi, &full[stage], i * 64, r0);
+        if (SPLIT == 3) {
+          for (int i = 0; i < 2; ++i)
+            tma_load_2d(sbase + C::kABytes + i * kBoxBytes, &maps.dy_lo, &full[stage], n0 + i * 64, r0);
+          for (int i = 0; i < xboxes; ++i)
+            tma_load_2d(sbase + 2 * C::kABytes + C::kBBytes + i * kBoxBytes, &maps.x_lo, &full[stage], i * 64, r0);
+        }
+        if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+      }
+    } else if (warp == 1 && lane == 0) {
+      const uint32_t idesc = make_idesc(kx, 1, 1);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int b = 0; b < nblk; ++b) {
+        mbar_wait(&full[stage], phase);
+        tc_fence_after();
+        const uint32_t sa_hi = smem_u32(smem + stage * C::kStageBytes);
+        const uint32_t sb_hi = sa_hi + C::kPlanes * C::kABytes;
+        const uint32_t sa_lo = sa_hi + C::kABytes;
+        const uint32_t sb_lo = sb_hi + C::kBBytes;
+#pragma unroll
+        for (int kk = 0; kk < kRowBlk / kUmmaK; ++kk) {
+          const uint32_t koff = kk * kUmmaK * 128;  // 16 rows of 128 B
+          // MN-major, 128B swizzle: LBO = stride between 64-feature blocks, SBO = stride between 8-row groups
+          const uint64_t da = make_desc(sa_hi + koff, kBoxBytes, 1024);
+          const uint64_t db = make_desc(sb_hi + koff, kBoxBytes, 1024);
+          umma_bf16(tmem_base, da, db, idesc, (b | kk) ? 1u : 0u);
+          if (SPLIT == 3) {
+            const uint64_t dal = make_desc(sa_lo + koff, kBoxBytes, 1024);
+            const uint64_t dbl = make_desc(sb_lo + koff, kBoxBytes, 1024);
+            umma_bf16(tmem_base, dal, db, idesc, 1u);
+            umma_bf16(tmem_base, da, dbl, idesc, 1u);
+          }
+        }
+        umma_commit(&empty[stage]);
+        if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+      }
+      umma_commit(&tfull[0]);
+    } else if (warp >= 4) {
+      const int q = warp - 4;
+      mbar_wait(&tfull[0], 0);
+      tc_fence_after();
+      const int nrow = n0 + q * 32 + lane;
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
+      for (int c0 = 0; c0 < kx; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld32(taddr + (uint32_t)c0, r);
+        tmem_ld_wait();
+        if (nrow < n_real) {
+#pragma unroll
+          for (int e = 0; e < 32; ++e) {
+            const int j = c0 + e;
+            if (j < k_real) atomicAdd(out + (size_t)nrow * out_ld + j, __uint_as_float(r[e]));
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, 256);
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side: tensor maps + launches
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// 2-D bf16 row-major [rows, valid_cols] with row pitch ld elements; box = [box_rows, 64 cols], 128B swizzle
+int make_map(CUtensorMap* map, const void* base, int64_t rows, int valid_cols, int ld, int box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return rn_set_error(RN_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
+  if (!base) {  // unused operand: still needs a valid descriptor object; alias is never dereferenced
+    memset(map, 0, sizeof(*map));
+    return RN_OK;
+  }
+  cuuint64_t dims[2] = {(cuuint64_t)valid_cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return rn_set_error(RN_ERR_CUDA, "cuTensorMapEncodeTiled failed");
+  return RN_OK;
+}
+
+int num_sms() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+template <typename K>
+int set_smem(K kernel, int bytes) {
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e != cudaSuccess) return rn_set_cuda_error(e, __FILE__, __LINE__);
+  return RN_OK;
+}
+
+}  // namespace
+
+int launch_gemm_tc(const GemmArgs& g, cudaStream_t st) {
+  if (g.m <= 0) return RN_OK;
+  if (g.prec != RN_PREC_BF16 && g.prec != RN_PREC_BF16X3) return rn_set_error(RN_ERR_ARG, "gemm_tc: bf16 modes only");
+  const bool x3 = g.prec == RN_PREC_BF16X3;
+  TcMaps maps;
+  int rc;
+  if ((rc = make_map(&maps.a1_hi, g.a1.hi, g.m, g.a1_valid, g.a1.ld, kBM))) return rc;
+  if ((rc = make_map(&maps.a1_lo, x3 ? g.a1.lo : nullptr, g.m, g.a1_valid, g.a1.ld, kBM))) return rc;
+  if ((rc = make_map(&maps.a2_hi, g.k2 ? g.a2.hi : nullptr, g.m, g.a2_valid, g.a2.ld, kBM))) return rc;
+  if ((rc = make_map(&maps.a2_lo, (x3 && g.k2) ? g.a2.lo : nullptr, g.m, g.a2_valid, g.a2.ld, kBM))) return rc;
+  if ((rc = make_map(&maps.b_hi, g.b_hi, g.n, g.k1 + g.k2, g.b_ld, g.n))) return rc;
+  if ((rc = make_map(&maps.b_lo, x3 ? g.b_lo : nullptr, g.n, g.k1 + g.k2, g.b_ld, g.n))) return rc;
+  const int64_t tiles = (g.m + kBM - 1) / kBM;
+  const unsigned grid = (unsigned)(tiles < num_sms() ? tiles : num_sms());
+  if (x3) {
+    static bool once = false;
+    if (!once) { if ((rc = set_smem(gemm_tc_kernel<3>, Cfg<3>::kSmemBytes))) return rc; once = true; }
+    gemm_tc_kernel<3><<<grid, 256, Cfg<3>::kSmemBytes, st>>>(maps, g.m, g.n, g.k1 / kBK, g.k2 / kBK, g.epi);
+  } else {
+    static bool once = false;
+    if (!once) { if ((rc = set_smem(gemm_tc_kernel<1>, Cfg<1>::kSmemBytes))) return rc; once = true; }
+    gemm_tc_kernel<1><<<grid, 256, Cfg<1>::kSmemBytes, st>>>(maps, g.m, g.n, g.k1 / kBK, g.k2 / kBK, g.epi);
+  }
+  RN_CUDA_CHECK_LAUNCH();
+  return RN_OK;
+}
+
+int launch_wgrad_tc(const WgradArgs& g, cudaStream_t st) {
+  if (g.m <= 0) return RN_OK;
+  if (g.prec != RN_PREC_BF16 && g.prec != RN_PREC_BF16X3) return rn_set_error(RN_ERR_ARG, "wgrad_tc: bf16 modes only");
+  const bool x3 = g.prec == RN_PREC_BF16X3;
+  WgMaps maps;
+  int rc;
+  if ((rc = make_map(&maps.dy_hi, g.dy.hi, g.m, g.dy_valid, g.dy.ld, 64))) return rc;
+  if ((rc = make_map(&maps.dy_lo, x3 ? g.dy.lo : nullptr, g.m, g.dy_valid, g.dy.ld, 64))) return rc;
+  if ((rc = make_map(&maps.x_hi, g.x.hi, g.m, g.x_valid, g.x.ld, 64))) return rc;
+  if ((rc = make_map(&maps.x_lo, x3 ? g.x.lo : nullptr, g.m, g.x_valid, g.x.ld, 64))) return rc;
+  int ctas = num_sms();
+  int64_t blocks64 = (g.m + 63) / 64;
+  if (ctas > blocks64) ctas = (int)blocks64;
+  int64_t rows_per = ((blocks64 + ctas - 1) / ctas) * 64;
+  const unsigned grid = (unsigned)((g.m + rows_per - 1) / rows_per);
+  if (x3) {
+    static bool once = false;
+    if (!once) { if ((rc = set_smem(wgrad_tc_kernel<3>, Cfg<3>::kSmemBytes))) return rc; once = true; }
+    wgrad_tc_kernel<3><<<grid, 256, Cfg<3>::kSmemBytes, st>>>(maps, g.m, rows_per, g.n0, g.n_real, g.kx, g.k_real, g.out, g.out_ld);
+  } else {
+    static bool once = false;
+    if (!once) { if ((rc = set_smem(wgrad_tc_kernel<1>, Cfg<1>::kSmemBytes))) return rc; once = true; }
+    wgrad_tc_kernel<1><<<grid, 256, Cfg<1>::kSmemBytes, st>>>(maps, g.m, rows_per, g.n0, g.n_real, g.kx, g.k_real, g.out, g.out_ld);
+  }
+  RN_CUDA_CHECK_LAUNCH();
+  return RN_OK;
+}
+
+}  // namespace rn

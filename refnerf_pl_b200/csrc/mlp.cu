@@ -1,0 +1,574 @@
+// Host-side sequencing of the NerfMLP level pass (models.py:533-750) over row chunks, and the C ABI.
+// No allocation, no host synchronisation: everything is enqueued on the caller's stream and all
+// scratch comes from the caller-provided workspace.
+#include <stdio.h>
+#include <string.h>
+
+#include "gemm.cuh"
+#include "layers.h"
+#include "pointwise.cuh"
+
+static thread_local char g_err[512] = "";
+
+int rn_set_error(int code, const char* msg) {
+  snprintf(g_err, sizeof(g_err), "%s", msg);
+  return code;
+}
+int rn_set_cuda_error(cudaError_t e, const char* file, int line) {
+  snprintf(g_err, sizeof(g_err), "CUDA error %d (%s) at %s:%d", (int)e, cudaGetErrorString(e), file, line);
+  return RN_ERR_CUDA;
+}
+
+namespace rn {
+namespace {
+
+#define RN_TRY(expr)            \
+  do {                          \
+    int rc__ = (expr);          \
+    if (rc__ != RN_OK) return rc__; \
+  } while (0)
+
+const char* kParamNames[RN_MLP_NUM_PARAMS] = {
+    "spatial_net.0.weight", "spatial_net.0.bias", "spatial_net.1.weight", "spatial_net.1.bias",
+    "spatial_net.2.weight", "spatial_net.2.bias", "spatial_net.3.weight", "spatial_net.3.bias",
+    "spatial_net.4.weight", "spatial_net.4.bias", "spatial_net.5.weight", "spatial_net.5.bias",
+    "spatial_net.6.weight", "spatial_net.6.bias", "spatial_net.7.weight", "spatial_net.7.bias",
+    "raw_density.weight", "raw_density.bias", "grad_pred.weight", "grad_pred.bias",
+    "raw_roughness.weight", "raw_roughness.bias", "raw_rgb_diffuse.weight", "raw_rgb_diffuse.bias",
+    "raw_tint.weight", "raw_tint.bias", "bottleneck.weight", "bottleneck.bias",
+    "viewdir_mlp.0.weight", "viewdir_mlp.0.bias", "viewdir_mlp.1.weight", "viewdir_mlp.1.bias",
+    "viewdir_mlp.2.weight", "viewdir_mlp.2.bias", "viewdir_mlp.3.weight", "viewdir_mlp.3.bias",
+    "viewdir_mlp.4.weight", "viewdir_mlp.4.bias", "viewdir_mlp.5.weight", "viewdir_mlp.5.bias",
+    "viewdir_mlp.6.weight", "viewdir_mlp.6.bias", "viewdir_mlp.7.weight", "viewdir_mlp.7.bias",
+    "rgb.weight", "rgb.bias"};
+
+// head rows inside the packed H layer: {param index of weight, first packed row, rows}
+struct HeadSeg { int param, row0, rows; };
+const HeadSeg kHeadSegs[6] = {{kParamBottleneck, 0, 128}, {kParamDensity, 128, 1},  {kParamGradPred, 129, 3},
+                              {kParamRoughness, 132, 1},  {kParamDiffuse, 133, 3}, {kParamTint, 136, 3}};
+
+int layer_param(int l) {  // weight param index of a non-head layer
+  if (l < 8) return 2 * l;
+  if (l >= kLayerV0 && l < kLayerC) return kParamView0 + 2 * (l - kLayerV0);
+  return kParamRgb;
+}
+
+int64_t param_numel(int i) {
+  const bool is_bias = i & 1;
+  const int w = i & ~1;
+  int n, k;
+  if (w < 16) { LayerDef d = layer_def(w / 2); n = d.n_real; k = d.k1_real + d.k2_real; }
+  else if (w == kParamDensity || w == kParamRoughness) { n = 1; k = 256; }
+  else if (w == kParamGradPred || w == kParamDiffuse || w == kParamTint) { n = 3; k = 256; }
+  else if (w == kParamBottleneck) { n = 128; k = 256; }
+  else if (w < kParamRgb) { LayerDef d = layer_def(kLayerV0 + (w - kParamView0) / 2); n = d.n_real; k = d.k1_real + d.k2_real; }
+  else { n = 3; k = 256; }
+  return is_bias ? n : (int64_t)n * k;
+}
+
+struct Carver {
+  uint8_t* base;
+  size_t off = 0;
+  void* take(size_t bytes) {
+    void* p = base ? base + off : nullptr;
+    off += align256(bytes);
+    return p;
+  }
+  ActBuf act(int prec, int64_t rows, int ld) {
+    ActBuf b;
+    b.ld = ld;
+    b.hi = take((size_t)rows * ld * elem_bytes(prec));
+    b.lo = prec == RN_PREC_BF16X3 ? take((size_t)rows * ld * 2) : nullptr;
+    return b;
+  }
+};
+
+struct Workspace {
+  ActBuf x0, v0, sp[8], vw[8], g[2], d_bott, d_scal, d_rgb_raw;
+  float *heads_raw, *rgb_raw, *gx0, *dv0f, *dcolor;
+  float* gW[kNumLayers];
+  float* gB[kNumLayers];
+  int nsp, nvw;
+  size_t bytes;
+  ActBuf& a(int i) { return sp[(i - 1) % nsp]; }   // spatial activation a_i = relu(y_{i-1}), i = 1..8
+  ActBuf& b(int i) { return vw[(i - 1) % nvw]; }   // view activation
+};
+
+// mode 0: eval forward, 1: training forward (+normals pass), 2: backward
+Workspace carve(void* base, int prec, int64_t rc, int mode) {
+  Workspace w;
+  Carver c{reinterpret_cast<uint8_t*>(base)};
+  w.nsp = mode == 0 ? 2 : 8;
+  w.nvw = mode == 2 ? 8 : 2;
+  w.x0 = c.act(prec, rc, kEncPad);
+  w.v0 = c.act(prec, rc, kViewPad);
+  for (int i = 0; i < w.nsp; ++i) w.sp[i] = c.act(prec, rc, 256);
+  for (int i = 0; i < w.nvw; ++i) w.vw[i] = c.act(prec, rc, 256);
+  w.heads_raw = (float*)c.take((size_t)rc * 16 * 4);
+  w.rgb_raw = (float*)c.take((size_t)rc * 4 * 4);
+  if (mode >= 1) {
+    w.g[0] = c.act(prec, rc, 256);
+    w.g[1] = c.act(prec, rc, 256);
+    w.gx0 = (float*)c.take((size_t)rc * 128 * 4);
+  }
+  if (mode == 2) {
+    w.dv0f = (float*)c.take((size_t)rc * 256 * 4);
+    w.dcolor = (float*)c.take((size_t)rc * 8 * 4);
+    w.d_bott = c.act(prec, rc, 128);
+    w.d_scal = c.act(prec, rc, 16);
+    w.d_rgb_raw = c.act(prec, rc, 16);
+    for (int l = 0; l < kNumLayers; ++l) {
+      LayerDef d = layer_def(l);
+      w.gW[l] = (float*)c.take((size_t)d.n_pad * d.k_tot() * 4);
+      w.gB[l] = (float*)c.take((size_t)d.n_pad * 4);
+    }
+  }
+  w.bytes = c.off;
+  return w;
+}
+
+struct Packed {
+  const uint8_t* base;
+  PackedLayout lay;
+  int prec;
+  const void* wf_hi(int l) const { return base + lay.wf[l]; }
+  const void* wf_lo(int l) const { return prec == RN_PREC_BF16X3 ? base + lay.wf[l] + lay.wf_plane[l] : nullptr; }
+  // transposed operand, starting at row `row` (rows are input features)
+  const void* wt_hi(int l, int row) const {
+    return base + lay.wt[l] + (size_t)row * layer_def(l).nt_pad * elem_bytes(prec);
+  }
+  const void* wt_lo(int l, int row) const {
+    return prec == RN_PREC_BF16X3 ? base + lay.wt[l] + lay.wt_plane[l] + (size_t)row * layer_def(l).nt_pad * 2 : nullptr;
+  }
+  const float* bias(int l) const { return reinterpret_cast<const float*>(base + lay.bias[l]); }
+  const float* wd() const { return reinterpret_cast<const float*>(base + lay.wd); }
+};
+
+struct Ctx {
+  const RnMlpConfig* cfg;
+  Packed pk;
+  const float *tdist, *origins, *dirs, *viewdirs, *radii;
+  int s;
+  cudaStream_t st;
+  MlpScalars sc;
+  int impl;
+};
+
+// y = act(W x + b) for chain layer l; input a1 (+ skip input a2)
+int fwd_layer(const Ctx& c, int l, int64_t rows, ActBuf a1, ActBuf a2, GemmEpilogue epi) {
+  LayerDef d = layer_def(l);
+  GemmArgs g;
+  g.prec = c.cfg->prec;
+  g.impl = c.impl;
+  g.m = rows;
+  g.n = d.n_pad;
+  g.a1 = a1; g.k1 = d.k1_pad; g.a1_valid = d.k1_pad;
+  g.a2 = a2; g.k2 = d.k2_pad; g.a2_valid = d.k2_pad;
+  g.b_hi = c.pk.wf_hi(l); g.b_lo = c.pk.wf_lo(l); g.b_ld = d.k_tot();
+  epi.bias = c.pk.bias(l);
+  g.epi = epi;
+  return launch_gemm(g, c.st);
+}
+
+// dX[:, row0 : row0+n] = dY W[:, row0 : row0+n]  (dY given as up to two K sources)
+int dgrad_layer(const Ctx& c, int l, int64_t rows, ActBuf dy1, int k1, int dy1_valid, ActBuf dy2, int k2, int dy2_valid,
+                int in_row0, int n, GemmEpilogue epi) {
+  GemmArgs g;
+  g.prec = c.cfg->prec;
+  g.impl = c.impl;
+  g.m = rows;
+  g.n = n;
+  g.a1 = dy1; g.k1 = k1; g.a1_valid = dy1_valid;
+  g.a2 = dy2; g.k2 = k2; g.a2_valid = dy2_valid;
+  g.b_hi = c.pk.wt_hi(l, in_row0); g.b_lo = c.pk.wt_lo(l, in_row0); g.b_ld = layer_def(l).nt_pad;
+  g.epi = epi;
+  return launch_gemm(g, c.st);
+}
+
+GemmEpilogue epi_act(ActBuf out, int cols, int relu) {
+  GemmEpilogue e;
+  e.out = out; e.out_cols = cols; e.relu = relu;
+  return e;
+}
+GemmEpilogue epi_masked(ActBuf out, ActBuf mask) {
+  GemmEpilogue e;
+  e.out = out; e.out_cols = 256; e.mask = mask;
+  return e;
+}
+GemmEpilogue epi_f32(float* p, int ld, int cols, int accum) {
+  GemmEpilogue e;
+  e.f32 = p; e.f32_ld = ld; e.f32_col0 = 0; e.f32_cols = cols; e.f32_accum = accum;
+  return e;
+}
+
+// forward for one chunk; normals_out != nullptr runs the in-forward density-gradient pass
+int forward_chunk(const Ctx& c, Workspace& w, int64_t row0, int64_t rows, const RnMlpOutputs& o, bool want_normals,
+                  bool write_outputs) {
+  const int prec = c.cfg->prec;
+  const ActBuf none = {nullptr, nullptr, 0};
+  RN_TRY(launch_encode(prec, c.tdist, c.origins, c.dirs, c.radii, c.s, row0, rows, w.x0, kEncPad, c.st));
+  for (int l = 0; l < 8; ++l)
+    RN_TRY(fwd_layer(c, l, rows, l == 0 ? w.x0 : w.a(l), l == 5 ? w.x0 : none, epi_act(w.a(l + 1), 256, 1)));
+  {
+    GemmEpilogue e = epi_act(w.v0, kBottleneck, 0);
+    e.f32 = w.heads_raw; e.f32_ld = 16; e.f32_col0 = kBottleneck; e.f32_cols = 16;
+    RN_TRY(fwd_layer(c, kLayerH, rows, w.a(8), none, e));
+  }
+  if (want_normals) {
+    // d raw_density / d x0 through the spatial net (models.py:603-609); result is a constant
+    RN_TRY(launch_density_grad_seed(prec, w.a(8), c.pk.wd(), w.g[0], rows, c.st));
+    int cur = 0;
+    for (int l = 7; l >= 1; --l) {
+      if (l == 5)
+        RN_TRY(dgrad_layer(c, l, rows, w.g[cur], 256, 256, none, 0, 0, 256, kEncPad, epi_f32(w.gx0, 128, 128, 0)));
+      RN_TRY(dgrad_layer(c, l, rows, w.g[cur], 256, 256, none, 0, 0, 0, 256, epi_masked(w.g[cur ^ 1], w.a(l))));
+      cur ^= 1;
+    }
+    RN_TRY(dgrad_layer(c, 0, rows, w.g[cur], 256, 256, none, 0, 0, 0, kEncPad, epi_f32(w.gx0, 128, 128, 1)));
+    RN_TRY(launch_ipe_grad_normals(w.gx0, 128, c.tdist, c.origins, c.dirs, c.radii, c.s, row0, rows,
+                                   o.normals + row0 * 3, c.st));
+  }
+  // outputs of the heads are written even in the recompute pass (cheap); callers pass scratch or real outputs
+  RN_TRY(launch_heads_prologue_fwd(prec, w.heads_raw, c.viewdirs, c.s, row0, rows, c.sc, w.v0, o.density + row0,
+                                   o.normals_pred + row0 * 3, o.grad_pred + row0 * 3, o.roughness + row0,
+                                   o.tint + row0 * 3, c.st));
+  for (int l = 0; l < 8; ++l)
+    RN_TRY(fwd_layer(c, kLayerV0 + l, rows, l == 0 ? w.v0 : w.b(l), l == 5 ? w.v0 : none, epi_act(w.b(l + 1), 256, 1)));
+  RN_TRY(fwd_layer(c, kLayerC, rows, w.b(8), none, epi_f32(w.rgb_raw, 4, 4, 0)));
+  if (write_outputs)
+    RN_TRY(launch_color_fwd(w.rgb_raw, w.heads_raw, rows, c.sc, o.rgb + row0 * 3, o.diffuse + row0 * 3,
+                            o.specular + row0 * 3, c.st));
+  return RN_OK;
+}
+
+int wgrad_layer(const Ctx& c, Workspace& w, int l, int64_t rows, ActBuf dy, int dy_valid, int n_real_total, ActBuf x1,
+                ActBuf x2) {
+  LayerDef d = layer_def(l);
+  for (int n0 = 0; n0 < n_real_total; n0 += 128) {
+    WgradArgs g;
+    g.prec = c.cfg->prec;
+    g.impl = c.impl;
+    g.m = rows;
+    g.dy = dy; g.dy_valid = dy_valid; g.n0 = n0; g.n_real = n_real_total;
+    g.x = x1; g.x_valid = d.k1_pad; g.kx = d.k1_pad; g.k_real = d.k1_real;
+    g.out = w.gW[l]; g.out_ld = d.k_tot();
+    RN_TRY(launch_wgrad(g, c.st));
+    if (d.k2_pad) {
+      g.x = x2; g.x_valid = d.k2_pad; g.kx = d.k2_pad; g.k_real = d.k2_real;
+      g.out = w.gW[l] + d.k1_pad;
+      RN_TRY(launch_wgrad(g, c.st));
+    }
+  }
+  return RN_OK;
+}
+
+int backward_chunk(const Ctx& c, Workspace& w, int64_t row0, int64_t rows, const RnMlpOutputs& g) {
+  const int prec = c.cfg->prec;
+  const ActBuf none = {nullptr, nullptr, 0};
+  auto off = [&](const float* p, int per) -> const float* { return p ? p + row0 * per : nullptr; };
+  RN_TRY(launch_color_bwd(prec, w.rgb_raw, w.heads_raw, rows, c.sc, off(g.rgb, 3), off(g.diffuse, 3), off(g.specular, 3),
+                          w.d_rgb_raw, w.dcolor, c.st));
+  // rgb head
+  RN_TRY(wgrad_layer(c, w, kLayerC, rows, w.d_rgb_raw, 16, 3, w.b(8), none));
+  RN_TRY(launch_colsum(prec, w.d_rgb_raw, rows, 16, w.gB[kLayerC], c.st));
+  RN_TRY(dgrad_layer(c, kLayerC, rows, w.d_rgb_raw, 64, 16, none, 0, 0, 0, 256, epi_masked(w.g[0], w.b(8))));
+  int cur = 0;
+  for (int l = 7; l >= 0; --l) {
+    const int L = kLayerV0 + l;
+    RN_TRY(wgrad_layer(c, w, L, rows, w.g[cur], 256, 256, l == 0 ? w.v0 : w.b(l), l == 5 ? w.v0 : none));
+    RN_TRY(launch_colsum(prec, w.g[cur], rows, 256, w.gB[L], c.st));
+    if (l == 5) RN_TRY(dgrad_layer(c, L, rows, w.g[cur], 256, 256, none, 0, 0, 256, 256, epi_f32(w.dv0f, 256, 256, 0)));
+    if (l > 0) {
+      RN_TRY(dgrad_layer(c, L, rows, w.g[cur], 256, 256, none, 0, 0, 0, 256, epi_masked(w.g[cur ^ 1], w.b(l))));
+      cur ^= 1;
+    } else {
+      RN_TRY(dgrad_layer(c, L, rows, w.g[cur], 256, 256, none, 0, 0, 0, 256, epi_f32(w.dv0f, 256, 256, 1)));
+    }
+  }
+  RN_TRY(launch_f32_to_act(prec, w.dv0f, 256, 0, rows, 128, w.d_bott, c.st));
+  RN_TRY(launch_heads_prologue_bwd(prec, w.heads_raw, c.viewdirs, c.s, row0, rows, c.sc, w.dv0f, w.dcolor,
+                                   off(g.density, 1), off(g.normals_pred, 3), off(g.grad_pred, 3), off(g.roughness, 1),
+                                   off(g.tint, 3), w.d_scal, c.st));
+  // heads
+  {
+    LayerDef d = layer_def(kLayerH);
+    WgradArgs a;
+    a.prec = prec; a.impl = c.impl; a.m = rows;
+    a.x = w.a(8); a.x_valid = 256; a.kx = 256; a.k_real = 256; a.out_ld = d.k_tot();
+    a.dy = w.d_bott; a.dy_valid = 128; a.n0 = 0; a.n_real = 128; a.out = w.gW[kLayerH];
+    RN_TRY(launch_wgrad(a, c.st));
+    a.dy = w.d_scal; a.dy_valid = 16; a.n0 = 0; a.n_real = kHeadScalars; a.out = w.gW[kLayerH] + (size_t)128 * d.k_tot();
+    RN_TRY(launch_wgrad(a, c.st));
+    RN_TRY(launch_colsum(prec, w.d_bott, rows, 128, w.gB[kLayerH], c.st));
+    RN_TRY(launch_colsum(prec, w.d_scal, rows, 16, w.gB[kLayerH] + 128, c.st));
+    RN_TRY(dgrad_layer(c, kLayerH, rows, w.d_bott, 128, 128, w.d_scal, 64, 16, 0, 256, epi_masked(w.g[0], w.a(8))));
+  }
+  cur = 0;
+  for (int l = 7; l >= 0; --l) {
+    RN_TRY(wgrad_layer(c, w, l, rows, w.g[cur], 256, 256, l == 0 ? w.x0 : w.a(l), l == 5 ? w.x0 : none));
+    RN_TRY(launch_colsum(prec, w.g[cur], rows, 256, w.gB[l], c.st));
+    if (l > 0) {
+      RN_TRY(dgrad_layer(c, l, rows, w.g[cur], 256, 256, none, 0, 0, 0, 256, epi_masked(w.g[cur ^ 1], w.a(l))));
+      cur ^= 1;
+    }
+  }
+  return RN_OK;
+}
+
+int make_ctx(Ctx& c, const RnMlpConfig* cfg, const void* packed, const float* tdist, const float* origins,
+             const float* dirs, const float* viewdirs, const float* radii, int s, void* stream) {
+  if (!cfg || !packed) return rn_set_error(RN_ERR_ARG, "rn_mlp: null config / packed weights");
+  if (cfg->prec < 0 || cfg->prec > 2) return rn_set_error(RN_ERR_ARG, "rn_mlp: bad precision");
+  if (cfg->chunk_rows <= 0 || cfg->chunk_rows % 128) return rn_set_error(RN_ERR_ARG, "rn_mlp: chunk_rows must be a positive multiple of 128");
+  if (s < 1) return rn_set_error(RN_ERR_ARG, "rn_mlp: bad sample count");
+  c.cfg = cfg;
+  c.pk.base = reinterpret_cast<const uint8_t*>(packed);
+  c.pk.lay = packed_layout(cfg->prec);
+  c.pk.prec = cfg->prec;
+  c.tdist = tdist; c.origins = origins; c.dirs = dirs; c.viewdirs = viewdirs; c.radii = radii;
+  c.s = s;
+  c.st = (cudaStream_t)stream;
+  c.sc = {cfg->srgb_mapping, cfg->srgb_normalization, cfg->density_bias, cfg->roughness_bias,
+          cfg->rgb_premultiplier, cfg->rgb_bias, cfg->rgb_padding};
+  c.impl = cfg->gemm_impl;
+  return RN_OK;
+}
+
+}  // namespace
+}  // namespace rn
+
+using namespace rn;
+
+extern "C" const char* rn_last_error(void) { return g_err; }
+extern "C" int rn_abi_version(void) { return 1; }
+extern "C" const char* rn_mlp_param_name(int i) { return (i >= 0 && i < RN_MLP_NUM_PARAMS) ? kParamNames[i] : nullptr; }
+extern "C" int64_t rn_mlp_param_numel(int i) { return (i >= 0 && i < RN_MLP_NUM_PARAMS) ? param_numel(i) : -1; }
+
+extern "C" size_t rn_mlp_packed_bytes(int prec) {
+  if (prec < 0 || prec > 2) return 0;
+  return packed_layout(prec).total;
+}
+
+extern "C" size_t rn_mlp_workspace_bytes(const RnMlpConfig* cfg, int training) {
+  if (!cfg || cfg->chunk_rows <= 0) return 0;
+  size_t b = carve(nullptr, cfg->prec, cfg->chunk_rows, training ? 2 : 0).bytes;
+  if (training) {
+    size_t b1 = carve(nullptr, cfg->prec, cfg->chunk_rows, 1).bytes;
+    if (b1 > b) b = b1;
+    b += (size_t)cfg->chunk_rows * 16 * 4;  // scratch head outputs of the recompute pass
+  }
+  return b;
+}
+
+extern "C" int rn_mlp_pack(const float* const* params, void* packed, int prec, void* stream) {
+  if (!params || !packed || prec < 0 || prec > 2) return rn_set_error(RN_ERR_ARG, "rn_mlp_pack: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  PackedLayout lay = packed_layout(prec);
+  uint8_t* base = reinterpret_cast<uint8_t*>(packed);
+  cudaError_t e = cudaMemsetAsync(packed, 0, lay.total, st);
+  if (e != cudaSuccess) return rn_set_cuda_error(e, __FILE__, __LINE__);
+  for (int l = 0; l < kNumLayers; ++l) {
+    LayerDef d = layer_def(l);
+    void* wf_hi = base + lay.wf[l];
+    void* wf_lo = base + lay.wf[l] + lay.wf_plane[l];
+    void* wt_hi = base + lay.wt[l];
+    void* wt_lo = base + lay.wt[l] + lay.wt_plane[l];
+    float* bias = reinterpret_cast<float*>(base + lay.bias[l]);
+    if (l == kLayerH) {
+      for (const HeadSeg& hs : kHeadSegs) {
+        RN_TRY(launch_pack_segment(prec, params[hs.param], 256, hs.rows, 256, 0, wf_hi, wf_lo, d.k_tot(), hs.row0, 0, st));
+        RN_TRY(launch_pack_segment(prec, params[hs.param], 256, hs.rows, 256, 1, wt_hi, wt_lo, d.nt_pad, 0, hs.row0, st));
+        e = cudaMemcpyAsync(bias + hs.row0, params[hs.param + 1], hs.rows * 4, cudaMemcpyDeviceToDevice, st);
+        if (e != cudaSuccess) return rn_set_cuda_error(e, __FILE__, __LINE__);
+      }
+      continue;
+    }
+    const int pi = layer_param(l);
+    const int kr = d.k1_real + d.k2_real;
+    RN_TRY(launch_pack_segment(prec, params[pi], kr, d.n_real, d.k1_real, 0, wf_hi, wf_lo, d.k_tot(), 0, 0, st));
+    RN_TRY(launch_pack_segment(prec, params[pi], kr, d.n_real, d.k1_real, 1, wt_hi, wt_lo, d.nt_pad, 0, 0, st));
+    if (d.k2_pad) {
+      RN_TRY(launch_pack_segment(prec, params[pi] + d.k1_real, kr, d.n_real, d.k2_real, 0, wf_hi, wf_lo, d.k_tot(), 0, d.k1_pad, st));
+      RN_TRY(launch_pack_segment(prec, params[pi] + d.k1_real, kr, d.n_real, d.k2_real, 1, wt_hi, wt_lo, d.nt_pad, d.k1_pad, 0, st));
+    }
+    e = cudaMemcpyAsync(bias, params[pi + 1], d.n_real * 4, cudaMemcpyDeviceToDevice, st);
+    if (e != cudaSuccess) return rn_set_cuda_error(e, __FILE__, __LINE__);
+  }
+  e = cudaMemcpyAsync(base + lay.wd, params[kParamDensity], 256 * 4, cudaMemcpyDeviceToDevice, st);
+  if (e != cudaSuccess) return rn_set_cuda_error(e, __FILE__, __LINE__);
+  return RN_OK;
+}
+
+extern "C" int rn_mlp_forward(const RnMlpConfig* cfg, const void* packed, const float* tdist, const float* origins,
+                              const float* dirs, const float* viewdirs, const float* radii, int64_t n_rays, int s,
+                              const RnMlpOutputs* out, void* workspace, size_t workspace_bytes, void* stream) {
+  Ctx c;
+  RN_TRY(make_ctx(c, cfg, packed, tdist, origins, dirs, viewdirs, radii, s, stream));
+  if (!out || !out->density || !out->rgb || !out->normals_pred || !out->grad_pred || !out->tint || !out->diffuse ||
+      !out->specular || !out->roughness)
+    return rn_set_error(RN_ERR_ARG, "rn_mlp_forward: missing output buffers");
+  const bool want_normals = out->normals != nullptr;
+  const int64_t rows_total = n_rays * s;
+  const int64_t rc = cfg->chunk_rows;
+  Workspace w = carve(workspace, cfg->prec, rc, want_normals ? 1 : 0);
+  if (w.bytes > workspace_bytes) return rn_set_error(RN_ERR_ARG, "rn_mlp_forward: workspace too small");
+  for (int64_t row0 = 0; row0 < rows_total; row0 += rc) {
+    const int64_t rows = rows_total - row0 < rc ? rows_total - row0 : rc;
+    RN_TRY(forward_chunk(c, w, row0, rows, *out, want_normals, true));
+  }
+  return RN_OK;
+}
+
+extern "C" int rn_mlp_backward(const RnMlpConfig* cfg, const void* packed, const float* tdist, const float* origins,
+                               const float* dirs, const float* viewdirs, const float* radii, int64_t n_rays, int s,
+                               const RnMlpOutputs* g, float* const* grads, void* workspace, size_t workspace_bytes,
+                               void* stream) {
+  Ctx c;
+  RN_TRY(make_ctx(c, cfg, packed, tdist, origins, dirs, viewdirs, radii, s, stream));
+  if (!g || !grads) return rn_set_error(RN_ERR_ARG, "rn_mlp_backward: null gradients");
+  const int64_t rows_total = n_rays * s;
+  const int64_t rc = cfg->chunk_rows;
+  Workspace w = carve(workspace, cfg->prec, rc, 2);
+  const size_t scratch_off = w.bytes;
+  if (w.bytes + (size_t)rc * 16 * 4 > workspace_bytes) return rn_set_error(RN_ERR_ARG, "rn_mlp_backward: workspace too small");
+  // scratch destinations for the per-sample head outputs of the recompute pass (density 1, normals_pred 3,
+  // grad_pred 3, roughness 1, tint 3 = 11 floats per row, packed as separate arrays)
+  float* scratch = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(workspace) + scratch_off);
+  cudaStream_t st = c.st;
+  for (int l = 0; l < kNumLayers; ++l) {
+    LayerDef d = layer_def(l);
+    cudaError_t e = cudaMemsetAsync(w.gW[l], 0, (size_t)d.n_pad * d.k_tot() * 4, st);
+    if (e == cudaSuccess) e = cudaMemsetAsync(w.gB[l], 0, (size_t)d.n_pad * 4, st);
+    if (e != cudaSuccess) return rn_set_cuda_error(e, __FILE__, __LINE__);
+  }
+  for (int64_t row0 = 0; row0 < rows_total; row0 += rc) {
+    const int64_t rows = rows_total - row0 < rc ? rows_total - row0 : rc;
+    RnMlpOutputs tmp;
+    memset(&tmp, 0, sizeof(tmp));
+    // recompute-pass outputs land in scratch, addressed so that "+ row0*k" inside forward_chunk hits the scratch base
+    tmp.density = scratch - row0;
+    tmp.roughness = scratch + rc - row0;
+    tmp.normals_pred = scratch + 2 * rc - row0 * 3;
+    tmp.grad_pred = scratch + 5 * rc - row0 * 3;
+    tmp.tint = scratch + 8 * rc - row0 * 3;
+    RN_TRY(forward_chunk(c, w, row0, rows, tmp, false, false));
+    RN_TRY(backward_chunk(c, w, row0, rows, *g));
+  }
+  // packed-layout gradients -> parameter gradients (+=)
+  for (int l = 0; l < kNumLayers; ++l) {
+    LayerDef d = layer_def(l);
+    if (l == kLayerH) {
+      for (const HeadSeg& hs : kHeadSegs) {
+        RN_TRY(launch_unpack_add(w.gW[l], d.k_tot(), hs.row0, 0, hs.rows, 256, grads[hs.param], 256, st));
+        RN_TRY(launch_unpack_add(w.gB[l], d.n_pad, 0, hs.row0, 1, hs.rows, grads[hs.param + 1], hs.rows, st));
+      }
+      continue;
+    }
+    const int pi = layer_param(l);
+    const int kr = d.k1_real + d.k2_real;
+    RN_TRY(launch_unpack_add(w.gW[l], d.k_tot(), 0, 0, d.n_real, d.k1_real, grads[pi], kr, st));
+    if (d.k2_pad) RN_TRY(launch_unpack_add(w.gW[l], d.k_tot(), 0, d.k1_pad, d.n_real, d.k2_real, grads[pi] + d.k1_real, kr, st));
+    RN_TRY(launch_unpack_add(w.gB[l], d.n_pad, 0, 0, 1, d.n_real, grads[pi + 1], d.n_real, st));
+  }
+  return RN_OK;
+}
+
+// ---- unit-level entry points ------------------------------------------------------------------
+extern "C" int rn_encode(const float* tdist, const float* origins, const float* dirs, const float* radii, int64_t n_rays,
+                         int s, float* feat_out, void* stream) {
+  ActBuf out = {feat_out, nullptr, 96};
+  return launch_encode(RN_PREC_FP32, tdist, origins, dirs, radii, s, 0, n_rays * s, out, 96, (cudaStream_t)stream);
+}
+
+extern "C" int rn_ide(const float* dirs, const float* kappa_inv, int64_t n, float* out, void* stream) {
+  return launch_ide(dirs, kappa_inv, n, out, (cudaStream_t)stream);
+}
+
+extern "C" size_t rn_gemm_scratch_bytes(int64_t m, int n, int k) {
+  size_t rows = (size_t)(m > 256 ? m : 256);
+  return 2 * align256(rows * (size_t)(k > 256 ? k : 256) * 4) + 2 * align256((size_t)256 * 512 * 4) + 4096;
+}
+
+namespace {
+ActBuf scratch_act(Carver& c, int prec, int64_t rows, int ld) { return c.act(prec, rows, ld); }
+}  // namespace
+
+extern "C" int rn_gemm_test(const float* a, const float* b, const float* bias, int64_t m, int n, int k, int relu,
+                            int prec, int impl, float* cmat, void* scratch, size_t scratch_bytes, void* stream) {
+  if (k % 64 || n % 16 || n > 256 || k > 512) return rn_set_error(RN_ERR_ARG, "rn_gemm_test: need k%64==0, k<=512, n%16==0, n<=256");
+  if (scratch_bytes < rn_gemm_scratch_bytes(m, n, k)) return rn_set_error(RN_ERR_ARG, "rn_gemm_test: scratch too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  Carver c{reinterpret_cast<uint8_t*>(scratch)};
+  ActBuf abuf = scratch_act(c, prec, m, k);
+  ActBuf bbuf = scratch_act(c, prec, n, k);
+  RN_TRY(launch_f32_to_act(prec, a, k, 0, m, k, abuf, st));
+  RN_TRY(launch_f32_to_act(prec, b, k, 0, n, k, bbuf, st));
+  GemmArgs g;
+  g.prec = prec; g.impl = impl; g.m = m; g.n = n;
+  // exercise the two-source path when k > 256
+  const int k1 = k > 256 ? 256 : k;
+  g.a1 = abuf; g.k1 = k1; g.a1_valid = k1;
+  if (k > k1) {
+    g.a2 = abuf;
+    g.a2.hi = reinterpret_cast<uint8_t*>(abuf.hi) + (size_t)k1 * elem_bytes(prec);
+    if (abuf.lo) g.a2.lo = reinterpret_cast<uint8_t*>(abuf.lo) + (size_t)k1 * 2;
+    g.k2 = k - k1; g.a2_valid = k - k1;
+  }
+  g.b_hi = bbuf.hi; g.b_lo = bbuf.lo; g.b_ld = k;
+  g.epi.bias = bias; g.epi.relu = relu;
+  g.epi.f32 = cmat; g.epi.f32_ld = n; g.epi.f32_col0 = 0; g.epi.f32_cols = n;
+  return launch_gemm(g, st);
+}
+
+extern "C" int rn_wgrad_test(const float* dy, const float* x, int64_t m, int n, int k, int prec, int impl, float* cmat,
+                             void* scratch, size_t scratch_bytes, void* stream) {
+  if (n % 8 || n > 128 || k % 64 || k > 256) return rn_set_error(RN_ERR_ARG, "rn_wgrad_test: need n%8==0, n<=128, k%64==0, k<=256");
+  if (scratch_bytes < rn_gemm_scratch_bytes(m, n, k)) return rn_set_error(RN_ERR_ARG, "rn_wgrad_test: scratch too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  Carver c{reinterpret_cast<uint8_t*>(scratch)};
+  ActBuf ybuf = scratch_act(c, prec, m, n);
+  ActBuf xbuf = scratch_act(c, prec, m, k);
+  RN_TRY(launch_f32_to_act(prec, dy, n, 0, m, n, ybuf, st));
+  RN_TRY(launch_f32_to_act(prec, x, k, 0, m, k, xbuf, st));
+  cudaError_t e = cudaMemsetAsync(cmat, 0, (size_t)n * k * 4, st);
+  if (e != cudaSuccess) return rn_set_cuda_error(e, __FILE__, __LINE__);
+  WgradArgs g;
+  g.prec = prec; g.impl = impl; g.m = m;
+  g.dy = ybuf; g.dy_valid = n; g.n0 = 0; g.n_real = n;
+  g.x = xbuf; g.x_valid = k; g.kx = k; g.k_real = k;
+  g.out = cmat; g.out_ld = k;
+  return launch_wgrad(g, st);
+}
+
+extern "C" int rn_gemm_bench(int64_t m, int prec, int impl, int iters, float* ms_out, void* scratch, size_t scratch_bytes,
+                             void* stream) {
+  if (scratch_bytes < rn_gemm_scratch_bytes(m, 256, 256) + align256((size_t)m * 256 * 4) * 2)
+    return rn_set_error(RN_ERR_ARG, "rn_gemm_bench: scratch too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  Carver c{reinterpret_cast<uint8_t*>(scratch)};
+  ActBuf abuf = scratch_act(c, prec, m, 256);
+  ActBuf bbuf = scratch_act(c, prec, 256, 256);
+  ActBuf obuf = scratch_act(c, prec, m, 256);
+  // operands: whatever bytes are in scratch are fine for timing, but avoid NaN-pattern slowdowns: zero them
+  cudaMemsetAsync(scratch, 0, c.off, st);
+  GemmArgs g;
+  g.prec = prec; g.impl = impl; g.m = m; g.n = 256;
+  g.a1 = abuf; g.k1 = 256; g.a1_valid = 256;
+  g.b_hi = bbuf.hi; g.b_lo = bbuf.lo; g.b_ld = 256;
+  g.epi.relu = 1; g.epi.out = obuf; g.epi.out_cols = 256;
+  RN_TRY(launch_gemm(g, st));  // warm-up
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  cudaEventRecord(e0, st);
+  for (int i = 0; i < iters; ++i) RN_TRY(launch_gemm(g, st));
+  cudaEventRecord(e1, st);
+  cudaError_t e = cudaEventSynchronize(e1);
+  if (e != cudaSuccess) return rn_set_cuda_error(e, __FILE__, __LINE__);
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, e0, e1);
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  *ms_out = ms / iters;
+  return RN_OK;
+}

@@ -1,0 +1,585 @@
+// K4: warp-per-ray interval resampling, alpha compositing (fwd/bwd) and the step-function losses.
+//
+// One warp owns one ray.  The ray's fenceposts / CDF / weights are staged in shared memory,
+// prefix sums and products run as warp-shuffle scans, the inverse-CDF lookup is a per-lane binary
+// search over the staged CDF.  All global traffic is 128-byte coalesced row segments.
+// Reference semantics: internal/stepfun.py, internal/math.py:88-111, internal/render.py:132-254.
+#include "common.cuh"
+
+namespace {
+
+constexpr int kWarps = 4;  // warps (= rays) per block
+
+__device__ __forceinline__ float nan_to_zero_clip01(float r) {
+  if (r != r) r = 0.f;                  // torch.nan_to_num(x, 0)
+  return fminf(fmaxf(r, 0.f), 1.f);     // +-inf -> clip
+}
+
+// ---------------------------------------------------------------------------------------------
+// resample: models.py:200-203 + stepfun.py:134-258 + math.py:88-111 + coord.py:98
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kWarps * 32)
+resample_kernel(const float* __restrict__ sdist_in, const float* __restrict__ w_in, const float* __restrict__ u,
+                const float* __restrict__ near_, const float* __restrict__ far_, int64_t n_rays, int s_in, int s_out,
+                float padding, float anneal, float dom_lo, float dom_hi, float* __restrict__ sdist_out,
+                float* __restrict__ tdist_out, float* __restrict__ cw_out, int32_t* __restrict__ idx_out) {
+  extern __shared__ float smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int per_warp = 2 * (s_in + 1) + s_out;
+  float* ts = smem + warp * per_warp;  // fenceposts of the input step function
+  float* cw = ts + (s_in + 1);         // CDF (also scratch for logits / exp)
+  float* cs = cw + (s_in + 1);         // sampled centres
+  const int64_t ray = (int64_t)blockIdx.x * kWarps + warp;
+  if (ray >= n_rays) return;
+
+  const float* tin = sdist_in + ray * (s_in + 1);
+  for (int i = lane; i <= s_in; i += 32) ts[i] = tin[i];
+  __syncwarp();
+
+  // logits (models.py:200-203) and their max
+  const float* win = w_in + ray * s_in;
+  float m = -INFINITY;
+  for (int i = lane; i < s_in; i += 32) {
+    float l = (ts[i + 1] > ts[i]) ? __fmul_rn(anneal, logf(__fadd_rn(win[i], padding))) : -INFINITY;
+    cw[i + 1] = l;
+    m = fmaxf(m, l);
+  }
+  m = warp_max(m);
+  // softmax numerators and their sum (stepfun.py:160)
+  float sum = 0.f;
+  for (int i = lane; i < s_in; i += 32) {
+    float e = expf(__fsub_rn(cw[i + 1], m));
+    cw[i + 1] = e;
+    sum += e;
+  }
+  sum = warp_sum(sum);
+  __syncwarp();
+  // CDF: cw[j] = min(1, sum_{i<j} w_i), cw[0] = 0, cw[s_in] = 1 (stepfun.py:149-154)
+  float carry = 0.f;
+  for (int base = 0; base < s_in; base += 32) {
+    int i = base + lane;
+    float w = (i < s_in) ? __fdiv_rn(cw[i + 1], sum) : 0.f;
+    float c = warp_scan_incl(w, lane) + carry;
+    carry = __shfl_sync(RN_FULL, c, 31);
+    if (i < s_in - 1) cw[i + 1] = fminf(c, 1.f);
+  }
+  if (lane == 0) {
+    cw[0] = 0.f;
+    cw[s_in] = 1.f;
+  }
+  __syncwarp();
+  if (cw_out) {
+    float* o = cw_out + ray * (s_in + 1);
+    for (int i = lane; i <= s_in; i += 32) o[i] = cw[i];
+  }
+
+  // inverse CDF at the fixed grid u (math.py:88-111 in index form: idx = #{cw <= u} - 1)
+  for (int j = lane; j < s_out; j += 32) {
+    const float uj = u[j];
+    int lo = 0, hi = s_in + 1;
+    while (lo < hi) {
+      int mid = (lo + hi) >> 1;
+      if (cw[mid] <= uj) lo = mid + 1; else hi = mid;
+    }
+    const int idx = lo - 1;
+    const int i0 = min(max(idx, 0), s_in), i1 = min(max(idx + 1, 0), s_in);
+    const float x0 = cw[i0], x1 = cw[i1], f0 = ts[i0], f1 = ts[i1];
+    const float off = nan_to_zero_clip01(__fdiv_rn(__fsub_rn(uj, x0), __fsub_rn(x1, x0)));
+    cs[j] = __fadd_rn(f0, __fmul_rn(off, __fsub_rn(f1, f0)));
+    if (idx_out) idx_out[ray * s_out + j] = idx;
+  }
+  __syncwarp();
+
+  // midpoints + reflected end fenceposts (stepfun.py:246-258), then t = s*far + (1-s)*near
+  const float nr = near_[ray], fr = far_[ray];
+  float* so = sdist_out + ray * (s_out + 1);
+  float* to = tdist_out ? tdist_out + ray * (s_out + 1) : nullptr;
+  for (int j = lane; j <= s_out; j += 32) {
+    float s;
+    if (j == 0) {
+      float mid0 = __fdiv_rn(__fadd_rn(cs[1], cs[0]), 2.f);
+      s = fmaxf(dom_lo, __fsub_rn(__fmul_rn(2.f, cs[0]), mid0));
+    } else if (j == s_out) {
+      float midl = __fdiv_rn(__fadd_rn(cs[s_out - 1], cs[s_out - 2]), 2.f);
+      s = fminf(dom_hi, __fsub_rn(__fmul_rn(2.f, cs[s_out - 1]), midl));
+    } else {
+      s = __fdiv_rn(__fadd_rn(cs[j], cs[j - 1]), 2.f);
+    }
+    so[j] = s;
+    if (to) to[j] = __fadd_rn(__fmul_rn(s, fr), __fmul_rn(__fsub_rn(1.f, s), nr));
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// compositing forward: render.py:132-149 + render.py:152-254
+// ---------------------------------------------------------------------------------------------
+// accumulate sum_i w[i] * v[i, c] for a [S,3] array read as 3*S contiguous floats
+__device__ __forceinline__ void accum_vec3(const float* __restrict__ v, const float* ws, int s, int lane, float acc[3]) {
+  const int n = 3 * s;
+  for (int f = lane; f < n; f += 32) {
+    const float x = v[f];
+    const int smp = f / 3, ch = f - 3 * smp;
+    const float p = ws[smp] * x;
+    acc[0] += (ch == 0) ? p : 0.f;
+    acc[1] += (ch == 1) ? p : 0.f;
+    acc[2] += (ch == 2) ? p : 0.f;
+  }
+}
+
+__global__ void __launch_bounds__(kWarps * 32)
+composite_fwd_kernel(const float* __restrict__ density, const float* __restrict__ tdist, const float* __restrict__ dirs,
+                     const float* __restrict__ far_, const float* __restrict__ rgb, const float* __restrict__ diffuse,
+                     const float* __restrict__ specular, const float* __restrict__ normals,
+                     const float* __restrict__ normals_pred, const float* __restrict__ roughness,
+                     const float* __restrict__ tint, int64_t n_rays, int s, float bg, float* __restrict__ weights_out,
+                     float* __restrict__ comp_out, float* __restrict__ extras_out, double* __restrict__ pct_out) {
+  extern __shared__ float smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int per_warp = 3 * (s + 2);
+  float* ts = smem + warp * per_warp;  // tdist (+far) [s+2]
+  float* ws = ts + (s + 2);            // weights [s]
+  float* cw = ws + (s + 2);            // CDF for percentiles [s+2]
+  const int64_t ray = (int64_t)blockIdx.x * kWarps + warp;
+  if (ray >= n_rays) return;
+
+  const float* tin = tdist + ray * (s + 1);
+  for (int i = lane; i <= s; i += 32) ts[i] = tin[i];
+  const float dx = dirs[ray * 3 + 0], dy = dirs[ray * 3 + 1], dz = dirs[ray * 3 + 2];
+  const float dnorm = sqrtf(dx * dx + dy * dy + dz * dz);
+  __syncwarp();
+
+  // w_i = (1 - exp(-dd_i)) * exp(-sum_{j<i} dd_j)
+  const float* din = density + ray * s;
+  float carry = 0.f, acc = 0.f, dist = 0.f, logd = 0.f;
+  for (int base = 0; base < s; base += 32) {
+    const int i = base + lane;
+    float dd = 0.f;
+    if (i < s) dd = din[i] * ((ts[i + 1] - ts[i]) * dnorm);
+    const float incl = warp_scan_incl(dd, lane) + carry;
+    carry = __shfl_sync(RN_FULL, incl, 31);
+    if (i < s) {
+      const float w = (1.f - expf(-dd)) * expf(-(incl - dd));
+      ws[i] = w;
+      weights_out[ray * s + i] = w;
+      acc += w;
+      const float tmid = 0.5f * (ts[i] + ts[i + 1]);
+      dist += w * tmid;
+      logd += w * logf(tmid);
+    }
+  }
+  acc = warp_sum(acc);
+  dist = warp_sum(dist);
+  logd = warp_sum(logd);
+  __syncwarp();
+
+  const float bg_w = fmaxf(0.f, 1.f - acc);
+  float c0[3] = {0, 0, 0}, c1[3] = {0, 0, 0}, c2[3] = {0, 0, 0};
+  accum_vec3(rgb + ray * 3 * s, ws, s, lane, c0);
+  accum_vec3(diffuse + ray * 3 * s, ws, s, lane, c1);
+  accum_vec3(specular + ray * 3 * s, ws, s, lane, c2);
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    c0[c] = warp_sum(c0[c]);
+    c1[c] = warp_sum(c1[c]);
+    c2[c] = warp_sum(c2[c]);
+  }
+  if (lane == 0) {
+    float* o = comp_out + ray * 16;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      o[c] = c0[c] + bg_w * bg;
+      o[3 + c] = c1[c] + bg_w * bg;
+      o[6 + c] = c2[c] + bg_w * bg;
+    }
+    o[9] = dist;
+    o[10] = acc;
+    // distance_mean = clip(nan_to_num(exp(sum w log t_mid / max(eps, acc)), inf), t0, tS)  (render.py:232-238)
+    float dm = expf(logd / fmaxf(RN_EPS32, acc));
+    if (dm != dm) dm = INFINITY;        // torch.nan_to_num(x, nan=inf)
+    dm = fminf(fmaxf(dm, ts[0]), ts[s]);
+    o[11] = dm;
+    o[12] = bg_w;
+    o[13] = o[14] = o[15] = 0.f;
+  }
+  if (extras_out) {
+    float e0[3] = {0, 0, 0}, e1[3] = {0, 0, 0}, e2[3] = {0, 0, 0};
+    float er = 0.f;
+    if (normals) accum_vec3(normals + ray * 3 * s, ws, s, lane, e0);
+    if (normals_pred) accum_vec3(normals_pred + ray * 3 * s, ws, s, lane, e1);
+    if (tint) accum_vec3(tint + ray * 3 * s, ws, s, lane, e2);
+    if (roughness)
+      for (int i = lane; i < s; i += 32) er += ws[i] * roughness[ray * s + i];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      e0[c] = warp_sum(e0[c]);
+      e1[c] = warp_sum(e1[c]);
+      e2[c] = warp_sum(e2[c]);
+    }
+    er = warp_sum(er);
+    if (lane == 0) {
+      float* o = extras_out + ray * 12;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        o[c] = e0[c];
+        o[3 + c] = e1[c];
+        o[6 + c] = e2[c];
+      }
+      o[9] = er;
+      o[10] = o[11] = 0.f;
+    }
+  }
+  if (pct_out) {
+    // weighted_percentile (stepfun.py:294-307) on t_aug=[tdist, far], w_aug=[weights, bg_w]:
+    // cw = [0, min(1, cumsum(weights)), 1]  (bg_w is the dropped last weight); fp64 interp (math.py:114-142)
+    float cr = 0.f;
+    for (int base = 0; base < s; base += 32) {
+      const int i = base + lane;
+      const float w = (i < s) ? ws[i] : 0.f;
+      const float c = warp_scan_incl(w, lane) + cr;
+      cr = __shfl_sync(RN_FULL, c, 31);
+      if (i < s) cw[i + 1] = fminf(c, 1.f);
+    }
+    if (lane == 0) {
+      cw[0] = 0.f;
+      cw[s + 1] = 1.f;
+      ts[s + 1] = far_[ray];
+    }
+    __syncwarp();
+    const float ps[3] = {0.05f, 0.5f, 0.95f};
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      int cnt = 0;
+      for (int i = lane; i < s + 2; i += 32) cnt += (ps[k] >= cw[i]) ? 1 : 0;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(RN_FULL, cnt, o);
+      if (lane == 0) {
+        int idx = min(max(cnt - 1, 0), s);
+        const double x0 = cw[idx], x1 = cw[idx + 1], f0 = ts[idx], f1 = ts[idx + 1];
+        const double mm = (f1 - f0) / (x1 - x0);
+        const double bb = f0 - mm * x0;
+        pct_out[ray * 3 + k] = mm * (double)ps[k] + bb;
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// compositing backward
+// ---------------------------------------------------------------------------------------------
+// gw[smp] += sum_c g[c] * v[smp,c]  and  dv[smp,c] = w[smp] * g[c]; v read as flat 3*S floats
+__device__ __forceinline__ void bwd_vec3(const float* __restrict__ v, float* __restrict__ dv, const float* ws, float* gw,
+                                         const float g[3], int s, int lane) {
+  const int n = 3 * s;
+  for (int f = lane; f < n; f += 32) {
+    const int smp = f / 3, ch = f - 3 * smp;
+    const float gc = (ch == 0) ? g[0] : ((ch == 1) ? g[1] : g[2]);
+    if (v) atomicAdd(&gw[smp], gc * v[f]);   // shared-memory atomic: 3 lanes hit one sample
+    if (dv) dv[f] = ws[smp] * gc;
+  }
+}
+
+__global__ void __launch_bounds__(kWarps * 32)
+composite_bwd_kernel(const float* __restrict__ density, const float* __restrict__ tdist, const float* __restrict__ dirs,
+                     const float* __restrict__ rgb, const float* __restrict__ diffuse, const float* __restrict__ specular,
+                     const float* __restrict__ normals, const float* __restrict__ normals_pred,
+                     const float* __restrict__ roughness, const float* __restrict__ tint,
+                     const float* __restrict__ weights, const float* __restrict__ comp,
+                     const float* __restrict__ g_weights, const float* __restrict__ g_comp,
+                     const float* __restrict__ g_extras, int64_t n_rays, int s, float bg, float* __restrict__ d_density,
+                     float* __restrict__ d_rgb, float* __restrict__ d_diffuse, float* __restrict__ d_specular,
+                     float* __restrict__ d_normals_pred, float* __restrict__ d_roughness, float* __restrict__ d_tint) {
+  extern __shared__ float smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int per_warp = 3 * (s + 2);
+  float* ts = smem + warp * per_warp;
+  float* ws = ts + (s + 2);
+  float* gw = ws + (s + 2);  // dL/dw per sample
+  const int64_t ray = (int64_t)blockIdx.x * kWarps + warp;
+  if (ray >= n_rays) return;
+
+  for (int i = lane; i <= s; i += 32) ts[i] = tdist[ray * (s + 1) + i];
+  for (int i = lane; i < s; i += 32) ws[i] = weights[ray * s + i];
+  const float dx = dirs[ray * 3 + 0], dy = dirs[ray * 3 + 1], dz = dirs[ray * 3 + 2];
+  const float dnorm = sqrtf(dx * dx + dy * dy + dz * dz);
+  const float acc = comp[ray * 16 + 10];
+  const float bgmask = (1.f - acc > 0.f) ? bg : 0.f;  // d max(0, 1-acc)/d acc
+  float g0[3], g1[3], g2[3];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    g0[c] = g_comp[ray * 16 + c];
+    g1[c] = g_comp[ray * 16 + 3 + c];
+    g2[c] = g_comp[ray * 16 + 6 + c];
+  }
+  const float g_dist = g_comp[ray * 16 + 9], g_acc = g_comp[ray * 16 + 10];
+  const float gbg = -bgmask * (g0[0] + g0[1] + g0[2] + g1[0] + g1[1] + g1[2] + g2[0] + g2[1] + g2[2]);
+  __syncwarp();
+  for (int i = lane; i < s; i += 32) {
+    float g = g_weights ? g_weights[ray * s + i] : 0.f;
+    g += g_acc + gbg + g_dist * 0.5f * (ts[i] + ts[i + 1]);
+    gw[i] = g;
+  }
+  __syncwarp();
+  bwd_vec3(rgb + ray * 3 * s, d_rgb + ray * 3 * s, ws, gw, g0, s, lane);
+  bwd_vec3(diffuse + ray * 3 * s, d_diffuse + ray * 3 * s, ws, gw, g1, s, lane);
+  bwd_vec3(specular + ray * 3 * s, d_specular + ray * 3 * s, ws, gw, g2, s, lane);
+  if (g_extras) {
+    float e0[3], e1[3], e2[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      e0[c] = g_extras[ray * 12 + c];
+      e1[c] = g_extras[ray * 12 + 3 + c];
+      e2[c] = g_extras[ray * 12 + 6 + c];
+    }
+    const float er = g_extras[ray * 12 + 9];
+    if (normals) bwd_vec3(normals + ray * 3 * s, nullptr, ws, gw, e0, s, lane);
+    if (normals_pred) bwd_vec3(normals_pred + ray * 3 * s, d_normals_pred ? d_normals_pred + ray * 3 * s : nullptr, ws, gw, e1, s, lane);
+    if (tint) bwd_vec3(tint + ray * 3 * s, d_tint ? d_tint + ray * 3 * s : nullptr, ws, gw, e2, s, lane);
+    if (roughness)
+      for (int i = lane; i < s; i += 32) {
+        atomicAdd(&gw[i], er * roughness[ray * s + i]);
+        if (d_roughness) d_roughness[ray * s + i] = ws[i] * er;
+      }
+  } else {
+    if (d_normals_pred) for (int f = lane; f < 3 * s; f += 32) d_normals_pred[ray * 3 * s + f] = 0.f;
+    if (d_tint) for (int f = lane; f < 3 * s; f += 32) d_tint[ray * 3 * s + f] = 0.f;
+    if (d_roughness) for (int i = lane; i < s; i += 32) d_roughness[ray * s + i] = 0.f;
+  }
+  __syncwarp();
+
+  // w_i = (1-e^{-dd_i}) T_i,  T_i = exp(-sum_{j<i} dd_j)
+  // dL/ddd_i = gw_i * T_i * e^{-dd_i} - sum_{j>i} gw_j w_j
+  float total = 0.f;
+  for (int i = lane; i < s; i += 32) total += gw[i] * ws[i];
+  total = warp_sum(total);
+  float carry_dd = 0.f, carry_gw = 0.f;
+  for (int base = 0; base < s; base += 32) {
+    const int i = base + lane;
+    float dd = 0.f, p = 0.f, delta = 0.f;
+    if (i < s) {
+      delta = (ts[i + 1] - ts[i]) * dnorm;
+      dd = density[ray * s + i] * delta;
+      p = gw[i] * ws[i];
+    }
+    const float incl_dd = warp_scan_incl(dd, lane) + carry_dd;
+    const float incl_p = warp_scan_incl(p, lane) + carry_gw;
+    carry_dd = __shfl_sync(RN_FULL, incl_dd, 31);
+    carry_gw = __shfl_sync(RN_FULL, incl_p, 31);
+    if (i < s) {
+      const float trans_next = expf(-incl_dd);  // T_i * e^{-dd_i}
+      const float suffix = total - incl_p;      // sum_{j>i} gw_j w_j
+      d_density[ray * s + i] = (gw[i] * trans_next - suffix) * delta;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// lossfun_outer (stepfun.py:31-89) and lossfun_distortion (stepfun.py:261-272)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ int count_le(const float* a, int n, float v) {  // #{a <= v}, a sorted
+  int lo = 0, hi = n;
+  while (lo < hi) {
+    int mid = (lo + hi) >> 1;
+    if (a[mid] <= v) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+
+template <bool BWD>
+__global__ void __launch_bounds__(kWarps * 32)
+lossfun_outer_kernel(const float* __restrict__ t, const float* __restrict__ w, const float* __restrict__ t_env,
+                     const float* __restrict__ w_env, const float* __restrict__ g_loss, int64_t n_rays, int s, int se,
+                     float* __restrict__ out) {
+  extern __shared__ float smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int per_warp = 3 * (se + 1);
+  float* te = smem + warp * per_warp;  // envelope fenceposts
+  float* cy = te + (se + 1);           // [0, cumsum(w_env)]
+  float* gcy = cy + (se + 1);          // grad wrt cy (bwd)
+  const int64_t ray = (int64_t)blockIdx.x * kWarps + warp;
+  if (ray >= n_rays) return;
+  for (int i = lane; i <= se; i += 32) {
+    te[i] = t_env[ray * (se + 1) + i];
+    gcy[i] = 0.f;
+  }
+  float carry = 0.f;
+  for (int base = 0; base < se; base += 32) {
+    const int i = base + lane;
+    const float v = (i < se) ? w_env[ray * se + i] : 0.f;
+    const float c = warp_scan_incl(v, lane) + carry;
+    carry = __shfl_sync(RN_FULL, c, 31);
+    if (i < se) cy[i + 1] = c;
+  }
+  if (lane == 0) cy[0] = 0.f;
+  __syncwarp();
+  for (int i = lane; i < s; i += 32) {
+    const float ta = t[ray * (s + 1) + i], tb = t[ray * (s + 1) + i + 1];
+    const int lo = max(count_le(te, se + 1, ta) - 1, 0);   // idx_lo of t[i]
+    const int hi = min(count_le(te, se + 1, tb), se);      // idx_hi of t[i+1]
+    const float w_outer = cy[hi] - cy[lo];
+    const float wi = w[ray * s + i];
+    const float r = fmaxf(0.f, wi - w_outer);
+    if (!BWD) {
+      out[ray * s + i] = r * r / (wi + RN_EPS32);
+    } else {
+      // d loss / d w_outer = -2 r / (w + eps)
+      const float g = -2.f * r / (wi + RN_EPS32) * g_loss[ray * s + i];
+      if (g != 0.f) {
+        atomicAdd(&gcy[hi], g);
+        atomicAdd(&gcy[lo], -g);
+      }
+    }
+  }
+  if (BWD) {
+    __syncwarp();
+    // cy[j] = sum_{i<j} w_env[i]  =>  d w_env[i] = sum_{j>i} gcy[j]  (suffix sum)
+    float tot = 0.f;
+    for (int i = lane; i <= se; i += 32) tot += gcy[i];
+    tot = warp_sum(tot);
+    float cr = 0.f;
+    for (int base = 0; base <= se; base += 32) {
+      const int i = base + lane;
+      const float v = (i <= se) ? gcy[i] : 0.f;
+      const float c = warp_scan_incl(v, lane) + cr;
+      cr = __shfl_sync(RN_FULL, c, 31);
+      if (i < se) out[ray * se + i] = tot - c;
+    }
+  }
+}
+
+template <bool BWD>
+__global__ void __launch_bounds__(kWarps * 32)
+distortion_kernel(const float* __restrict__ t, const float* __restrict__ w, const float* __restrict__ g_loss,
+                  int64_t n_rays, int s, float* __restrict__ out) {
+  extern __shared__ float smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* ut = smem + warp * 2 * s;
+  float* ws = ut + s;
+  const int64_t ray = (int64_t)blockIdx.x * kWarps + warp;
+  if (ray >= n_rays) return;
+  for (int i = lane; i < s; i += 32) {
+    ut[i] = 0.5f * (t[ray * (s + 1) + i] + t[ray * (s + 1) + i + 1]);
+    ws[i] = w[ray * s + i];
+  }
+  __syncwarp();
+  float acc = 0.f;
+  const float g = BWD ? g_loss[ray] : 0.f;
+  for (int i = lane; i < s; i += 32) {
+    float inner = 0.f;
+    const float ui = ut[i];
+    for (int j = 0; j < s; ++j) inner += ws[j] * fabsf(ui - ut[j]);
+    const float width = t[ray * (s + 1) + i + 1] - t[ray * (s + 1) + i];
+    if (!BWD) {
+      acc += ws[i] * inner + ws[i] * ws[i] * width * (1.f / 3.f);
+    } else {
+      out[ray * s + i] = g * (2.f * inner + 2.f * ws[i] * width * (1.f / 3.f));
+    }
+  }
+  if (!BWD) {
+    acc = warp_sum(acc);
+    if (lane == 0) out[ray] = acc;
+  }
+}
+
+inline unsigned blocks_for(int64_t n_rays) { return (unsigned)((n_rays + kWarps - 1) / kWarps); }
+
+template <typename K>
+int ensure_smem(K kernel, size_t bytes) {
+  if (bytes > 48 * 1024) {
+    if (bytes > 200 * 1024) return rn_set_error(RN_ERR_UNSUPPORTED, "too many samples per ray for the shared-memory staging");
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e != cudaSuccess) return rn_set_cuda_error(e, __FILE__, __LINE__);
+  }
+  return RN_OK;
+}
+
+}  // namespace
+
+extern "C" int rn_resample(const float* sdist_in, const float* weights_in, const float* u, const float* near_,
+                           const float* far_, int64_t n_rays, int s_in, int s_out, float padding, float anneal,
+                           float dom_lo, float dom_hi, float* sdist_out, float* tdist_out, float* cw_out,
+                           int32_t* idx_out, void* stream) {
+  if (n_rays < 0 || s_in < 1 || s_out < 2) return rn_set_error(RN_ERR_ARG, "rn_resample: need s_in >= 1 and s_out >= 2");
+  if (n_rays == 0) return RN_OK;
+  size_t smem = (size_t)kWarps * (2 * (s_in + 1) + s_out) * sizeof(float);
+  if (int rc = ensure_smem(resample_kernel, smem)) return rc;
+  resample_kernel<<<blocks_for(n_rays), kWarps * 32, smem, (cudaStream_t)stream>>>(
+      sdist_in, weights_in, u, near_, far_, n_rays, s_in, s_out, padding, anneal, dom_lo, dom_hi, sdist_out, tdist_out,
+      cw_out, idx_out);
+  RN_CUDA_CHECK_LAUNCH();
+  return RN_OK;
+}
+
+extern "C" int rn_composite_fwd(const float* density, const float* tdist, const float* dirs, const float* far_,
+                                const float* rgb, const float* diffuse, const float* specular, const float* normals,
+                                const float* normals_pred, const float* roughness, const float* tint, int64_t n_rays,
+                                int s, float bg, float* weights_out, float* comp_out, float* extras_out,
+                                double* pct_out, void* stream) {
+  if (n_rays < 0 || s < 1) return rn_set_error(RN_ERR_ARG, "rn_composite_fwd: bad sizes");
+  if (n_rays == 0) return RN_OK;
+  size_t smem = (size_t)kWarps * 3 * (s + 2) * sizeof(float);
+  if (int rc = ensure_smem(composite_fwd_kernel, smem)) return rc;
+  composite_fwd_kernel<<<blocks_for(n_rays), kWarps * 32, smem, (cudaStream_t)stream>>>(
+      density, tdist, dirs, far_, rgb, diffuse, specular, normals, normals_pred, roughness, tint, n_rays, s, bg,
+      weights_out, comp_out, extras_out, pct_out);
+  RN_CUDA_CHECK_LAUNCH();
+  return RN_OK;
+}
+
+extern "C" int rn_composite_bwd(const float* density, const float* tdist, const float* dirs, const float* rgb,
+                                const float* diffuse, const float* specular, const float* normals,
+                                const float* normals_pred, const float* roughness, const float* tint,
+                                const float* weights, const float* comp, const float* g_weights, const float* g_comp,
+                                const float* g_extras, int64_t n_rays, int s, float bg, float* d_density, float* d_rgb,
+                                float* d_diffuse, float* d_specular, float* d_normals_pred, float* d_roughness,
+                                float* d_tint, void* stream) {
+  if (n_rays < 0 || s < 1) return rn_set_error(RN_ERR_ARG, "rn_composite_bwd: bad sizes");
+  if (n_rays == 0) return RN_OK;
+  size_t smem = (size_t)kWarps * 3 * (s + 2) * sizeof(float);
+  if (int rc = ensure_smem(composite_bwd_kernel, smem)) return rc;
+  composite_bwd_kernel<<<blocks_for(n_rays), kWarps * 32, smem, (cudaStream_t)stream>>>(
+      density, tdist, dirs, rgb, diffuse, specular, normals, normals_pred, roughness, tint, weights, comp, g_weights,
+      g_comp, g_extras, n_rays, s, bg, d_density, d_rgb, d_diffuse, d_specular, d_normals_pred, d_roughness, d_tint);
+  RN_CUDA_CHECK_LAUNCH();
+  return RN_OK;
+}
+
+extern "C" int rn_lossfun_outer_fwd(const float* t, const float* w, const float* t_env, const float* w_env,
+                                    int64_t n_rays, int s, int se, float* loss_out, void* stream) {
+  if (n_rays == 0) return RN_OK;
+  size_t smem = (size_t)kWarps * 3 * (se + 1) * sizeof(float);
+  if (int rc = ensure_smem(lossfun_outer_kernel<false>, smem)) return rc;
+  lossfun_outer_kernel<false><<<blocks_for(n_rays), kWarps * 32, smem, (cudaStream_t)stream>>>(
+      t, w, t_env, w_env, nullptr, n_rays, s, se, loss_out);
+  RN_CUDA_CHECK_LAUNCH();
+  return RN_OK;
+}
+
+extern "C" int rn_lossfun_outer_bwd(const float* t, const float* w, const float* t_env, const float* w_env,
+                                    const float* g_loss, int64_t n_rays, int s, int se, float* d_w_env, void* stream) {
+  if (n_rays == 0) return RN_OK;
+  size_t smem = (size_t)kWarps * 3 * (se + 1) * sizeof(float);
+  if (int rc = ensure_smem(lossfun_outer_kernel<true>, smem)) return rc;
+  lossfun_outer_kernel<true><<<blocks_for(n_rays), kWarps * 32, smem, (cudaStream_t)stream>>>(
+      t, w, t_env, w_env, g_loss, n_rays, s, se, d_w_env);
+  RN_CUDA_CHECK_LAUNCH();
+  return RN_OK;
+}
+
+extern "C" int rn_distortion_fwd(const float* t, const float* w, int64_t n_rays, int s, float* loss_out, void* stream) {
+  if (n_rays == 0) return RN_OK;
+  size_t smem = (size_t)kWarps * 2 * s * sizeof(float);
+  if (int rc = ensure_smem(distortion_kernel<false>, smem)) return rc;
+  distortion_kernel<false><<<blocks_for(n_rays), kWarps * 32, smem, (cudaStream_t)stream>>>(t, w, nullptr, n_rays, s, loss_out);
+  RN_CUDA_CHECK_LAUNCH();
+  return RN_OK;
+}
+
+extern "C" int rn_distortion_bwd(const float* t, const float* w, const float* g_loss, int64_t n_rays, int s, float* d_w,
+                                 void* stream) {
+  if (n_rays == 0) return RN_OK;
+  size_t smem = (size_t)kWarps * 2 * s * sizeof(float);
+  if (int rc = ensure_smem(distortion_kernel<true>, smem)) return rc;
+  distortion_kernel<true><<<blocks_for(n_rays), kWarps * 32, smem, (cudaStream_t)stream>>>(t, w, g_loss, n_rays, s, d_w);
+  RN_CUDA_CHECK_LAUNCH();
+  return RN_OK;
+}

@@ -1,0 +1,389 @@
+"""Drop-in replacements for the reference's `internal/models.py` `Model`, `MLP`, `NerfMLP`, `PropMLP`,
+`construct_model` and `render_image`, executing on hand-written sm_100a CUDA through the
+`refnerf_b200::*` custom ops (refnerf_pl_b200/ops.py -> include/refnerf_b200.h).
+
+Same constructor kwargs / gin names, same parameter names and shapes (reference checkpoints load
+with `load_state_dict`), same `(renderings, ray_history)` return structure and keys
+(models.py:129-321, 731-750; render.py:217-252).  Only the Ref-NeRF configuration exercised by the
+shipped gin files runs on the CUDA path; other settings raise (there is no eager fallback).
+"""
+import math as python_math
+from typing import Any, Callable, Tuple
+
+import numpy as np
+import torch
+from torch import nn
+
+from . import _lib, configs, ops, utils
+
+
+def _reset_linear(layer: nn.Linear):
+    """models.py:38-47: kaiming_uniform_(a=sqrt(5)) weights, zero bias."""
+    nn.init.kaiming_uniform_(layer.weight, a=python_math.sqrt(5))
+    if layer.bias is not None:
+        nn.init.constant_(layer.bias, val=0)
+
+
+class CastRays:
+    """What `render.cast_rays` returns here: the ray segment description the fused encode kernel
+    consumes (the Gaussians of render.py:105-129 are formed inside the kernel, never in HBM)."""
+
+    def __init__(self, tdist, origins, directions, radii):
+        self.tdist, self.origins, self.directions, self.radii = tdist, origins, directions, radii
+
+
+class MLP(nn.Module):
+    """A PosEnc MLP (models.py:343-750)."""
+
+    def __init__(
+            self,
+            net_depth: int = 8,
+            net_width: int = 256,
+            bottleneck_width: int = 256,
+            net_depth_viewdirs: int = 1,
+            net_width_viewdirs: int = 128,
+            net_activation: Callable[..., Any] = torch.nn.functional.relu,
+            min_deg_point: int = 0,
+            max_deg_point: int = 12,
+            weight_init: str = 'he_uniform',
+            skip_layer: int = 4,
+            skip_layer_dir: int = 4,
+            num_rgb_channels: int = 3,
+            deg_view: int = 4,
+            use_reflections: bool = False,
+            use_directional_enc: bool = False,
+            enable_pred_roughness: bool = False,
+            roughness_activation: Callable[..., Any] = torch.nn.functional.softplus,
+            roughness_bias: float = -1.,
+            use_diffuse_color: bool = False,
+            use_specular_tint: bool = False,
+            use_n_dot_v: bool = False,
+            enable_pred_specular_density: bool = False,
+            bottleneck_noise: float = 0.0,
+            density_activation: Callable[..., Any] = torch.nn.functional.softplus,
+            density_bias: float = -1.,
+            density_noise: float = 0.,
+            rgb_premultiplier: float = 1.,
+            rgb_activation: Callable[..., Any] = torch.sigmoid,
+            rgb_bias: float = 0.,
+            rgb_padding: float = 0.001,
+            enable_pred_normals: bool = False,
+            disable_density_normals: bool = False,
+            disable_rgb: bool = False,
+            srgb_mapping: bool = True,
+            srgb_mapping_normalization: bool = True,
+            warp_fn: Callable[..., Any] = None,
+            basis_shape: str = 'icosahedron',
+            basis_subdivisions: int = 2,
+            precision: str = 'bf16x3',
+            chunk_rows: int = 0,
+            gemm_impl: int = 0,
+    ):
+        super().__init__()
+        for k, v in list(locals().items()):
+            if k not in ('self', '__class__'):
+                setattr(self, k, v)
+        # same consistency checks as the reference (models.py:471-480)
+        if self.use_reflections and not (self.enable_pred_normals or not self.disable_density_normals):
+            raise ValueError('Normals must be computed for reflection directions.')
+        if self.enable_pred_specular_density and not self.use_diffuse_color:
+            raise ValueError('Specular density is useless if not using diffuse color.')
+        if precision not in _lib.PREC_BY_NAME:
+            raise ValueError(f'precision must be one of {sorted(_lib.PREC_BY_NAME)}')
+        self._check_supported()
+
+        w = self.net_width
+        in_feat = 3 * (self.max_deg_point - self.min_deg_point) * 2          # octahedron-1 basis: 3 axes
+        view_in = self.bottleneck_width + 72 + 1                              # bottleneck | IDE(deg 5) | n.v
+        dims, k = [], in_feat
+        for i in range(self.net_depth):
+            dims.append(k)
+            k = w + (in_feat if (i % self.skip_layer == 0 and i > 0) else 0)
+        self.spatial_net = nn.ModuleList([nn.Linear(d, w) for d in dims])
+        self.raw_density = nn.Linear(w, 1)
+        self.grad_pred = nn.Linear(w, 3)
+        self.raw_roughness = nn.Linear(w, 1)
+        self.raw_rgb_diffuse = nn.Linear(w, self.num_rgb_channels)
+        self.raw_tint = nn.Linear(w, 3)
+        self.bottleneck = nn.Linear(w, self.bottleneck_width)
+        dims, k = [], view_in
+        for i in range(self.net_depth_viewdirs):
+            dims.append(k)
+            k = self.net_width_viewdirs + (view_in if (i % self.skip_layer == 0 and i > 0) else 0)
+        self.viewdir_mlp = nn.ModuleList([nn.Linear(d, self.net_width_viewdirs) for d in dims])
+        self.rgb = nn.Linear(self.net_width_viewdirs, self.num_rgb_channels)
+        for m in self.modules():
+            if isinstance(m, nn.Linear):
+                _reset_linear(m)
+        self._packed = {}
+
+    def _check_supported(self):
+        want = dict(net_depth=8, net_width=256, bottleneck_width=128, net_depth_viewdirs=8, net_width_viewdirs=256,
+                    min_deg_point=0, max_deg_point=16, skip_layer=4, num_rgb_channels=3, deg_view=5,
+                    use_reflections=True, use_directional_enc=True, enable_pred_roughness=True, use_diffuse_color=True,
+                    use_specular_tint=True, use_n_dot_v=True, enable_pred_specular_density=False, bottleneck_noise=0.0,
+                    density_noise=0.0, enable_pred_normals=True, disable_density_normals=False, disable_rgb=False,
+                    basis_shape='octahedron', basis_subdivisions=1)
+        bad = {k: getattr(self, k) for k, v in want.items() if getattr(self, k) != v}
+        if bad:
+            raise NotImplementedError(
+                'refnerf_pl_b200 implements the Ref-NeRF configuration of configs/*_refnerf*.gin on CUDA; '
+                f'unsupported NerfMLP settings: {bad} (expected {dict((k, want[k]) for k in bad)})')
+        for name, fn, ref in (('net_activation', self.net_activation, torch.nn.functional.relu),
+                              ('density_activation', self.density_activation, torch.nn.functional.softplus),
+                              ('roughness_activation', self.roughness_activation, torch.nn.functional.softplus),
+                              ('rgb_activation', self.rgb_activation, torch.sigmoid)):
+            if fn is not ref:
+                raise NotImplementedError(f'{name} must be the reference default')
+
+    # -- parameters in the order of the C ABI (include/refnerf_b200.h) --------------------------
+    def ordered_params(self):
+        named = dict(self.named_parameters())
+        return [named[n] for n in _lib.param_names()]
+
+    def packed_weights(self):
+        prec = _lib.PREC_BY_NAME[self.precision]
+        ps = self.ordered_params()
+        key = tuple((p.data_ptr(), p._version) for p in ps)
+        hit = self._packed.get(prec)
+        if hit is None or hit[0] != key:
+            with torch.no_grad():
+                blob = ops.mlp_pack(ps, prec)
+            self._packed = {prec: (key, blob)}
+            hit = self._packed[prec]
+        return hit[1]
+
+    def __call__(self, gaussians, viewdirs=None, imageplane=None):
+        """gaussians: the `CastRays` object returned by `render.cast_rays` of this package."""
+        if not isinstance(gaussians, CastRays):
+            raise NotImplementedError('pass the result of refnerf_pl_b200.render.cast_rays: the Gaussians are formed '
+                                      'inside the fused encode kernel')
+        if viewdirs is None:
+            raise NotImplementedError('use_viewdirs=False is not part of the Ref-NeRF configuration')
+        g = gaussians
+        lead = g.tdist.shape[:-1]
+        s = g.tdist.shape[-1] - 1
+        flat = lambda t, c: ops._f32c(t.reshape(-1, c))
+        training = self.training
+        out = ops.mlp_forward(flat(g.tdist, s + 1), flat(g.origins, 3), flat(g.directions, 3), flat(viewdirs, 3),
+                              flat(g.radii, 1), self.ordered_params(), self.packed_weights(), training,
+                              _lib.PREC_BY_NAME[self.precision], self.srgb_mapping, self.srgb_mapping_normalization,
+                              float(self.density_bias), float(self.roughness_bias), float(self.rgb_premultiplier),
+                              float(self.rgb_bias), float(self.rgb_padding), int(self.chunk_rows), int(self.gemm_impl))
+        density, rgb, normals, npred, gpred, tint, diffuse, spec, rough = out
+        v3 = lambda t: t.reshape(lead + (s, 3))
+        return dict(density=density.reshape(lead + (s,)), rgb=v3(rgb), normals=v3(normals) if training else None,
+                    normals_pred=v3(npred), grad_pred=v3(gpred), tint=v3(tint), diffuse=v3(diffuse),
+                    specular=v3(spec), roughness=rough.reshape(lead + (s, 1)))
+
+
+@configs.configurable
+class NerfMLP(MLP):
+    pass
+
+
+@configs.configurable
+class PropMLP(MLP):
+    pass
+
+
+def _max_dilate_weights(t, w, dilation, domain, renormalize):
+    """stepfun.py:102-131 (disabled in every shipped config): sort-and-scan on the GPU."""
+    eps = torch.finfo(torch.float32).eps ** 2
+    p = w / torch.clamp(t[..., 1:] - t[..., :-1], min=eps)
+    t0, t1 = t[..., :-1] - dilation, t[..., 1:] + dilation
+    td = torch.clip(torch.sort(torch.cat([t, t0, t1], dim=-1), dim=-1).values, domain[0], domain[1])
+    inside = (t0[..., None, :] <= td[..., None]) & (t1[..., None, :] > td[..., None])
+    pd = torch.where(inside, p[..., None, :], torch.zeros_like(p[..., None, :])).amax(dim=-1)[..., :-1]
+    wd = pd * (td[..., 1:] - td[..., :-1])
+    if renormalize:
+        wd = wd / torch.clamp(wd.sum(dim=-1, keepdim=True), min=eps)
+    return td, wd
+
+
+_SRGB_MAPPINGS = ('none', 'linear', 'norm_linear', 'srgb', 'norm_srgb')
+
+
+def _linear_to_srgb(x):
+    eps = torch.finfo(torch.float32).eps
+    return torch.where(x <= 0.0031308, 323 / 25 * x, (211 * torch.clamp(x, min=eps) ** (5 / 12) - 11) / 200)
+
+
+def _render_tone_map(rgb, diffuse, specular, mapping):
+    """render.py:181-216 on the composited [N,3] colours."""
+    if mapping == 'none':
+        return rgb, diffuse, specular
+    if mapping not in _SRGB_MAPPINGS:
+        raise ValueError('Mapping types are none, linear, norm_linear, srgb, norm_srgb')
+    if mapping.startswith('norm_'):
+        rgb = rgb / torch.clamp(rgb.amax(dim=-1, keepdim=True), min=1.0)
+    if mapping.endswith('srgb'):
+        rgb, diffuse, specular = _linear_to_srgb(rgb), _linear_to_srgb(diffuse), _linear_to_srgb(specular)
+    return tuple(torch.clip(v, 0.0, 1.0) for v in (rgb, diffuse, specular))
+
+
+@configs.configurable
+class Model(nn.Module):
+    """The mip-NeRF-360-style level loop around the NerfMLP (models.py:50-321)."""
+
+    def __init__(
+            self,
+            config: Any = None,
+            num_prop_samples: int = 64,
+            num_nerf_samples: int = 32,
+            num_levels: int = 3,
+            bg_intensity_range: Tuple[float] = (1., 1.),
+            anneal_slope: float = 10,
+            use_viewdirs: bool = True,
+            raydist_fn: Callable[..., Any] = None,
+            ray_shape: str = 'cone',
+            disable_integration: bool = False,
+            single_jitter: bool = True,
+            dilation_bias: float = 0.0025,
+            dilation_multiplier: float = 0.5,
+            single_mlp: bool = False,
+            resample_padding: float = 0.0,
+            opaque_background: bool = False,
+            init_s_near: float = 0.,
+            init_s_far: float = 1.,
+    ):
+        super().__init__()
+        for k, v in list(locals().items()):
+            if k not in ('self', '__class__'):
+                setattr(self, k, v)
+        if self.config is None:
+            self.config = configs.Config()
+        if ray_shape != 'cone':
+            if ray_shape != 'cylinder':
+                raise ValueError("ray_shape must be 'cone' or 'cylinder'")
+            raise NotImplementedError("only ray_shape='cone' (every shipped config) runs on the CUDA path")
+        if raydist_fn is not None or disable_integration or opaque_background or not use_viewdirs:
+            raise NotImplementedError('raydist_fn / disable_integration / opaque_background / use_viewdirs=False are '
+                                      'not used by the Ref-NeRF configs and are not implemented on the CUDA path')
+        self.nerf_mlp = NerfMLP()
+        self.prop_mlp = self.nerf_mlp if self.single_mlp else PropMLP()
+
+    @property
+    def device(self):
+        return next(self.parameters()).device
+
+    def _flat_rays(self, rays):
+        dev = self.device
+        lead = tuple(np.shape(rays.origins)[:-1])
+
+        def get(name, c):
+            v = getattr(rays, name)
+            if isinstance(v, np.ndarray):
+                v = torch.from_numpy(np.ascontiguousarray(v, dtype=np.float32))
+            v = v.to(device=dev, dtype=torch.float32, non_blocking=True).reshape(-1, c)
+            return v.contiguous()
+
+        return lead, dict(origins=get('origins', 3), directions=get('directions', 3), viewdirs=get('viewdirs', 3),
+                          radii=get('radii', 1), near=get('near', 1), far=get('far', 1))
+
+    def __call__(self, rays, train_frac, compute_extras):
+        """rays: utils.Rays (numpy or torch fields, any leading dims).  Returns (renderings, ray_history)."""
+        from . import render  # noqa: PLC0415 (function-level surface built on the same ops)
+        lead, r = self._flat_rays(rays)
+        n = r['origins'].shape[0]
+        dev = r['origins'].device
+        near, far = r['near'], r['far']
+        sdist = torch.cat([torch.full_like(near, self.init_s_near), torch.full_like(far, self.init_s_far)], dim=-1)
+        weights = torch.ones_like(near)
+        prod_num_samples = 1
+        if self.config.render_with_specular_density:
+            raise ValueError('Specular density prediction from mlps should be enabled.')  # models.py:250-252
+        if self.bg_intensity_range[0] == self.bg_intensity_range[1]:
+            bg = float(self.bg_intensity_range[0])
+        else:
+            bg = float(self.bg_intensity_range[0] + self.bg_intensity_range[1]) / 2
+        mapping = self.config.srgb_mapping_type if self.config.srgb_mapping_when_rendering else 'none'
+        renderings, ray_history = [], []
+        for i_level in range(self.num_levels):
+            is_prop = i_level < (self.num_levels - 1)
+            num_samples = self.num_prop_samples if is_prop else self.num_nerf_samples
+            dilation = self.dilation_bias + self.dilation_multiplier * (self.init_s_far - self.init_s_near) / prod_num_samples
+            prod_num_samples *= num_samples
+            if i_level > 0 and (self.dilation_bias > 0 or self.dilation_multiplier > 0):
+                sdist, weights = _max_dilate_weights(sdist, weights.detach(), dilation,
+                                                     (self.init_s_near, self.init_s_far), True)
+                sdist, weights = sdist[..., 1:-1].contiguous(), weights[..., 1:-1].contiguous()
+            if self.anneal_slope > 0:
+                s_ = self.anneal_slope
+                anneal = float((s_ * train_frac) / ((s_ - 1) * train_frac + 1))
+            else:
+                anneal = 1.
+            # models.py:200-218: logits -> sample_intervals(.detach()) -> s_to_t, one fused kernel
+            sdist, tdist, _, _ = ops.resample(sdist.detach(), weights.detach(), near, far, num_samples,
+                                              float(self.resample_padding), anneal, float(self.init_s_near),
+                                              float(self.init_s_far), False)
+            gaussians = render.cast_rays(tdist, r['origins'], r['directions'], r['radii'], self.ray_shape, diag=False)
+            mlp = self.prop_mlp if is_prop else self.nerf_mlp
+            res = mlp(gaussians, viewdirs=r['viewdirs'], imageplane=None)
+            normals_in = res['normals'] if res['normals'] is not None else tdist.new_empty((0,))
+            weights, comp, ex, pct = ops.composite_fwd(res['density'], tdist, r['directions'], far, res['rgb'],
+                                                       res['diffuse'], res['specular'], normals_in,
+                                                       res['normals_pred'], res['roughness'], res['tint'], bg,
+                                                       bool(compute_extras))
+            rgb, dif, spe = _render_tone_map(comp[:, 0:3], comp[:, 3:6], comp[:, 6:9], mapping)
+            shp = lambda t, *tail: t.reshape(lead + tail)
+            rendering = dict(rgb=shp(rgb, 3), diffuse=shp(dif, 3), specular=shp(spe, 3), distance=shp(comp[:, 9], 1),
+                             acc=shp(comp[:, 10]))
+            if compute_extras:
+                if res['normals'] is not None:
+                    rendering['normals'] = shp(ex[:, 0:3], 3)
+                rendering['normals_pred'] = shp(ex[:, 3:6], 3)
+                rendering['tint'] = shp(ex[:, 6:9], 3)
+                rendering['roughness'] = shp(ex[:, 9], 1)
+                rendering['distance_mean'] = shp(comp[:, 11])
+                rendering['distance_percentile_5'] = shp(pct[:, 0])
+                rendering['distance_median'] = shp(pct[:, 1])
+                rendering['distance_percentile_95'] = shp(pct[:, 2])
+                nv = self.config.vis_num_rays
+                rendering['ray_sdist'] = sdist[:nv]
+                rendering['ray_weights'] = weights[:nv]
+                rendering['ray_rgbs'] = res['rgb'][:nv]
+            renderings.append(rendering)
+            s = num_samples
+            hist = {k: (v.reshape(lead + v.shape[1:]) if v is not None else None) for k, v in res.items()}
+            hist['sdist'] = sdist.reshape(lead + (s + 1,)).clone()
+            hist['weights'] = weights.reshape(lead + (s,))
+            ray_history.append(hist)
+        if compute_extras:
+            final_rgb = torch.sum(renderings[-1]['ray_rgbs'] * renderings[-1]['ray_weights'][..., None], dim=-2)
+            for rd in renderings[:-1]:
+                rd['ray_rgbs'] = torch.broadcast_to(final_rgb[:, None, :], rd['ray_rgbs'].shape)
+        return renderings, ray_history
+
+
+def construct_model(rays, config, device='cuda', **model_kwargs):
+    """models.py:324-340.  Shapes are static here (no LazyLinear), so no dummy forward is needed."""
+    del rays
+    return Model(config=config, **model_kwargs).to(device)
+
+
+def render_image(render_fn, rays, config, verbose=True, device=None):
+    """models.py:763-825: chunked full-image render in eval mode."""
+    height, width = rays.origins.shape[:2]
+    num_rays = height * width
+    rays = rays.reshape(num_rays, -1)
+    chunks = []
+    for idx0 in range(0, num_rays, config.render_chunk_size):
+        chunk_rays = rays[idx0:idx0 + config.render_chunk_size]
+        chunk_renderings, _ = render_fn(chunk_rays)
+        chunk_rendering = chunk_renderings[-1]
+        for k in chunk_renderings[0]:
+            if k.startswith('ray_'):
+                chunk_rendering[k] = [r[k] for r in chunk_renderings]
+        chunks.append({k: utils.recursive_detach(v) for k, v in chunk_rendering.items()})
+    rendering = utils.merge_chunks(chunks)
+    for k, z in rendering.items():
+        if not k.startswith('ray_'):
+            rendering[k] = z.reshape((height, width) + z.shape[1:])
+    keys = [k for k in rendering if k.startswith('ray_')]
+    if keys:
+        n = rendering[keys[0]][0].shape[0]
+        ray_idx = torch.randperm(n)[:config.vis_num_rays]
+        for k in keys:
+            rendering[k] = [r[ray_idx.to(r.device)] for r in rendering[k]]
+    return rendering

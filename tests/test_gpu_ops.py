@@ -1,0 +1,196 @@
+"""-m gpu parity tests of the non-MLP kernels, through the C ABI (ctypes -> librefnerf_b200.so)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import refnerf_oracle as O
+from tests._cases import GOLDEN
+from tests._gpu import DEV
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module')
+def ops():
+    from refnerf_pl_b200 import ops as _ops
+    return _ops
+
+
+@pytest.fixture(scope='module')
+def gold():
+    return np.load(GOLDEN + '/ops.npz')
+
+
+def _resample(ops, t, w, padding=0.01, s_out=128):
+    n = t.shape[0]
+    near = torch.zeros(n, 1, device=DEV)
+    far = torch.ones(n, 1, device=DEV)
+    so, to, cw, idx = ops.resample(t.to(DEV), w.to(DEV), near, far, s_out, padding, 1.0, 0.0, 1.0, True)
+    return so.cpu(), to.cpu(), cw.cpu(), idx.cpu()
+
+
+def test_resample_golden(ops, gold):
+    t, w = torch.tensor(gold['rs_t']), torch.tensor(gold['rs_w'])
+    so, to, cw, idx = _resample(ops, t, w)
+    # CDF within a few ulp of the reference's (softmax/exp/cumsum order differ between any two backends)
+    assert np.abs(cw.numpy() - gold['rs_cw']).max() <= 4e-7
+    # interval indices: bit-exact w.r.t. the index definition on the kernel's own CDF ...
+    u = O.sample_grid(128).expand(t.shape[0], 128)
+    assert torch.equal(idx.long(), O.interval_index(u, cw))
+    # ... and the interpolated fenceposts are bit-exact given that CDF (no FMA contraction in the kernel)
+    centers = O.sorted_interp(u, cw, t)
+    mid = (centers[..., 1:] + centers[..., :-1]) / 2
+    first = torch.clamp(2 * centers[..., :1] - mid[..., :1], min=0.0)
+    last = torch.clamp(2 * centers[..., -1:] - mid[..., -1:], max=1.0)
+    assert torch.equal(so, torch.cat([first, mid, last], -1))
+    assert torch.equal(to, so)  # near=0, far=1
+    # against the reference's own outputs: indices agree except where u is within an ulp of a CDF knot
+    mism = (idx.numpy() != gold['rs_idx']).mean()
+    assert mism <= 2e-3, mism
+    assert np.abs(so.numpy() - gold['rs_sdist']).max() <= 2e-6
+
+
+def test_resample_level0_constant(ops, gold):
+    t = torch.tensor([[0.0, 1.0]]).repeat(5, 1)
+    w = torch.ones(5, 1)
+    so, _, _, _ = _resample(ops, t, w)
+    assert np.array_equal(so.numpy(), np.repeat(gold['rs_level0'], 5, 0))   # bit-exact incl. sdist[0]=4.66e-10
+
+
+def test_resample_large_properties(ops):
+    g = torch.Generator().manual_seed(0)
+    n = 100_000
+    t = torch.sort(torch.rand(n, 129, generator=g), -1).values
+    w = torch.rand(n, 128, generator=g) ** 8
+    w[::7, 20:100] = 0
+    w[::11] = 0                                   # all-zero rows: uniform via the padding
+    so, to, cw, idx = _resample(ops, t, w)
+    assert torch.isfinite(so).all()
+    assert (so[:, 1:] >= so[:, :-1]).all() and so.min() >= 0 and so.max() <= 1
+    assert (cw[:, 1:] >= cw[:, :-1]).all() and (cw[:, 0] == 0).all() and (cw[:, -1] == 1).all()
+    u = O.sample_grid(128).expand(n, 128)
+    assert torch.equal(idx.long(), O.interval_index(u, cw))
+    ref = O.sample_intervals(t[:4096], O.resample_logits(t[:4096], w[:4096], 0.01), 128)
+    assert (so[:4096] - ref).abs().max() <= 5e-6
+
+
+def test_encode_matches_oracle(ops, gold):
+    td = torch.tensor(gold['ipe_tdist'])
+    o, d, r = (torch.tensor(gold['ipe_' + k]) for k in ('origins', 'directions', 'radii'))
+    enc = ops.encode(td.to(DEV), o.to(DEV), d.to(DEV), r.to(DEV)).cpu().numpy()
+    ref = gold['ipe_enc']
+    # identical fp32 op order for the phase => only sinf/expf ulp differences remain
+    assert np.abs(enc - ref).max() <= 2e-6, np.abs(enc - ref).max()
+
+
+def test_encode_blender_rays(ops):
+    from refnerf_pl_b200 import synthetic
+    r = synthetic.blender_rays(512, seed=4)
+    rt = {k: torch.tensor(v) for k, v in r.items()}
+    sd = O.sample_intervals(torch.tensor([[0., 1.]]).repeat(512, 1), torch.zeros(512, 1), 128)
+    td = O.s_to_t(sd, rt['near'], rt['far'])
+    means, cov = O.cast_rays(td, rt['origins'], rt['directions'], rt['radii'])
+    lm, lv = O.lift_and_diagonalize(means, cov, torch.tensor(O.octahedron_basis()))
+    ref = O.integrated_pos_enc(lm, lv, 0, 16)
+    enc = ops.encode(td.to(DEV), rt['origins'].to(DEV), rt['directions'].to(DEV), rt['radii'].to(DEV)).cpu()
+    assert (enc - ref).abs().max() <= 2e-6
+
+
+def test_ide_matches_reference_within_its_noise(ops, gold):
+    d = torch.tensor(gold['ide_dirs'])
+    ls = np.array([l for i in range(5) for _ in range(2 ** i + 1) for l in [2 ** i]])
+    hi_band = np.concatenate([ls == 16, ls == 16])
+    for i, k in enumerate(gold['ide_kappa_inv']):
+        out = ops.ide(d.to(DEV), torch.full((256,), float(k), device=DEV)).cpu().numpy()
+        ref32 = gold[f'ide_enc_{i}']
+        ref64 = O.integrated_dir_enc(d.double(), torch.full((256, 1), float(k), dtype=torch.float64)).numpy()
+        # tight against exact arithmetic on the reference's (fp32-rounded) coefficients
+        assert np.abs(out - ref64).max() <= 2e-6
+        # against the fp32 reference: l<=8 tight; l=16 band within the reference's own fp32 noise
+        assert np.abs(out - ref32)[:, ~hi_band].max() <= 5e-5
+        assert np.abs(out - ref32)[:, hi_band].max() <= max(2e-2 * np.exp(-136 * float(k)), 1e-6)
+
+
+def _composite_inputs(n=64, s=128, seed=0, extras=True):
+    g = torch.Generator().manual_seed(seed)
+    dens = torch.rand(n, s, generator=g) * 4
+    td = torch.sort(torch.rand(n, s + 1, generator=g) * 4 + 2, -1).values
+    dirs = torch.randn(n, 3, generator=g)
+    far = torch.full((n, 1), 6.0)
+    v3 = lambda: torch.rand(n, s, 3, generator=g)
+    return dict(density=dens, tdist=td, dirs=dirs, far=far, rgb=v3(), diffuse=v3(), specular=v3(), normals=v3() - 0.5,
+                normals_pred=v3() - 0.5, roughness=torch.rand(n, s, 1, generator=g), tint=v3())
+
+
+def _oracle_composite(x, extras):
+    w = O.compute_alpha_weights(x['density'], x['tdist'], x['dirs'])
+    ex = {k: x[k] for k in ('normals', 'normals_pred', 'roughness', 'tint')}
+    return w, O.volumetric_rendering(x['rgb'], x['diffuse'], x['specular'], w, x['tdist'], 1.0, x['far'], extras, ex)
+
+
+@pytest.mark.parametrize('extras', [False, True])
+def test_composite_forward_backward(ops, extras):
+    x = _composite_inputs()
+    leaf = ('density', 'rgb', 'diffuse', 'specular', 'normals_pred', 'roughness', 'tint')
+    xc = {k: v.clone().requires_grad_(k in leaf) for k, v in x.items()}
+    xg = {k: v.to(DEV).requires_grad_(k in leaf) for k, v in x.items()}
+    w_ref, r_ref = _oracle_composite(xc, extras)
+    w, comp, ex, pct = ops.composite_fwd(xg['density'], xg['tdist'], xg['dirs'], xg['far'], xg['rgb'], xg['diffuse'],
+                                         xg['specular'], xg['normals'], xg['normals_pred'], xg['roughness'], xg['tint'],
+                                         1.0, extras)
+    tol = 2e-6
+    assert (w.cpu() - w_ref).abs().max() <= tol
+    assert (comp[:, 0:3].cpu() - r_ref['rgb']).abs().max() <= 5e-6
+    assert (comp[:, 3:6].cpu() - r_ref['diffuse']).abs().max() <= 5e-6
+    assert (comp[:, 6:9].cpu() - r_ref['specular']).abs().max() <= 5e-6
+    assert (comp[:, 9:10].cpu() - r_ref['distance']).abs().max() <= 2e-5
+    assert (comp[:, 10].cpu() - r_ref['acc']).abs().max() <= 5e-6
+    gen = torch.Generator().manual_seed(5)
+    cw = torch.randn(w_ref.shape, generator=gen)
+    terms_ref = [(w_ref * cw).sum(), (r_ref['rgb'] * 1.3).sum(), (r_ref['diffuse'] * 0.7).sum(),
+                 (r_ref['specular'] * -0.4).sum(), (r_ref['distance'] * 0.2).sum(), (r_ref['acc'] * 0.9).sum()]
+    terms = [(w * cw.to(DEV)).sum(), (comp[:, 0:3] * 1.3).sum(), (comp[:, 3:6] * 0.7).sum(), (comp[:, 6:9] * -0.4).sum(),
+             (comp[:, 9] * 0.2).sum(), (comp[:, 10] * 0.9).sum()]
+    if extras:
+        assert (ex[:, 0:3].cpu() - r_ref['normals']).abs().max() <= 5e-6
+        assert (ex[:, 3:6].cpu() - r_ref['normals_pred']).abs().max() <= 5e-6
+        assert (ex[:, 6:9].cpu() - r_ref['tint']).abs().max() <= 5e-6
+        assert (ex[:, 9:10].cpu() - r_ref['roughness']).abs().max() <= 5e-6
+        assert (comp[:, 11].cpu() - r_ref['distance_mean']).abs().max() <= 2e-5
+        for i, k in enumerate(('distance_percentile_5', 'distance_median', 'distance_percentile_95')):
+            assert pct.dtype == torch.float64
+            assert (pct[:, i].cpu() - r_ref[k]).abs().max() <= 1e-4, k
+        terms_ref += [(r_ref['normals'] * 0.3).sum(), (r_ref['normals_pred'] * -0.6).sum(), (r_ref['tint'] * 0.5).sum(),
+                      (r_ref['roughness'] * 1.1).sum()]
+        terms += [(ex[:, 0:3] * 0.3).sum(), (ex[:, 3:6] * -0.6).sum(), (ex[:, 6:9] * 0.5).sum(), (ex[:, 9] * 1.1).sum()]
+    sum(terms_ref).backward()
+    sum(terms).backward()
+    for k in leaf:
+        if xc[k].grad is None:
+            continue
+        a, b = xg[k].grad.cpu(), xc[k].grad
+        assert (a - b).abs().max() <= 1e-4 * max(1.0, float(b.abs().max())), k
+
+
+def test_step_losses(ops, gold):
+    t, w, te, we = (torch.tensor(gold[k]) for k in ('lo_t', 'lo_w', 'lo_tenv', 'lo_wenv'))
+    out = ops.lossfun_outer(t.to(DEV), w.to(DEV), te.to(DEV), we.to(DEV).requires_grad_(True))
+    assert np.abs(out.detach().cpu().numpy() - gold['lo_loss']).max() <= 1e-6
+    we_c = we.clone().requires_grad_(True)
+    cot = torch.rand(out.shape, generator=torch.Generator().manual_seed(1))
+    (O.lossfun_outer(t, w, te, we_c) * cot).sum().backward()
+    we_g = we.to(DEV).requires_grad_(True)
+    (ops.lossfun_outer(t.to(DEV), w.to(DEV), te.to(DEV), we_g) * cot.to(DEV)).sum().backward()
+    assert (we_g.grad.cpu() - we_c.grad).abs().max() <= 1e-5
+    d = ops.distortion(t.to(DEV), w.to(DEV))
+    assert np.abs(d.cpu().numpy() - gold['dist_loss']).max() <= 1e-6
+    w_c = w.clone().requires_grad_(True)
+    O.lossfun_distortion(t, w_c).sum().backward()
+    w_g = w.to(DEV).requires_grad_(True)
+    ops.distortion(t.to(DEV), w_g).sum().backward()
+    assert (w_g.grad.cpu() - w_c.grad).abs().max() <= 1e-5
+
+
+def test_cpu_tensors_fail_loudly(ops):
+    with pytest.raises((NotImplementedError, RuntimeError)):
+        ops.distortion(torch.rand(2, 5), torch.rand(2, 4))
