@@ -1,0 +1,345 @@
+#!/usr/bin/env python
+"""bench.py -- Ref-NeRF hot-path throughput on B200 (BASELINE.json: "train rays/s (fwd+bwd) & 800x800
+render ms/frame at 1/2/4/8 B200 vs host CPU").
+
+  python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+  python bench.py --impl reference --gpus N --steps K --warmup W   # CPU oracle port on the host cores
+
+One "step" = one full training step of configs/blender_refnerf.gin on a batch of synthetic
+Blender-shaped rays with reference-init weights: Model forward in training mode (both levels, incl. the
+in-forward density-gradient normals pass, compute_extras=True as nerf_system.py:89-95 does), data +
+orientation + predicted-normal losses, backward, [N>1: one NCCL all-reduce of the 4.44 MB gradient],
+grad clipping and the Adam update.  Weak scaling: every rank runs `--rays` rays (default 16384).
+Prints ONE JSON line (rank 0).
+"""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+METRIC = 'train rays/s (fwd+bwd)'
+UNIT = 'rays/s'
+# algorithmic MLP FLOPs per sample (dense, unpadded) for fwd + in-forward normals dgrad + bwd
+FLOP_PER_SAMPLE_TRAIN = 7_651_840
+FLOP_PER_SAMPLE_EVAL = 2_211_840
+SAMPLES_PER_RAY = 256  # 2 levels x 128
+
+
+def load_peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm_gbs=d['hbm_gbs'], bf16_burst=d['bf16_tflops'], bf16_sustained=d['bf16_tflops_sustained'],
+                    source='measured')
+    return dict(hbm_gbs=6650.0, bf16_burst=1590.0, bf16_sustained=1400.0, source='fallback')
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+         'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, gpu_index=0):
+        self.idx, self.proc, self.lines = gpu_index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits',
+                                          '-lms', '200', '-i', str(self.idx)], stdout=subprocess.PIPE, text=True)
+            self.th = threading.Thread(target=lambda: self.lines.extend(self.proc.stdout), daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def stop(self):
+        if not self.proc:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        time.sleep(0.25)
+        self.proc.terminate()
+        self.th.join(timeout=2)
+        sm, smax, reasons = [], None, set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(',')]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                smax = float(f[2])
+            except ValueError:
+                continue
+            for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), f[5:9]):
+                if v.lower().startswith('active'):
+                    reasons.add(name)
+        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': smax, 'reasons': sorted(reasons),
+                'samples': len(sm)}
+
+
+def oracle_step_fn(n_rays, seed=0):
+    """One training step of the CPU oracle port (forward in training mode, losses, backward)."""
+    from oracle import refnerf_oracle as O
+    from refnerf_pl_b200 import synthetic
+    rays = {k: torch.tensor(v) for k, v in synthetic.blender_rays(n_rays, seed=seed).items()}
+    gt = torch.tensor(synthetic.gt_rgb(n_rays, seed))
+    p = {k: v.requires_grad_(True) for k, v in O.init_params(seed=0).items()}
+
+    def step():
+        for v in p.values():
+            v.grad = None
+        rend, hist = O.model_forward(p, rays, 1.0, True, True)
+        loss = O.total_loss(rend, hist, rays, gt)
+        loss.backward()
+        return float(loss)
+
+    return step
+
+
+def time_cpu(n_rays, steps, warmup):
+    torch.set_num_threads(os.cpu_count() or 1)
+    step = oracle_step_fn(n_rays)
+    for _ in range(warmup):
+        step()
+    ts = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        step()
+        ts.append(time.perf_counter() - t0)
+    return float(np.median(ts))
+
+
+def cpu_model_name():
+    try:
+        for ln in open('/proc/cpuinfo'):
+            if ln.startswith('model name'):
+                return ln.split(':', 1)[1].strip()
+    except OSError:
+        pass
+    return 'unknown'
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', 0))
+    if rank != 0:
+        return
+    n = args.cpu_rays
+    sec = time_cpu(n, max(1, args.steps), max(0, min(args.warmup, 1)))
+    val = n / sec
+    cores = os.cpu_count() or 1
+    line = {
+        'impl': 'reference', 'metric': METRIC, 'value': val, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
+        'warmup': args.warmup, 'ms_per_step': sec * 1e3, 'higher_is_better': True, 'scaling': 'weak',
+        'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': f'blender_refnerf.gin single training step (fwd+bwd), {args.rays}-ray batch; timed on a '
+                               f'{n}-ray sample of it', 'rays_per_step': n, 'levels': 2, 'samples_per_level': 128},
+        'cpu_baseline': {'value': val, 'unit': UNIT, 'cores': cores, 'kind': 'port',
+                         'sample': f'{n} rays of the {args.rays}-ray batch, {args.steps} step(s), median; '
+                                   f'torch threads={cores}; {cpu_model_name()}'},
+        'e2e': {'value': val, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+    }
+    print(json.dumps(line))
+
+
+def build_everything(precision, device):
+    from refnerf_pl_b200 import configs, models
+    configs.clear_bindings()
+    gin = os.path.join(ROOT, 'configs', 'blender_refnerf.gin')
+    configs.parse_gin_files_and_bindings([gin])
+    configs.bind('NerfMLP', precision=precision)
+    cfg = configs.Config()
+    torch.manual_seed(0)
+    model = models.Model(config=cfg).to(device)
+    return model, cfg
+
+
+def run_b200(args):
+    from refnerf_pl_b200 import _lib, parallel, synthetic, train_utils, utils
+    rank, world, local_rank = parallel.init_distributed()
+    assert torch.cuda.is_available(), 'bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm'
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    lib = _lib.load()
+    peaks = load_peaks()
+    model, cfg = build_everything(args.precision, dev)
+    model.train(True)
+    opt, sched = train_utils.create_optimizer(cfg, [p for p in model.nerf_mlp.parameters()])
+    reducer = parallel.GradAllReducer(model.nerf_mlp.parameters()) if world > 1 else None
+
+    n = args.rays
+    rays_np = synthetic.blender_rays(n, seed=100 + rank)
+    gt_np = synthetic.gt_rgb(n, seed=100 + rank)
+    pinned = {k: torch.from_numpy(v).pin_memory() for k, v in rays_np.items()}
+    gt_pinned = torch.from_numpy(gt_np).pin_memory()
+    resident = utils.Rays(**{k: v.to(dev) for k, v in pinned.items()})
+    gt_res = gt_pinned.to(dev)
+    h2d_bytes = sum(v.numel() * v.element_size() for v in pinned.values()) + gt_pinned.numel() * 4
+
+    def train_step(rays, gt):
+        rend, hist = model(rays, 1.0, True)
+        loss, _ = train_utils.total_loss(model, rays.viewdirs, rays.lossmult, gt, rend, hist, cfg)
+        opt.zero_grad(set_to_none=True)
+        loss.backward()
+        if reducer is not None:
+            reducer.allreduce()
+        if cfg.grad_max_norm > 0:
+            torch.nn.utils.clip_grad_norm_(model.nerf_mlp.parameters(), cfg.grad_max_norm)
+        opt.step()
+        sched.step()
+        return loss
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+            ms = float(t)
+        return ms
+
+    for _ in range(args.warmup):
+        train_step(resident, gt_res)
+    # ---- device-resident timed region (value) with per-kernel-class CUDA-event timing --------------
+    sampler = ClockSampler(local_rank).start() if rank == 0 else None
+    lib.rn_prof_enable(1)
+    for c in range(3):
+        lib.rn_prof_summary(c, None, None, None)
+    l0 = lib.rn_launch_count()
+    ms_total = timed(lambda: train_step(resident, gt_res), args.steps)
+    launches = lib.rn_launch_count() - l0
+    prof = {}
+    for c, name in enumerate(('gemm_tc', 'wgrad_tc', 'gemm_simt')):
+        nl, tms, fl = ctypes.c_int64(0), ctypes.c_double(0), ctypes.c_double(0)
+        lib.rn_prof_summary(c, ctypes.byref(nl), ctypes.byref(tms), ctypes.byref(fl))
+        prof[name] = dict(launches=nl.value, ms=tms.value, flops=fl.value)
+    lib.rn_prof_enable(0)
+    clocks = sampler.stop() if sampler else None
+    ms_step = ms_total / args.steps
+    value = world * n / (ms_step * 1e-3)
+
+    # ---- end-to-end: pinned host rays -> H2D every step, loss read back every step -------------------
+    def e2e_step():
+        rays = utils.Rays(**{k: v.to(dev, non_blocking=True) for k, v in pinned.items()})
+        gt = gt_pinned.to(dev, non_blocking=True)
+        return float(train_step(rays, gt))   # .item(): D2H of the loss
+
+    e2e_step()
+    ms_e2e = timed(e2e_step, args.steps) / args.steps
+    e2e_value = world * n / (ms_e2e * 1e-3)
+
+    if rank != 0:
+        return
+    # ---- roofline of the dominant kernel (tcgen05 fwd/dgrad GEMM; SIMT GEMM in fp32 mode) ----------
+    dom = 'gemm_tc' if prof['gemm_tc']['launches'] else 'gemm_simt'
+    d = prof[dom]
+    achieved = d['flops'] / (d['ms'] * 1e-3) / 1e12 if d['ms'] > 0 else 0.0
+    peak = peaks['bf16_sustained']
+    roofline = {'bound': 'tensor', 'kernel': dom, 'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s',
+                'frac': achieved / peak, 'traffic': None, 'peak_source': peaks['source'] + ' (sustained bf16)',
+                'launches_per_step': d['launches'] / args.steps, 'avg_launch_ms': d['ms'] / max(1, d['launches']),
+                'kernel_share_of_step': d['ms'] / ms_total,
+                'algo_flops_per_launch': d['flops'] / max(1, d['launches'])}
+    step_tflops = FLOP_PER_SAMPLE_TRAIN * SAMPLES_PER_RAY * n / (ms_step * 1e-3) / 1e12
+
+    # ---- CPU baseline on this box's host cores (oracle port, bounded sample) -----------------------
+    cpu = None
+    if world == 1 and not args.no_cpu:
+        cores = os.cpu_count() or 1
+        sec = time_cpu(args.cpu_rays, 2, 1)
+        cpu = {'value': args.cpu_rays / sec, 'unit': UNIT, 'cores': cores, 'kind': 'port',
+               'sample': f'{args.cpu_rays} rays of the {n}-ray batch, fwd+bwd, median of 2 after 1 warm-up; torch '
+                         f'threads={cores}; {cpu_model_name()}'}
+
+    # ---- 800x800 frame render (eval path, chunked) ------------------------------------------------
+    render = None
+    if not args.no_render:
+        from refnerf_pl_b200 import models
+        model.eval()
+        frame = synthetic.blender_rays(None, seed=7)
+        lo, hi = parallel.shard_range(640000, 0, 1)
+        fr = utils.Rays(**{k: torch.from_numpy(v).to(dev).reshape(800, 800, -1) for k, v in frame.items()})
+        cfg.render_chunk_size = args.render_chunk
+        fn = lambda r: model(r, 1.0, True)
+        with torch.no_grad():
+            models.render_image(fn, fr, cfg)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(2):
+                models.render_image(fn, fr, cfg)
+            e1.record()
+            torch.cuda.synchronize()
+        fms = e0.elapsed_time(e1) / 2
+        render = {'ms_per_frame': fms, 'rays_per_s': 640000 / (fms * 1e-3), 'chunk_rays': args.render_chunk,
+                  'frame': '800x800', 'compute_extras': True,
+                  'mlp_tflops': FLOP_PER_SAMPLE_EVAL * SAMPLES_PER_RAY * 640000 / (fms * 1e-3) / 1e12}
+
+    line = {
+        'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
+        'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+        'dtype': {'bf16': 'bf16', 'bf16x3': 'bf16x3 (split-bf16, fp32 accumulate)', 'fp32': 'f32'}[args.precision],
+        'data': 'synthetic',
+        'config': {'workload': f'configs/blender_refnerf.gin single training step, {n}-ray batch per GPU, NerfMLP at '
+                               'both levels (single_mlp), fwd (incl. density-gradient normals) + losses + bwd + Adam',
+                   'rays_per_gpu': n, 'levels': 2, 'samples_per_level': 128, 'precision': args.precision,
+                   'l2': 'no explicit flush: per-step activation working set (>2 GB) exceeds the 126 MB L2',
+                   'parallelism': f'ray-sharded dp{world}, one NCCL gradient all-reduce per step' if world > 1 else 'single GPU'},
+        'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': h2d_bytes, 'd2h_bytes_per_step': 4,
+                'ms_per_step': ms_e2e},
+        'gpu_launches': int(launches),
+        'clocks': clocks,
+        'roofline': roofline,
+        'cpu_baseline': cpu,
+        'mlp_tflops_step': step_tflops,
+        'mlp_frac_of_bf16_peak': step_tflops / peaks['bf16_sustained'],
+        'kernel_classes': prof,
+        'render': render,
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=5)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--precision', default=os.environ.get('REFNERF_B200_PRECISION', 'bf16'),
+                    choices=['bf16', 'bf16x3', 'fp32'])
+    ap.add_argument('--rays', type=int, default=16384)
+    ap.add_argument('--cpu-rays', type=int, default=512)
+    ap.add_argument('--render-chunk', type=int, default=65536)
+    ap.add_argument('--no-render', action='store_true')
+    ap.add_argument('--no-cpu', action='store_true')
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        run_b200(args)
+    if torch.distributed.is_available() and torch.distributed.is_initialized():
+        torch.distributed.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

@@ -160,6 +160,16 @@ RN_API int rn_wgrad_test(const float* dy, const float* x, int64_t m, int n, int 
 RN_API int rn_gemm_bench(int64_t m, int prec, int impl, int iters, float* ms_out, void* scratch, size_t scratch_bytes,
                   void* stream);
 
+/* ---- instrumentation -------------------------------------------------------------------------
+ * rn_launch_count: kernels launched by this library since load (process-wide).
+ * rn_prof_enable(1) makes the GEMM launchers bracket every launch with CUDA events on the launching
+ * stream; rn_prof_summary(cls, ...) synchronises the recorded events and returns, for kernel class
+ * cls (0 = tcgen05 fwd/dgrad GEMM, 1 = tcgen05 wgrad, 2 = SIMT GEMMs), the number of launches, their
+ * summed device time in ms and the algorithmic FLOPs they carried, then clears the class. */
+RN_API int64_t rn_launch_count(void);
+RN_API int rn_prof_enable(int on);
+RN_API int rn_prof_summary(int cls, int64_t* launches, double* total_ms, double* algo_flops);
+
 #ifdef __cplusplus
 }
 #endif

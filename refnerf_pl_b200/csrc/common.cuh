@@ -11,12 +11,18 @@
 
 #define RN_CUDA_CHECK_LAUNCH()                       \
   do {                                               \
+    rn_count_launch();                               \
     cudaError_t e__ = cudaGetLastError();            \
     if (e__ != cudaSuccess) return rn_set_cuda_error(e__, __FILE__, __LINE__); \
   } while (0)
 
 int rn_set_cuda_error(cudaError_t e, const char* file, int line);
 int rn_set_error(int code, const char* msg);
+void rn_count_launch();
+// optional CUDA-event timing of kernel classes (bench.py roofline); no-ops unless rn_prof_enable(1)
+enum { RN_PROF_GEMM_TC = 0, RN_PROF_WGRAD_TC = 1, RN_PROF_GEMM_SIMT = 2, RN_PROF_NUM = 3 };
+void rn_prof_begin(int cls, cudaStream_t st, double algo_flops);
+void rn_prof_end(int cls, cudaStream_t st);
 
 // ------------------------------------------------------------------------------------------
 // Activation buffers: [rows, ld] matrices that feed / leave the GEMMs.

@@ -30,6 +30,7 @@ struct GemmArgs {
   const void* b_lo = nullptr;
   int b_ld = 0;
   GemmEpilogue epi;
+  double algo_flops = 0.0;  // algorithmic (unpadded, non-recompute) FLOPs carried by this launch (profiling)
 };
 
 // dW[n0 + i, j] += sum_r dY[r, n0 + i] * X[r, j]   for i < 128, j < kx  (guards: n0+i < n_real, j < k_real)
@@ -47,6 +48,7 @@ struct WgradArgs {
   int k_real = 0;
   float* out = nullptr;  // dW (fp32), row-major [.., out_ld], element (n, j) at out[n*out_ld + j]
   int out_ld = 0;
+  double algo_flops = 0.0;
 };
 
 int launch_gemm(const GemmArgs& g, cudaStream_t st);

@@ -140,12 +140,14 @@ wgrad_simt_kernel(WgradArgs g, int64_t rows_per_split) {
 int launch_gemm_simt(const GemmArgs& g, cudaStream_t st) {
   if (g.m <= 0) return RN_OK;
   dim3 grid((unsigned)((g.m + BM - 1) / BM), (unsigned)((g.n + BN - 1) / BN));
+  rn_prof_begin(RN_PROF_GEMM_SIMT, st, g.algo_flops);
   switch (g.prec) {
     case RN_PREC_FP32: gemm_simt_kernel<RN_PREC_FP32><<<grid, 256, 0, st>>>(g); break;
     case RN_PREC_BF16: gemm_simt_kernel<RN_PREC_BF16><<<grid, 256, 0, st>>>(g); break;
     case RN_PREC_BF16X3: gemm_simt_kernel<RN_PREC_BF16X3><<<grid, 256, 0, st>>>(g); break;
     default: return rn_set_error(RN_ERR_ARG, "gemm: bad precision");
   }
+  rn_prof_end(RN_PROF_GEMM_SIMT, st);
   RN_CUDA_CHECK_LAUNCH();
   return RN_OK;
 }

@@ -466,6 +466,7 @@ int launch_gemm_tc(const GemmArgs& g, cudaStream_t st) {
   if ((rc = make_map(&maps.b_lo, x3 ? g.b_lo : nullptr, g.n, g.k1 + g.k2, g.b_ld, g.n))) return rc;
   const int64_t tiles = (g.m + kBM - 1) / kBM;
   const unsigned grid = (unsigned)(tiles < num_sms() ? tiles : num_sms());
+  rn_prof_begin(RN_PROF_GEMM_TC, st, g.algo_flops);
   if (x3) {
     static bool once = false;
     if (!once) { if ((rc = set_smem(gemm_tc_kernel<3>, Cfg<3>::kSmemBytes))) return rc; once = true; }
@@ -475,6 +476,7 @@ int launch_gemm_tc(const GemmArgs& g, cudaStream_t st) {
     if (!once) { if ((rc = set_smem(gemm_tc_kernel<1>, Cfg<1>::kSmemBytes))) return rc; once = true; }
     gemm_tc_kernel<1><<<grid, 256, Cfg<1>::kSmemBytes, st>>>(maps, g.m, g.n, g.k1 / kBK, g.k2 / kBK, g.epi);
   }
+  rn_prof_end(RN_PROF_GEMM_TC, st);
   RN_CUDA_CHECK_LAUNCH();
   return RN_OK;
 }
@@ -494,6 +496,7 @@ int launch_wgrad_tc(const WgradArgs& g, cudaStream_t st) {
   if (ctas > blocks64) ctas = (int)blocks64;
   int64_t rows_per = ((blocks64 + ctas - 1) / ctas) * 64;
   const unsigned grid = (unsigned)((g.m + rows_per - 1) / rows_per);
+  rn_prof_begin(RN_PROF_WGRAD_TC, st, g.algo_flops);
   if (x3) {
     static bool once = false;
     if (!once) { if ((rc = set_smem(wgrad_tc_kernel<3>, Cfg<3>::kSmemBytes))) return rc; once = true; }
@@ -503,6 +506,7 @@ int launch_wgrad_tc(const WgradArgs& g, cudaStream_t st) {
     if (!once) { if ((rc = set_smem(wgrad_tc_kernel<1>, Cfg<1>::kSmemBytes))) return rc; once = true; }
     wgrad_tc_kernel<1><<<grid, 256, Cfg<1>::kSmemBytes, st>>>(maps, g.m, rows_per, g.n0, g.n_real, g.kx, g.k_real, g.out, g.out_ld);
   }
+  rn_prof_end(RN_PROF_WGRAD_TC, st);
   RN_CUDA_CHECK_LAUNCH();
   return RN_OK;
 }

@@ -19,6 +19,72 @@ int rn_set_cuda_error(cudaError_t e, const char* file, int line) {
   return RN_ERR_CUDA;
 }
 
+// ---- instrumentation: launch counter and per-class CUDA-event timing --------------------------
+#include <atomic>
+#include <mutex>
+#include <vector>
+static std::atomic<long long> g_launches{0};
+void rn_count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+namespace {
+struct ProfClass {
+  std::vector<cudaEvent_t> ev;  // pairs: start, stop
+  size_t used = 0;
+  double flops = 0.0;
+};
+bool g_prof_on = false;
+ProfClass g_prof[RN_PROF_NUM];
+std::mutex g_prof_mu;
+}  // namespace
+
+void rn_prof_begin(int cls, cudaStream_t st, double algo_flops) {
+  if (!g_prof_on) return;
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  ProfClass& p = g_prof[cls];
+  if (p.used + 2 > p.ev.size()) {
+    for (int i = 0; i < 2; ++i) {
+      cudaEvent_t e;
+      cudaEventCreate(&e);
+      p.ev.push_back(e);
+    }
+  }
+  cudaEventRecord(p.ev[p.used], st);
+  p.flops += algo_flops;
+}
+void rn_prof_end(int cls, cudaStream_t st) {
+  if (!g_prof_on) return;
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  ProfClass& p = g_prof[cls];
+  cudaEventRecord(p.ev[p.used + 1], st);
+  p.used += 2;
+}
+
+extern "C" int64_t rn_launch_count(void) { return (int64_t)g_launches.load(); }
+extern "C" int rn_prof_enable(int on) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  g_prof_on = on != 0;
+  return RN_OK;
+}
+extern "C" int rn_prof_summary(int cls, int64_t* launches, double* total_ms, double* algo_flops) {
+  if (cls < 0 || cls >= RN_PROF_NUM) return rn_set_error(RN_ERR_ARG, "rn_prof_summary: bad class");
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  ProfClass& p = g_prof[cls];
+  double ms = 0.0;
+  for (size_t i = 0; i + 1 < p.used; i += 2) {
+    cudaError_t e = cudaEventSynchronize(p.ev[i + 1]);
+    if (e != cudaSuccess) return rn_set_cuda_error(e, __FILE__, __LINE__);
+    float t = 0.f;
+    cudaEventElapsedTime(&t, p.ev[i], p.ev[i + 1]);
+    ms += t;
+  }
+  if (launches) *launches = (int64_t)(p.used / 2);
+  if (total_ms) *total_ms = ms;
+  if (algo_flops) *algo_flops = p.flops;
+  p.used = 0;
+  p.flops = 0.0;
+  return RN_OK;
+}
+
 namespace rn {
 namespace {
 
@@ -152,6 +218,7 @@ struct Ctx {
   cudaStream_t st;
   MlpScalars sc;
   int impl;
+  bool algo = true;  // launches carry algorithmic FLOPs (false while recomputing activations in backward)
 };
 
 // y = act(W x + b) for chain layer l; input a1 (+ skip input a2)
@@ -167,6 +234,7 @@ int fwd_layer(const Ctx& c, int l, int64_t rows, ActBuf a1, ActBuf a2, GemmEpilo
   g.b_hi = c.pk.wf_hi(l); g.b_lo = c.pk.wf_lo(l); g.b_ld = d.k_tot();
   epi.bias = c.pk.bias(l);
   g.epi = epi;
+  g.algo_flops = c.algo ? 2.0 * (double)rows * d.n_real * (d.k1_real + d.k2_real) : 0.0;
   return launch_gemm(g, c.st);
 }
 
@@ -182,6 +250,10 @@ int dgrad_layer(const Ctx& c, int l, int64_t rows, ActBuf dy1, int k1, int dy1_v
   g.a2 = dy2; g.k2 = k2; g.a2_valid = dy2_valid;
   g.b_hi = c.pk.wt_hi(l, in_row0); g.b_lo = c.pk.wt_lo(l, in_row0); g.b_ld = layer_def(l).nt_pad;
   g.epi = epi;
+  {
+    LayerDef d = layer_def(l);
+    g.algo_flops = c.algo ? 2.0 * (double)rows * d.n_real * (in_row0 == 0 ? d.k1_real : d.k2_real) : 0.0;
+  }
   return launch_gemm(g, c.st);
 }
 
@@ -252,10 +324,13 @@ int wgrad_layer(const Ctx& c, Workspace& w, int l, int64_t rows, ActBuf dy, int 
     g.dy = dy; g.dy_valid = dy_valid; g.n0 = n0; g.n_real = n_real_total;
     g.x = x1; g.x_valid = d.k1_pad; g.kx = d.k1_pad; g.k_real = d.k1_real;
     g.out = w.gW[l]; g.out_ld = d.k_tot();
+    const int nslab = n_real_total - n0 < 128 ? n_real_total - n0 : 128;
+    g.algo_flops = 2.0 * (double)rows * nslab * d.k1_real;
     RN_TRY(launch_wgrad(g, c.st));
     if (d.k2_pad) {
       g.x = x2; g.x_valid = d.k2_pad; g.kx = d.k2_pad; g.k_real = d.k2_real;
       g.out = w.gW[l] + d.k1_pad;
+      g.algo_flops = 2.0 * (double)rows * nslab * d.k2_real;
       RN_TRY(launch_wgrad(g, c.st));
     }
   }
@@ -296,8 +371,10 @@ int backward_chunk(const Ctx& c, Workspace& w, int64_t row0, int64_t rows, const
     a.prec = prec; a.impl = c.impl; a.m = rows;
     a.x = w.a(8); a.x_valid = 256; a.kx = 256; a.k_real = 256; a.out_ld = d.k_tot();
     a.dy = w.d_bott; a.dy_valid = 128; a.n0 = 0; a.n_real = 128; a.out = w.gW[kLayerH];
+    a.algo_flops = 2.0 * (double)rows * 128 * 256;
     RN_TRY(launch_wgrad(a, c.st));
     a.dy = w.d_scal; a.dy_valid = 16; a.n0 = 0; a.n_real = kHeadScalars; a.out = w.gW[kLayerH] + (size_t)128 * d.k_tot();
+    a.algo_flops = 2.0 * (double)rows * kHeadScalars * 256;
     RN_TRY(launch_wgrad(a, c.st));
     RN_TRY(launch_colsum(prec, w.d_bott, rows, 128, w.gB[kLayerH], c.st));
     RN_TRY(launch_colsum(prec, w.d_scal, rows, 16, w.gB[kLayerH] + 128, c.st));
@@ -451,7 +528,9 @@ extern "C" int rn_mlp_backward(const RnMlpConfig* cfg, const void* packed, const
     tmp.normals_pred = scratch + 2 * rc - row0 * 3;
     tmp.grad_pred = scratch + 5 * rc - row0 * 3;
     tmp.tint = scratch + 8 * rc - row0 * 3;
+    c.algo = false;
     RN_TRY(forward_chunk(c, w, row0, rows, tmp, false, false));
+    c.algo = true;
     RN_TRY(backward_chunk(c, w, row0, rows, *g));
   }
   // packed-layout gradients -> parameter gradients (+=)

@@ -113,7 +113,7 @@ def composite_bwd(density: Tensor, tdist: Tensor, dirs: Tensor, rgb: Tensor, dif
     if extras:
         d_np, d_ro, d_ti = torch.empty_like(normals_pred), torch.empty_like(roughness), torch.empty_like(tint)
     else:
-        d_np = d_ro = d_ti = density.new_empty((0,))
+        d_np, d_ro, d_ti = (density.new_empty((0,)) for _ in range(3))
     has_ge = extras and g_extras.numel() > 0
     _lib.check(lib.rn_composite_bwd(
         _ptr(density), _ptr(tdist), _ptr(dirs), _ptr(rgb), _ptr(diffuse), _ptr(specular),
@@ -127,10 +127,10 @@ def composite_bwd(density: Tensor, tdist: Tensor, dirs: Tensor, rgb: Tensor, dif
 @composite_bwd.register_fake
 def _(density, tdist, dirs, rgb, diffuse, specular, normals, normals_pred, roughness, tint, weights, comp, g_weights,
       g_comp, g_extras, bg, extras):
-    e = density.new_empty((0,))
+    e = lambda: density.new_empty((0,))
     return [torch.empty_like(density), torch.empty_like(rgb), torch.empty_like(diffuse), torch.empty_like(specular),
-            torch.empty_like(normals_pred) if extras else e, torch.empty_like(roughness) if extras else e,
-            torch.empty_like(tint) if extras else e]
+            torch.empty_like(normals_pred) if extras else e(), torch.empty_like(roughness) if extras else e(),
+            torch.empty_like(tint) if extras else e()]
 
 
 def _composite_setup(ctx, inputs, output):

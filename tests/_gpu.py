@@ -12,20 +12,16 @@ def to_dev(d):
     return {k: (v.to(DEV) if isinstance(v, torch.Tensor) else torch.tensor(v, device=DEV)) for k, v in d.items()}
 
 
-def build_model(precision, gin=None, mlp_kwargs=None, model_kwargs=None, config_kwargs=None):
-    """Model with the blender_refnerf.gin bindings (restated here: the gin files live in the reference tree,
-    which does not exist on the GPU box)."""
+GIN_FOR_CASE = {'blender_init': 'blender_refnerf.gin', 'blender_pert': 'blender_refnerf.gin',
+                'llff_geom': 'llff_refnerf_geometry_losses.gin'}
+
+
+def build_model(precision, gin='blender_refnerf.gin', mlp_kwargs=None, model_kwargs=None, config_kwargs=None):
+    """Model driven by this repo's configs/*.gin (same binding names/values as the reference's files)."""
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     configs.clear_bindings()
-    configs.bind('Model', num_levels=2, single_mlp=True, num_prop_samples=128, num_nerf_samples=128, anneal_slope=0.,
-                 dilation_multiplier=0., dilation_bias=0., single_jitter=False, resample_padding=0.01)
-    configs.bind('NerfMLP', net_depth=8, net_width=256, net_depth_viewdirs=8, net_width_viewdirs=256,
-                 basis_shape='octahedron', basis_subdivisions=1, disable_density_normals=False, enable_pred_normals=True,
-                 use_directional_enc=True, use_reflections=True, deg_view=5, enable_pred_roughness=True,
-                 use_diffuse_color=True, use_specular_tint=True, use_n_dot_v=True, bottleneck_width=128,
-                 bottleneck_noise=0.0, density_bias=0.5, max_deg_point=16)
-    configs.bind('Config', data_loss_type='mse', orientation_loss_mult=0.1, predicted_normal_loss_mult=3e-4,
-                 orientation_coarse_loss_mult=0.01, predicted_normal_coarse_loss_mult=3e-5, interlevel_loss_mult=0.0,
-                 data_coarse_loss_mult=0.1, data_loss_mult=1.0, batch_size=1024, render_chunk_size=4096)
+    configs.parse_gin_files_and_bindings([os.path.join(root, 'configs', gin)])
     configs.bind('NerfMLP', precision=precision, **(mlp_kwargs or {}))
     if model_kwargs:
         configs.bind('Model', **model_kwargs)

@@ -19,35 +19,33 @@ from tests._gpu import DEV, build_model, load_params, norm_rel, rays_obj, rel_er
 
 pytestmark = pytest.mark.gpu
 
-# (per-sample rel 99.9th pct, composited abs max, normals mean abs, grad norm-rel)
+# Limits per precision mode.  "rel" = |a-b| / (|b| + 1e-3 max|b|), 99.9th percentile over samples
+# (bounded heavy tails: a ReLU flip moves single samples); "abs" = max abs error.
 TOL = {
-    'fp32':   dict(sample=1e-4, comp=2e-5, normals_mean=2e-3, normals_p99=5e-2, grad=1e-3),
-    'bf16x3': dict(sample=1e-3, comp=1e-4, normals_mean=5e-3, normals_p99=1e-1, grad=1e-2),
-    'bf16':   dict(sample=1e-3, comp=1e-3, normals_mean=5e-2, normals_p99=1.0, grad=1e-2),
+    #          density/roughness rel | colours, tint, weights abs | unit normals_pred abs | composited abs | normals | grads
+    'fp32':   dict(rel=2e-4, colour=2e-5, npred=2e-4, comp=2e-5, normals_mean=2e-3, normals_p99=5e-2, grad=5e-3),
+    'bf16x3': dict(rel=1e-3, colour=1e-4, npred=1e-3, comp=1e-4, normals_mean=5e-3, normals_p99=1e-1, grad=1e-2),
+    'bf16':   dict(rel=1e-2, colour=1e-3, npred=2e-2, comp=1e-3, normals_mean=1e-1, normals_p99=2.0, grad=1e-1),
 }
-REPORT = {}
-
-
-def _mlp_kwargs(name):
-    return dict(srgb_mapping=False) if name == 'llff_geom' else {}
-
-
-def _cfg_kwargs(name):
-    if name == 'llff_geom':
-        return dict(srgb_mapping_when_rendering=True, srgb_mapping_type='norm_linear',
-                    predicted_normal_loss_mult=3e-5, predicted_normal_coarse_loss_mult=3e-6)
-    return {}
+LEVEL1 = 8.0   # level-1 samples sit on fenceposts resampled from level-0 weights: errors compound
 
 
 def _run(name, precision, mode):
+    from tests._gpu import GIN_FOR_CASE
     g, rays = load_case(name)
-    model, cfg = build_model(precision, mlp_kwargs=_mlp_kwargs(name), config_kwargs=_cfg_kwargs(name))
+    model, cfg = build_model(precision, gin=GIN_FOR_CASE[name])
     load_params(model, case_params(g))
     model.train(mode == 'train')
     r = rays_obj(dict(rays))
     with (torch.enable_grad() if mode == 'train' else torch.no_grad()):
         rend, hist = model(r, 1.0, True)
     return g, model, cfg, r, rend, hist
+
+
+def _report(key, rep):
+    os.makedirs('gpurun_out', exist_ok=True)
+    with open('gpurun_out/parity_report.jsonl', 'a') as f:
+        f.write(json.dumps({'case': key, **rep}) + '\n')
 
 
 @pytest.mark.parametrize('precision', ['fp32', 'bf16x3', 'bf16'])
@@ -58,31 +56,33 @@ def test_model_vs_reference_fixture(name, precision, mode):
         pytest.skip('plain bf16 is the throughput mode: gated at reference init only (SURVEY 7.4)')
     g, model, cfg, r, rend, hist = _run(name, precision, mode)
     tol = TOL[precision]
-    rep = {}
+    rep, bad = {}, []
+
+    def gate(key, val, lim):
+        rep[key] = float(val)
+        if not val <= lim:
+            bad.append((key, float(val), lim))
+
     for lvl in range(2):
-        # the interval fenceposts: level 0 is input-independent and bit-exact
+        f = LEVEL1 if lvl == 1 else 1.0
         sd = hist[lvl]['sdist'].cpu().numpy()
         ref_sd = g[f'{mode}_hist{lvl}_sdist']
         if lvl == 0:
-            assert np.array_equal(sd, ref_sd)
+            assert np.array_equal(sd, ref_sd)          # level-0 fenceposts: input independent, bit-exact
         else:
-            rep[f'sdist{lvl}'] = float(np.abs(sd - ref_sd).max())
-            assert rep[f'sdist{lvl}'] <= 5e-3
-        for k in ('density', 'rgb', 'diffuse', 'specular', 'tint', 'roughness', 'normals_pred', 'weights'):
-            a = hist[lvl][k].detach().cpu().numpy()
-            b = g[f'{mode}_hist{lvl}_{k}']
-            e = rel_err(a, b)
-            rep[f'{k}{lvl}_p999'] = float(np.quantile(e, 0.999))
-            rep[f'{k}{lvl}_max'] = float(e.max())
-            assert rep[f'{k}{lvl}_p999'] <= tol['sample'] * (10 if lvl == 1 else 1), (k, lvl, rep[f'{k}{lvl}_p999'])
+            gate('sdist1_abs', np.abs(sd - ref_sd).max(), 2e-3 if precision != 'bf16' else 2e-2)
+        for k in ('density', 'roughness'):
+            e = rel_err(hist[lvl][k].detach().cpu().numpy(), g[f'{mode}_hist{lvl}_{k}'])
+            gate(f'{k}{lvl}_rel_p999', np.quantile(e, 0.999), tol['rel'] * f)
+        for k in ('rgb', 'diffuse', 'specular', 'tint', 'weights'):
+            e = np.abs(hist[lvl][k].detach().cpu().numpy() - g[f'{mode}_hist{lvl}_{k}'])
+            gate(f'{k}{lvl}_abs_p999', np.quantile(e, 0.999), tol['colour'] * f)
+        e = np.abs(hist[lvl]['normals_pred'].detach().cpu().numpy() - g[f'{mode}_hist{lvl}_normals_pred'])
+        gate(f'normals_pred{lvl}_abs_p999', np.quantile(e, 0.999), tol['npred'] * f)
         if mode == 'train':
-            a = hist[lvl]['normals'].cpu().numpy()
-            b = g[f'{mode}_hist{lvl}_normals']
-            e = np.abs(a - b)
-            rep[f'normals{lvl}_mean'] = float(e.mean())
-            rep[f'normals{lvl}_p99'] = float(np.quantile(e, 0.99))
-            assert rep[f'normals{lvl}_mean'] <= tol['normals_mean'] * (4 if lvl == 1 else 1)
-            assert rep[f'normals{lvl}_p99'] <= tol['normals_p99']
+            e = np.abs(hist[lvl]['normals'].cpu().numpy() - g[f'{mode}_hist{lvl}_normals'])
+            gate(f'normals{lvl}_mean', e.mean(), tol['normals_mean'] * f)
+            gate(f'normals{lvl}_p99', np.quantile(e, 0.99), tol['normals_p99'])
         else:
             assert hist[lvl]['normals'] is None
         for k in ('rgb', 'diffuse', 'specular', 'distance', 'acc', 'normals_pred', 'tint', 'roughness', 'distance_mean',
@@ -90,16 +90,12 @@ def test_model_vs_reference_fixture(name, precision, mode):
             a = rend[lvl][k].detach().cpu().numpy()
             b = g[f'{mode}_rend{lvl}_{k}']
             assert a.shape == b.shape and a.dtype == b.dtype, (k, a.shape, b.shape, a.dtype, b.dtype)
-            err = float(np.abs(a - b).max())
-            rep[f'rend_{k}{lvl}'] = err
-            lim = tol['comp'] * (50 if 'percentile' in k or 'median' in k or 'distance' in k else 1) * (4 if lvl == 1 else 1)
-            assert err <= lim, (k, lvl, err, lim)
+            depthlike = 'distance' in k
+            gate(f'rend_{k}{lvl}', np.abs(a - b).max(), tol['comp'] * f * (50 if depthlike else 1))
         for k in ('ray_sdist', 'ray_weights', 'ray_rgbs'):
             assert tuple(rend[lvl][k].shape) == g[f'{mode}_rend{lvl}_{k}'].shape
-    REPORT[f'{name}/{precision}/{mode}'] = rep
-    os.makedirs('gpurun_out', exist_ok=True)
-    with open('gpurun_out/parity_report.json', 'w') as f:
-        json.dump(REPORT, f, indent=1)
+    _report(f'{name}/{precision}/{mode}', rep)
+    assert not bad, bad
 
 
 @pytest.mark.parametrize('precision', ['fp32', 'bf16x3', 'bf16'])
@@ -111,11 +107,10 @@ def test_gradients_vs_reference_fixture(name, precision):
     g, model, cfg, r, rend, hist = _run(name, precision, 'train')
     gt = torch.tensor(g['gt_rgb'], device=DEV)
     loss, _ = train_utils.total_loss(model, r.viewdirs, r.lossmult, gt, rend, hist, cfg)
-    assert abs(float(loss) - float(g['train_loss'])) <= 1e-3 * abs(float(g['train_loss'])) + 1e-6
+    assert abs(float(loss.detach()) - float(g['train_loss'])) <= 1e-3 * abs(float(g['train_loss'])) + 1e-6
     loss.backward()
     tol = TOL[precision]['grad']
     rep = {}
-    worst = 0.0
     for kname, p in model.nerf_mlp.named_parameters():
         ref_norm = float(g['grad_norm_' + kname])
         gn = float(p.grad.double().norm())
@@ -123,12 +118,9 @@ def test_gradients_vs_reference_fixture(name, precision):
         ref_sub = g['grad_sub_' + kname]
         e_norm = abs(gn - ref_norm) / max(ref_norm, 1e-30)
         e_sub = float(np.linalg.norm(sub - ref_sub) / max(np.linalg.norm(ref_sub), 1e-30))
-        rep[kname] = (e_norm, e_sub)
-        worst = max(worst, e_norm, e_sub)
-    REPORT[f'{name}/{precision}/grad'] = rep
-    with open('gpurun_out/parity_report.json', 'w') as f:
-        json.dump(REPORT, f, indent=1)
-    bad = {k: v for k, v in rep.items() if max(v) > tol}
+        rep[kname] = max(e_norm, e_sub)
+    _report(f'{name}/{precision}/grad', rep)
+    bad = {k: v for k, v in rep.items() if v > tol}
     assert not bad, bad
 
 
