@@ -112,7 +112,7 @@ typedef struct RnMlpConfig {
   float rgb_bias;
   float rgb_padding;        /* models.py:729                                               */
   int chunk_rows;           /* rows processed per internal chunk (multiple of 128)         */
-  int gemm_impl;            /* 0 = default for prec, 1 = force SIMT fp32-accumulate GEMMs  */
+  int gemm_impl;            /* 0 = default (fused chains in bf16), 1 = SIMT GEMMs, 2 = per-layer tcgen05 */
 } RnMlpConfig;
 
 /* bytes of the packed-weight blob / of the scratch workspace for the given chunk size */
@@ -164,7 +164,7 @@ RN_API int rn_gemm_bench(int64_t m, int prec, int impl, int iters, float* ms_out
  * rn_launch_count: kernels launched by this library since load (process-wide).
  * rn_prof_enable(1) makes the GEMM launchers bracket every launch with CUDA events on the launching
  * stream; rn_prof_summary(cls, ...) synchronises the recorded events and returns, for kernel class
- * cls (0 = tcgen05 fwd/dgrad GEMM, 1 = tcgen05 wgrad, 2 = SIMT GEMMs), the number of launches, their
+ * cls (0 = tcgen05 fwd/dgrad GEMM, 1 = tcgen05 wgrad, 2 = SIMT GEMMs, 3 = fused tcgen05 forward chain), the number of launches, their
  * summed device time in ms and the algorithmic FLOPs they carried, then clears the class. */
 RN_API int64_t rn_launch_count(void);
 RN_API int rn_prof_enable(int on);

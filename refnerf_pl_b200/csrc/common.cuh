@@ -20,7 +20,7 @@ int rn_set_cuda_error(cudaError_t e, const char* file, int line);
 int rn_set_error(int code, const char* msg);
 void rn_count_launch();
 // optional CUDA-event timing of kernel classes (bench.py roofline); no-ops unless rn_prof_enable(1)
-enum { RN_PROF_GEMM_TC = 0, RN_PROF_WGRAD_TC = 1, RN_PROF_GEMM_SIMT = 2, RN_PROF_NUM = 3 };
+enum { RN_PROF_GEMM_TC = 0, RN_PROF_WGRAD_TC = 1, RN_PROF_GEMM_SIMT = 2, RN_PROF_CHAIN_TC = 3, RN_PROF_NUM = 4 };
 void rn_prof_begin(int cls, cudaStream_t st, double algo_flops);
 void rn_prof_end(int cls, cudaStream_t st);
 
@@ -120,6 +120,16 @@ __device__ __forceinline__ float warp_scan_incl(float v, int lane) {
   for (int o = 1; o < 32; o <<= 1) {
     float t = __shfl_up_sync(RN_FULL, v, o);
     if (lane >= o) v += t;
+  }
+  return v;
+}
+
+// inclusive running max across the warp (exact, so any evaluation order gives the same result)
+__device__ __forceinline__ float warp_scan_max(float v, int lane) {
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    float t = __shfl_up_sync(RN_FULL, v, o);
+    if (lane >= o) v = fmaxf(v, t);
   }
   return v;
 }

@@ -51,6 +51,28 @@ struct WgradArgs {
   double algo_flops = 0.0;
 };
 
+// Fused forward chain (bf16, tcgen05): layers run back to back on one 128-row tile with the activations
+// resident in shared memory; only the last layer's epilogue (and optional activation saves) writes HBM.
+struct ChainLayerArgs {
+  int n = 0;                 // output columns; 256 for hidden layers
+  int kb_act = 0;            // 64-wide K blocks from the previous layer's activation (0 for layer 0, else 4)
+  int kb_in = 0;             // K blocks from the chain input tile (layer 0, skip layer)
+  const void* w = nullptr;   // bf16 weights [n, (kb_act + kb_in) * 64] K-major
+  int w_ld = 0;
+  const float* bias = nullptr;
+  void* save_hi = nullptr;   // optional bf16 [m,256] copy of the layer output
+};
+struct ChainArgs {
+  int64_t m = 0;
+  ActBuf in = {nullptr, nullptr, 0};
+  int in_cols = 0;           // 128 (x0) or 256 (v0)
+  int num_layers = 0;
+  ChainLayerArgs layer[9];
+  GemmEpilogue final_epi;    // epilogue of the last layer
+  double algo_flops = 0.0;
+};
+int launch_chain_fwd(const ChainArgs& a, cudaStream_t st);
+
 int launch_gemm(const GemmArgs& g, cudaStream_t st);
 int launch_wgrad(const WgradArgs& g, cudaStream_t st);
 

@@ -125,6 +125,85 @@ __device__ __forceinline__ uint32_t make_idesc(int n, int a_mn_major, int b_mn_m
   return d;
 }
 
+
+// ---- 256-bit global accesses (full 32-byte sectors per thread) and the 16-column epilogue ------------
+__device__ __forceinline__ void ldg256(const void* p, uint32_t* a) {
+  asm volatile("ld.global.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(a[0]), "=r"(a[1]), "=r"(a[2]), "=r"(a[3]), "=r"(a[4]), "=r"(a[5]), "=r"(a[6]), "=r"(a[7])
+               : "l"(p));
+}
+__device__ __forceinline__ void stg256(void* p, const uint32_t* a) {
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]),
+               "r"(a[4]), "r"(a[5]), "r"(a[6]), "r"(a[7])
+               : "memory");
+}
+
+// mask bits for 16 columns: bit i set iff mask[row, col+i] > 0 (bf16 hi plane: sign/zero test on the raw bits)
+__device__ __forceinline__ uint32_t mask_bits16(const uint32_t* m) {
+  uint32_t bits = 0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const uint32_t lo = m[i] & 0xffffu, hi = m[i] >> 16;
+    bits |= ((lo != 0u && lo < 0x8000u) ? 1u : 0u) << (2 * i);
+    bits |= ((hi != 0u && hi < 0x8000u) ? 1u : 0u) << (2 * i + 1);
+  }
+  return bits;
+}
+
+// epilogue for 16 consecutive columns of one row (bf16 modes); v holds the fp32 accumulators.
+template <int PREC>
+__device__ __forceinline__ void epi_store16(const GemmEpilogue& e, size_t row, int col, float* v, const uint32_t* mask_raw) {
+  if (e.bias) {
+    const float4* b4 = reinterpret_cast<const float4*>(e.bias + col);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float4 b = __ldg(b4 + i);
+      v[4 * i] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w;
+    }
+  }
+  if (e.relu) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
+  }
+  if (e.mask.hi) {
+    const uint32_t bits = mask_bits16(mask_raw);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = ((bits >> i) & 1u) ? v[i] : 0.f;
+  }
+  if (e.out.hi && col < e.out_cols) {
+    uint32_t h[8], l[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) split2(v[2 * i], v[2 * i + 1], h[i], l[i]);
+    stg256(reinterpret_cast<uint16_t*>(e.out.hi) + row * e.out.ld + col, h);
+    if (PREC == RN_PREC_BF16X3) stg256(reinterpret_cast<uint16_t*>(e.out.lo) + row * e.out.ld + col, l);
+  }
+  if (e.f32 && col + 16 > e.f32_col0 && col < e.f32_col0 + e.f32_cols) {
+    const int c0 = col - e.f32_col0;
+    float* p = e.f32 + row * e.f32_ld + c0;
+    if (c0 >= 0 && c0 + 16 <= e.f32_cols && (e.f32_ld & 7) == 0) {
+      uint32_t a[8];
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        if (e.f32_accum) {
+          ldg256(p + 8 * half, a);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) a[i] = __float_as_uint(__uint_as_float(a[i]) + v[8 * half + i]);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) a[i] = __float_as_uint(v[8 * half + i]);
+        }
+        stg256(p + 8 * half, a);
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const int c = c0 + i;
+        if (c >= 0 && c < e.f32_cols) p[i] = e.f32_accum ? (p[i] + v[i]) : v[i];
+      }
+    }
+  }
+}
+
 struct TcMaps {
   CUtensorMap a1_hi, a1_lo, a2_hi, a2_lo, b_hi, b_lo;
 };
@@ -250,16 +329,22 @@ gemm_tc_kernel(const __grid_constant__ TcMaps maps, int64_t m, int n, int kb1, i
       const uint32_t taddr = tmem_base + (uint32_t)buf * 256u + ((uint32_t)(q * 32) << 16);
       for (int c0 = 0; c0 < n; c0 += 32) {
         uint32_t r[32];
+        uint32_t mk[2][8];
         tmem_ld32(taddr + (uint32_t)c0, r);
+        if (epi.mask.hi && row < m) {   // issue the ReLU-mask loads while the TMEM load is in flight
+#pragma unroll
+          for (int h = 0; h < 2; ++h)
+            if (c0 + 16 * h < n) ldg256(reinterpret_cast<const uint16_t*>(epi.mask.hi) + (size_t)row * epi.mask.ld + c0 + 16 * h, mk[h]);
+        }
         tmem_ld_wait();
         if (row < m) {
 #pragma unroll
-          for (int g8 = 0; g8 < 4; ++g8) {
-            if (c0 + g8 * 8 < n) {
-              float v[8];
+          for (int h = 0; h < 2; ++h) {
+            if (c0 + 16 * h < n) {
+              float v[16];
 #pragma unroll
-              for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(r[g8 * 8 + e]);
-              epi_store8<PREC>(epi, (size_t)row, c0 + g8 * 8, v);
+              for (int e = 0; e < 16; ++e) v[e] = __uint_as_float(r[16 * h + e]);
+              epi_store16<PREC>(epi, (size_t)row, c0 + 16 * h, v, mk[h]);
             }
           }
         }
@@ -394,6 +479,219 @@ wgrad_tc_kernel(const __grid_constant__ WgMaps maps, int64_t m, int64_t rows_per
   if (warp == 2) tmem_dealloc(tmem_base, 256);
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Fused forward chain (bf16): up to 9 GEMM layers over one 128-row tile with the activations resident
+// in shared memory.  Hidden layers: TMEM accumulator -> bias + ReLU -> bf16 -> written back (128B
+// swizzle, K-major) as the next layer's A operand, 64 columns (= one K block) at a time so the next
+// layer's MMAs start as soon as its first K block exists.  Weights stream through a TMA ring; the
+// input tile (x0 / v0) stays resident for layer 0 and the skip layer.  Only the last layer (heads /
+// rgb head) and, in training, the optional activation saves touch global memory.
+// ---------------------------------------------------------------------------------------------
+constexpr int kChainMaxLayers = 9;
+struct ChainLayer {
+  int n;           // output columns (multiple of 16)
+  int kb_act;      // K blocks read from the resident activation tile (0 for layer 0, else 4)
+  int kb_in;       // K blocks read from the resident input tile (layer 0 and the skip layer)
+  int last_in_use; // 1 if this layer is the last reader of the input tile within the chain
+  const float* bias;
+  void* save_hi;   // optional global copy of this layer's output activation (bf16 [m,256]); hidden layers only
+};
+struct ChainParams {
+  int num_layers;
+  int in_kb;       // K blocks of the input tile (2: x0, 4: v0)
+  int stages;
+  int64_t m;
+  ChainLayer layer[kChainMaxLayers];
+  GemmEpilogue final_epi;  // epilogue of the last layer (heads / rgb head): global outputs
+};
+struct ChainMaps {
+  CUtensorMap in;
+  CUtensorMap w[kChainMaxLayers];
+};
+
+__global__ void __launch_bounds__(256, 1)
+chain_fwd_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__ ChainParams p) {
+  constexpr int kStageBytes = 256 * kBK * 2;  // 32 KB weight K block
+  constexpr int kBlkBytes = kBM * kBK * 2;    // 16 KB activation K block
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* s_act = smem;                               // 4 K blocks
+  uint8_t* s_in = s_act + 4 * kBlkBytes;               // in_kb K blocks
+  uint8_t* s_w = s_in + p.in_kb * kBlkBytes;           // weight ring
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_w + p.stages * kStageBytes);
+  uint64_t* w_full = bars;            // [stages]
+  uint64_t* w_empty = bars + 8;       // [stages]
+  uint64_t* a_ready = bars + 16;      // [4]
+  uint64_t* tfull = bars + 20;        // [2]
+  uint64_t* tempty = bars + 22;       // [2]
+  uint64_t* in_full = bars + 24;
+  uint64_t* in_empty = bars + 25;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 26);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t num_tiles = (p.m + kBM - 1) / kBM;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&maps.in);
+    for (int i = 0; i < p.num_layers; ++i) tma_prefetch_desc(&maps.w[i]);
+    for (int i = 0; i < p.stages; ++i) {
+      mbar_init(&w_full[i], 1);
+      mbar_init(&w_empty[i], 1);
+    }
+    for (int i = 0; i < 4; ++i) mbar_init(&a_ready[i], 4);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull[i], 1);
+      mbar_init(&tempty[i], 4);
+    }
+    mbar_init(in_full, 1);
+    mbar_init(in_empty, 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0 && lane == 0) {
+    // ===== TMA producer: input tile, then the weight K blocks of every layer in order =====
+    int stage = 0;
+    uint32_t phase = 0, in_phase = 0;
+    for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m0 = (int)(tile * kBM);
+      mbar_wait(in_empty, in_phase ^ 1);
+      mbar_arrive_expect_tx(in_full, (uint32_t)(p.in_kb * kBlkBytes));
+      for (int kb = 0; kb < p.in_kb; ++kb) tma_load_2d(s_in + kb * kBlkBytes, &maps.in, in_full, kb * kBK, m0);
+      in_phase ^= 1;
+      for (int l = 0; l < p.num_layers; ++l) {
+        const int nkb = p.layer[l].kb_act + p.layer[l].kb_in;
+        const uint32_t tx = (uint32_t)p.layer[l].n * kBK * 2;
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait(&w_empty[stage], phase ^ 1);
+          mbar_arrive_expect_tx(&w_full[stage], tx);
+          tma_load_2d(s_w + stage * kStageBytes, &maps.w[l], &w_full[stage], kb * kBK, 0);
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ===== MMA issuer =====
+    int stage = 0;
+    uint32_t phase = 0, in_phase = 0, act_phase = 0;
+    int buf = 0;
+    uint32_t tphase = 0;
+    for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      bool in_ready = false;
+      for (int l = 0; l < p.num_layers; ++l) {
+        const ChainLayer& L = p.layer[l];
+        const uint32_t idesc = make_idesc(L.n, 0, 0);
+        mbar_wait(&tempty[buf], tphase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)buf * 256u;
+        const int nkb = L.kb_act + L.kb_in;
+        for (int kb = 0; kb < nkb; ++kb) {
+          uint32_t sa;
+          if (kb < L.kb_act) {
+            mbar_wait(&a_ready[kb], act_phase);
+            sa = smem_u32(s_act + kb * kBlkBytes);
+          } else {
+            if (!in_ready) { mbar_wait(in_full, in_phase); in_ready = true; }
+            sa = smem_u32(s_in + (kb - L.kb_act) * kBlkBytes);
+          }
+          mbar_wait(&w_full[stage], phase);
+          tc_fence_after();
+          const uint32_t sb = smem_u32(s_w + stage * kStageBytes);
+#pragma unroll
+          for (int kk = 0; kk < kBK / kUmmaK; ++kk) {
+            const uint32_t koff = kk * kUmmaK * 2;
+            umma_bf16(tmem_d, make_desc(sa + koff, 16, 1024), make_desc(sb + koff, 16, 1024), idesc, (kb | kk) ? 1u : 0u);
+          }
+          umma_commit(&w_empty[stage]);
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tfull[buf]);
+        if (L.last_in_use) umma_commit(in_empty);
+        if (L.kb_act) act_phase ^= 1;
+        if (++buf == 2) { buf = 0; tphase ^= 1; }
+      }
+      in_phase ^= 1;
+    }
+  } else if (warp >= 4) {
+    // ===== epilogue warps =====
+    const int q = warp - 4;
+    int buf = 0;
+    uint32_t tphase = 0;
+    for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int r_in_tile = q * 32 + lane;
+      const int64_t row = tile * kBM + r_in_tile;
+      for (int l = 0; l < p.num_layers; ++l) {
+        const ChainLayer& L = p.layer[l];
+        mbar_wait(&tfull[buf], tphase);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + (uint32_t)buf * 256u + ((uint32_t)(q * 32) << 16);
+        if (l + 1 < p.num_layers) {
+          // hidden layer: 4 chunks of 64 columns -> swizzled K blocks of the activation tile
+          for (int j = 0; j < 4; ++j) {
+            uint32_t r[64];
+            tmem_ld32(taddr + (uint32_t)(j * 64), r);
+            tmem_ld32(taddr + (uint32_t)(j * 64 + 32), r + 32);
+            tmem_ld_wait();
+            uint32_t packed[32];
+            const float4* b4 = reinterpret_cast<const float4*>(L.bias + j * 64);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const float4 b = __ldg(b4 + i);
+              const float v0 = fmaxf(__uint_as_float(r[4 * i]) + b.x, 0.f), v1 = fmaxf(__uint_as_float(r[4 * i + 1]) + b.y, 0.f);
+              const float v2 = fmaxf(__uint_as_float(r[4 * i + 2]) + b.z, 0.f), v3 = fmaxf(__uint_as_float(r[4 * i + 3]) + b.w, 0.f);
+              packed[2 * i] = (uint32_t)float_to_bf16_bits(v0) | ((uint32_t)float_to_bf16_bits(v1) << 16);
+              packed[2 * i + 1] = (uint32_t)float_to_bf16_bits(v2) | ((uint32_t)float_to_bf16_bits(v3) << 16);
+            }
+            uint8_t* blk = s_act + j * kBlkBytes + r_in_tile * 128;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+              const int pos = c ^ (r_in_tile & 7);
+              *reinterpret_cast<uint4*>(blk + pos * 16) = make_uint4(packed[4 * c], packed[4 * c + 1], packed[4 * c + 2], packed[4 * c + 3]);
+            }
+            fence_proxy_async();   // make the generic-proxy smem writes visible to the tensor core (async proxy)
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&a_ready[j]);
+            if (L.save_hi && row < p.m) {
+              uint16_t* g = reinterpret_cast<uint16_t*>(L.save_hi) + (size_t)row * 256 + j * 64;
+#pragma unroll
+              for (int c = 0; c < 4; ++c) stg256(g + c * 16, packed + 8 * c);
+            }
+          }
+        } else {
+          for (int c0 = 0; c0 < L.n; c0 += 32) {
+            uint32_t r[32];
+            tmem_ld32(taddr + (uint32_t)c0, r);
+            tmem_ld_wait();
+            if (row < p.m) {
+#pragma unroll
+              for (int h = 0; h < 2; ++h) {
+                if (c0 + 16 * h < L.n) {
+                  float v[16];
+#pragma unroll
+                  for (int e = 0; e < 16; ++e) v[e] = __uint_as_float(r[16 * h + e]);
+                  epi_store16<RN_PREC_BF16>(p.final_epi, (size_t)row, c0 + 16 * h, v, nullptr);
+                }
+              }
+            }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty[buf]);
+        if (++buf == 2) { buf = 0; tphase ^= 1; }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, kTmemCols);
+}
+
 // ---------------------------------------------------------------------------------------------
 // host side: tensor maps + launches
 // ---------------------------------------------------------------------------------------------
@@ -477,6 +775,59 @@ int launch_gemm_tc(const GemmArgs& g, cudaStream_t st) {
     gemm_tc_kernel<1><<<grid, 256, Cfg<1>::kSmemBytes, st>>>(maps, g.m, g.n, g.k1 / kBK, g.k2 / kBK, g.epi);
   }
   rn_prof_end(RN_PROF_GEMM_TC, st);
+  RN_CUDA_CHECK_LAUNCH();
+  return RN_OK;
+}
+
+int launch_chain_fwd(const ChainArgs& a, cudaStream_t st) {
+  if (a.m <= 0) return RN_OK;
+  if (a.num_layers < 2 || a.num_layers > kChainMaxLayers) return rn_set_error(RN_ERR_ARG, "chain: 2..9 layers");
+  if (a.in_cols != 128 && a.in_cols != 256) return rn_set_error(RN_ERR_ARG, "chain: input tile must be 128 or 256 columns");
+  ChainMaps maps;
+  ChainParams p;
+  memset(&p, 0, sizeof(p));
+  int rc;
+  if ((rc = make_map(&maps.in, a.in.hi, a.m, a.in_cols, a.in.ld, kBM))) return rc;
+  p.num_layers = a.num_layers;
+  p.in_kb = a.in_cols / kBK;
+  p.m = a.m;
+  int last_in = 0;
+  for (int l = 0; l < a.num_layers; ++l)
+    if (a.layer[l].kb_in) last_in = l;
+  for (int l = 0; l < kChainMaxLayers; ++l) {
+    if (l < a.num_layers) {
+      const ChainLayerArgs& L = a.layer[l];
+      if (L.n % 16 || L.n > 256 || (l + 1 < a.num_layers && L.n != 256)) return rn_set_error(RN_ERR_ARG, "chain: bad layer width");
+      if ((l == 0) != (L.kb_act == 0) || (L.kb_act != 0 && L.kb_act != 4) || (L.kb_in != 0 && L.kb_in != p.in_kb))
+        return rn_set_error(RN_ERR_ARG, "chain: bad K structure");
+      const int ktot = (L.kb_act + L.kb_in) * kBK;
+      if ((rc = make_map(&maps.w[l], L.w, L.n, ktot, L.w_ld, L.n))) return rc;
+      p.layer[l].n = L.n;
+      p.layer[l].kb_act = L.kb_act;
+      p.layer[l].kb_in = L.kb_in;
+      p.layer[l].last_in_use = (l == last_in) ? 1 : 0;
+      p.layer[l].bias = L.bias;
+      p.layer[l].save_hi = L.save_hi;
+    } else {
+      memset(&maps.w[l], 0, sizeof(CUtensorMap));
+    }
+  }
+  p.final_epi = a.final_epi;
+  const int fixed = 4 * kBM * kBK * 2 + p.in_kb * kBM * kBK * 2;
+  p.stages = (232448 - 1024 - 512 - fixed) / (256 * kBK * 2);
+  if (p.stages > 8) p.stages = 8;
+  if (p.stages < 2) return rn_set_error(RN_ERR_ARG, "chain: not enough shared memory for the weight ring");
+  const int smem = fixed + p.stages * 256 * kBK * 2 + 1024 + 512;
+  static int smem_set = 0;
+  if (smem_set < smem) {
+    if ((rc = set_smem(chain_fwd_kernel, 232448))) return rc;
+    smem_set = 232448;
+  }
+  const int64_t tiles = (a.m + kBM - 1) / kBM;
+  const unsigned grid = (unsigned)(tiles < num_sms() ? tiles : num_sms());
+  rn_prof_begin(RN_PROF_CHAIN_TC, st, a.algo_flops);
+  chain_fwd_kernel<<<grid, 256, smem, st>>>(maps, p);
+  rn_prof_end(RN_PROF_CHAIN_TC, st);
   RN_CUDA_CHECK_LAUNCH();
   return RN_OK;
 }

@@ -218,6 +218,7 @@ struct Ctx {
   cudaStream_t st;
   MlpScalars sc;
   int impl;
+  bool chain = false;  // bf16: fused forward chains
   bool algo = true;  // launches carry algorithmic FLOPs (false while recomputing activations in backward)
 };
 
@@ -273,18 +274,50 @@ GemmEpilogue epi_f32(float* p, int ld, int cols, int accum) {
   return e;
 }
 
+// layers [l0, l0+8) + the head layer `lh` as one fused launch; `keep` != null saves every hidden activation
+int chain_layers(const Ctx& c, int l0, int lh, int64_t rows, ActBuf in, int in_cols, Workspace* keep, bool spatial,
+                 GemmEpilogue final_epi) {
+  ChainArgs a;
+  a.m = rows;
+  a.in = in;
+  a.in_cols = in_cols;
+  a.num_layers = 9;
+  double flops = 0.0;
+  for (int i = 0; i < 9; ++i) {
+    const int l = i < 8 ? l0 + i : lh;
+    LayerDef d = layer_def(l);
+    ChainLayerArgs& L = a.layer[i];
+    L.n = d.n_pad;
+    L.kb_act = i == 0 ? 0 : 4;
+    L.kb_in = (i == 0 ? d.k1_pad : d.k2_pad) / 64;
+    L.w = c.pk.wf_hi(l);
+    L.w_ld = d.k_tot();
+    L.bias = c.pk.bias(l);
+    L.save_hi = (keep && i < 8) ? (spatial ? keep->a(i + 1).hi : keep->b(i + 1).hi) : nullptr;
+    flops += 2.0 * (double)rows * d.n_real * (d.k1_real + d.k2_real);
+  }
+  final_epi.bias = c.pk.bias(lh);
+  a.final_epi = final_epi;
+  a.algo_flops = c.algo ? flops : 0.0;
+  return launch_chain_fwd(a, c.st);
+}
+
 // forward for one chunk; normals_out != nullptr runs the in-forward density-gradient pass
 int forward_chunk(const Ctx& c, Workspace& w, int64_t row0, int64_t rows, const RnMlpOutputs& o, bool want_normals,
                   bool write_outputs) {
   const int prec = c.cfg->prec;
+  const bool keep_spatial = w.nsp == 8;   // training forward / backward recompute: every activation is needed later
+  const bool keep_view = w.nvw == 8;
   const ActBuf none = {nullptr, nullptr, 0};
   RN_TRY(launch_encode(prec, c.tdist, c.origins, c.dirs, c.radii, c.s, row0, rows, w.x0, kEncPad, c.st));
-  for (int l = 0; l < 8; ++l)
-    RN_TRY(fwd_layer(c, l, rows, l == 0 ? w.x0 : w.a(l), l == 5 ? w.x0 : none, epi_act(w.a(l + 1), 256, 1)));
-  {
-    GemmEpilogue e = epi_act(w.v0, kBottleneck, 0);
-    e.f32 = w.heads_raw; e.f32_ld = 16; e.f32_col0 = kBottleneck; e.f32_cols = 16;
-    RN_TRY(fwd_layer(c, kLayerH, rows, w.a(8), none, e));
+  GemmEpilogue heads_epi = epi_act(w.v0, kBottleneck, 0);
+  heads_epi.f32 = w.heads_raw; heads_epi.f32_ld = 16; heads_epi.f32_col0 = kBottleneck; heads_epi.f32_cols = 16;
+  if (c.chain) {
+    RN_TRY(chain_layers(c, 0, kLayerH, rows, w.x0, kEncPad, keep_spatial ? &w : nullptr, true, heads_epi));
+  } else {
+    for (int l = 0; l < 8; ++l)
+      RN_TRY(fwd_layer(c, l, rows, l == 0 ? w.x0 : w.a(l), l == 5 ? w.x0 : none, epi_act(w.a(l + 1), 256, 1)));
+    RN_TRY(fwd_layer(c, kLayerH, rows, w.a(8), none, heads_epi));
   }
   if (want_normals) {
     // d raw_density / d x0 through the spatial net (models.py:603-609); result is a constant
@@ -304,9 +337,13 @@ int forward_chunk(const Ctx& c, Workspace& w, int64_t row0, int64_t rows, const 
   RN_TRY(launch_heads_prologue_fwd(prec, w.heads_raw, c.viewdirs, c.s, row0, rows, c.sc, w.v0, o.density + row0,
                                    o.normals_pred + row0 * 3, o.grad_pred + row0 * 3, o.roughness + row0,
                                    o.tint + row0 * 3, c.st));
-  for (int l = 0; l < 8; ++l)
-    RN_TRY(fwd_layer(c, kLayerV0 + l, rows, l == 0 ? w.v0 : w.b(l), l == 5 ? w.v0 : none, epi_act(w.b(l + 1), 256, 1)));
-  RN_TRY(fwd_layer(c, kLayerC, rows, w.b(8), none, epi_f32(w.rgb_raw, 4, 4, 0)));
+  if (c.chain) {
+    RN_TRY(chain_layers(c, kLayerV0, kLayerC, rows, w.v0, kViewPad, keep_view ? &w : nullptr, false, epi_f32(w.rgb_raw, 4, 4, 0)));
+  } else {
+    for (int l = 0; l < 8; ++l)
+      RN_TRY(fwd_layer(c, kLayerV0 + l, rows, l == 0 ? w.v0 : w.b(l), l == 5 ? w.v0 : none, epi_act(w.b(l + 1), 256, 1)));
+    RN_TRY(fwd_layer(c, kLayerC, rows, w.b(8), none, epi_f32(w.rgb_raw, 4, 4, 0)));
+  }
   if (write_outputs)
     RN_TRY(launch_color_fwd(w.rgb_raw, w.heads_raw, rows, c.sc, o.rgb + row0 * 3, o.diffuse + row0 * 3,
                             o.specular + row0 * 3, c.st));
@@ -407,7 +444,8 @@ int make_ctx(Ctx& c, const RnMlpConfig* cfg, const void* packed, const float* td
   c.st = (cudaStream_t)stream;
   c.sc = {cfg->srgb_mapping, cfg->srgb_normalization, cfg->density_bias, cfg->roughness_bias,
           cfg->rgb_premultiplier, cfg->rgb_bias, cfg->rgb_padding};
-  c.impl = cfg->gemm_impl;
+  c.impl = cfg->gemm_impl == 1 ? 1 : 0;
+  c.chain = cfg->prec == RN_PREC_BF16 && cfg->gemm_impl == 0;
   return RN_OK;
 }
 

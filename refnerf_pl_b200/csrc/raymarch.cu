@@ -55,12 +55,16 @@ resample_kernel(const float* __restrict__ sdist_in, const float* __restrict__ w_
   sum = warp_sum(sum);
   __syncwarp();
   // CDF: cw[j] = min(1, sum_{i<j} w_i), cw[0] = 0, cw[s_in] = 1 (stepfun.py:149-154)
-  float carry = 0.f;
+  // (a parallel prefix sum is not monotone to the last ulp; the running max restores the monotonicity a
+  //  sequential cumsum of non-negative terms has, which the binary search below relies on)
+  float carry = 0.f, cmax = 0.f;
   for (int base = 0; base < s_in; base += 32) {
     int i = base + lane;
     float w = (i < s_in) ? __fdiv_rn(cw[i + 1], sum) : 0.f;
     float c = warp_scan_incl(w, lane) + carry;
     carry = __shfl_sync(RN_FULL, c, 31);
+    c = fmaxf(warp_scan_max(c, lane), cmax);
+    cmax = __shfl_sync(RN_FULL, c, 31);
     if (i < s_in - 1) cw[i + 1] = fminf(c, 1.f);
   }
   if (lane == 0) {
@@ -231,12 +235,14 @@ composite_fwd_kernel(const float* __restrict__ density, const float* __restrict_
   if (pct_out) {
     // weighted_percentile (stepfun.py:294-307) on t_aug=[tdist, far], w_aug=[weights, bg_w]:
     // cw = [0, min(1, cumsum(weights)), 1]  (bg_w is the dropped last weight); fp64 interp (math.py:114-142)
-    float cr = 0.f;
+    float cr = 0.f, crmax = 0.f;
     for (int base = 0; base < s; base += 32) {
       const int i = base + lane;
       const float w = (i < s) ? ws[i] : 0.f;
-      const float c = warp_scan_incl(w, lane) + cr;
+      float c = warp_scan_incl(w, lane) + cr;
       cr = __shfl_sync(RN_FULL, c, 31);
+      c = fmaxf(warp_scan_max(c, lane), crmax);
+      crmax = __shfl_sync(RN_FULL, c, 31);
       if (i < s) cw[i + 1] = fminf(c, 1.f);
     }
     if (lane == 0) {

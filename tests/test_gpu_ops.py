@@ -181,7 +181,7 @@ def test_step_losses(ops, gold):
     (O.lossfun_outer(t, w, te, we_c) * cot).sum().backward()
     we_g = we.to(DEV).requires_grad_(True)
     (ops.lossfun_outer(t.to(DEV), w.to(DEV), te.to(DEV), we_g) * cot.to(DEV)).sum().backward()
-    assert (we_g.grad.cpu() - we_c.grad).abs().max() <= 1e-5
+    assert (we_g.grad.cpu() - we_c.grad).abs().max() <= 1e-4 * max(1.0, float(we_c.grad.abs().max()))
     d = ops.distortion(t.to(DEV), w.to(DEV))
     assert np.abs(d.cpu().numpy() - gold['dist_loss']).max() <= 1e-6
     w_c = w.clone().requires_grad_(True)
