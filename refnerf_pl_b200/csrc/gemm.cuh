@@ -51,27 +51,34 @@ struct WgradArgs {
   double algo_flops = 0.0;
 };
 
-// Fused forward chain (bf16, tcgen05): layers run back to back on one 128-row tile with the activations
-// resident in shared memory; only the last layer's epilogue (and optional activation saves) writes HBM.
-struct ChainLayerArgs {
-  int n = 0;                 // output columns; 256 for hidden layers
-  int kb_act = 0;            // 64-wide K blocks from the previous layer's activation (0 for layer 0, else 4)
-  int kb_in = 0;             // K blocks from the chain input tile (layer 0, skip layer)
+// Fused chain (bf16, tcgen05): a sequence of GEMM "ops" runs back to back on one 128-row tile with the
+// running activation resident in shared memory.  Hidden ops turn the TMEM accumulator into the next A
+// operand (forward: bias + ReLU; backward: ReLU mask read from a saved activation) and may also save it
+// to global memory; global ops run an ordinary GemmEpilogue.  Only weights stream through the TMA ring.
+struct ChainOpArgs {
+  int n = 0;                 // output columns; 256 for hidden ops
+  int kb_act = 0;            // 64-wide K blocks from the running activation (0 or 4)
+  int kb_in = 0;             // K blocks from the chain input tile (0 or all of them)
+  int kind = 0;              // 0 hidden, 1 global epilogue
+  int mode = 0;              // hidden: 0 bias + ReLU, 1 ReLU mask
+  int gepi = 0;              // global: epilogue index (0/1)
   const void* w = nullptr;   // bf16 weights [n, (kb_act + kb_in) * 64] K-major
   int w_ld = 0;
   const float* bias = nullptr;
-  void* save_hi = nullptr;   // optional bf16 [m,256] copy of the layer output
+  const void* mask = nullptr;  // bf16 [m,256] saved activation
+  void* save_hi = nullptr;     // optional bf16 [m,256] copy of the hidden result
 };
 struct ChainArgs {
   int64_t m = 0;
   ActBuf in = {nullptr, nullptr, 0};
-  int in_cols = 0;           // 128 (x0) or 256 (v0)
-  int num_layers = 0;
-  ChainLayerArgs layer[9];
-  GemmEpilogue final_epi;    // epilogue of the last layer
+  int in_cols = 0;           // K extent of the input tile: multiple of 64, <= 256
+  int in_valid = 0;          // valid columns of the input buffer (beyond: zero)
+  int num_ops = 0;
+  ChainOpArgs op[12];
+  GemmEpilogue gepi[2];
   double algo_flops = 0.0;
 };
-int launch_chain_fwd(const ChainArgs& a, cudaStream_t st);
+int launch_chain(const ChainArgs& a, cudaStream_t st);
 
 int launch_gemm(const GemmArgs& g, cudaStream_t st);
 int launch_wgrad(const WgradArgs& g, cudaStream_t st);

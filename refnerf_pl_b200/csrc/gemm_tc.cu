@@ -488,30 +488,34 @@ wgrad_tc_kernel(const __grid_constant__ WgMaps maps, int64_t m, int64_t rows_per
 // input tile (x0 / v0) stays resident for layer 0 and the skip layer.  Only the last layer (heads /
 // rgb head) and, in training, the optional activation saves touch global memory.
 // ---------------------------------------------------------------------------------------------
-constexpr int kChainMaxLayers = 9;
-struct ChainLayer {
-  int n;           // output columns (multiple of 16)
-  int kb_act;      // K blocks read from the resident activation tile (0 for layer 0, else 4)
-  int kb_in;       // K blocks read from the resident input tile (layer 0 and the skip layer)
-  int last_in_use; // 1 if this layer is the last reader of the input tile within the chain
-  const float* bias;
-  void* save_hi;   // optional global copy of this layer's output activation (bf16 [m,256]); hidden layers only
+constexpr int kChainMaxOps = 12;
+struct ChainOp {
+  int n;           // MMA N = output columns (multiple of 16)
+  int kb_act;      // K blocks read from the resident activation tile (0 or 4)
+  int kb_in;       // K blocks read from the resident input tile
+  int last_in_use; // this op is the last reader of the input tile
+  int kind;        // 0: hidden (result -> next activation tile in smem [+ global save]); 1: global epilogue
+  int mode;        // hidden transform: 0 = bias + ReLU (forward), 1 = ReLU mask from a saved activation (backward)
+  int gepi;        // kind 1: which global epilogue
+  const float* bias;       // mode 0
+  const uint16_t* mask;    // mode 1: bf16 [m,256]; positive entries pass the gradient
+  void* save_hi;           // optional bf16 [m,256] copy of the hidden result
 };
 struct ChainParams {
-  int num_layers;
-  int in_kb;       // K blocks of the input tile (2: x0, 4: v0)
+  int num_ops;
+  int in_kb;       // K blocks of the input tile (1..4)
   int stages;
   int64_t m;
-  ChainLayer layer[kChainMaxLayers];
-  GemmEpilogue final_epi;  // epilogue of the last layer (heads / rgb head): global outputs
+  ChainOp op[kChainMaxOps];
+  GemmEpilogue gepi[2];
 };
 struct ChainMaps {
   CUtensorMap in;
-  CUtensorMap w[kChainMaxLayers];
+  CUtensorMap w[kChainMaxOps];
 };
 
 __global__ void __launch_bounds__(256, 1)
-chain_fwd_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__ ChainParams p) {
+chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__ ChainParams p) {
   constexpr int kStageBytes = 256 * kBK * 2;  // 32 KB weight K block
   constexpr int kBlkBytes = kBM * kBK * 2;    // 16 KB activation K block
   extern __shared__ uint8_t smem_raw[];
@@ -528,13 +532,14 @@ chain_fwd_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__
   uint64_t* in_full = bars + 24;
   uint64_t* in_empty = bars + 25;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 26);
+  float* bias_s = reinterpret_cast<float*>(bars + 32);  // [256] bias of the op being drained
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t num_tiles = (p.m + kBM - 1) / kBM;
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&maps.in);
-    for (int i = 0; i < p.num_layers; ++i) tma_prefetch_desc(&maps.w[i]);
+    for (int i = 0; i < p.num_ops; ++i) tma_prefetch_desc(&maps.w[i]);
     for (int i = 0; i < p.stages; ++i) {
       mbar_init(&w_full[i], 1);
       mbar_init(&w_empty[i], 1);
@@ -555,7 +560,7 @@ chain_fwd_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0 && lane == 0) {
-    // ===== TMA producer: input tile, then the weight K blocks of every layer in order =====
+    // ===== TMA producer: input tile, then the weight K blocks of every op in order =====
     int stage = 0;
     uint32_t phase = 0, in_phase = 0;
     for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -564,9 +569,9 @@ chain_fwd_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__
       mbar_arrive_expect_tx(in_full, (uint32_t)(p.in_kb * kBlkBytes));
       for (int kb = 0; kb < p.in_kb; ++kb) tma_load_2d(s_in + kb * kBlkBytes, &maps.in, in_full, kb * kBK, m0);
       in_phase ^= 1;
-      for (int l = 0; l < p.num_layers; ++l) {
-        const int nkb = p.layer[l].kb_act + p.layer[l].kb_in;
-        const uint32_t tx = (uint32_t)p.layer[l].n * kBK * 2;
+      for (int l = 0; l < p.num_ops; ++l) {
+        const int nkb = p.op[l].kb_act + p.op[l].kb_in;
+        const uint32_t tx = (uint32_t)p.op[l].n * kBK * 2;
         for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(&w_empty[stage], phase ^ 1);
           mbar_arrive_expect_tx(&w_full[stage], tx);
@@ -578,13 +583,14 @@ chain_fwd_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__
   } else if (warp == 1 && lane == 0) {
     // ===== MMA issuer =====
     int stage = 0;
-    uint32_t phase = 0, in_phase = 0, act_phase = 0;
+    uint32_t phase = 0, in_phase = 0;
+    uint32_t hidden_done = 0;  // hidden ops issued so far == activation generations requested
     int buf = 0;
     uint32_t tphase = 0;
     for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       bool in_ready = false;
-      for (int l = 0; l < p.num_layers; ++l) {
-        const ChainLayer& L = p.layer[l];
+      for (int l = 0; l < p.num_ops; ++l) {
+        const ChainOp& L = p.op[l];
         const uint32_t idesc = make_idesc(L.n, 0, 0);
         mbar_wait(&tempty[buf], tphase ^ 1);
         tc_fence_after();
@@ -593,7 +599,7 @@ chain_fwd_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__
         for (int kb = 0; kb < nkb; ++kb) {
           uint32_t sa;
           if (kb < L.kb_act) {
-            mbar_wait(&a_ready[kb], act_phase);
+            mbar_wait(&a_ready[kb], (hidden_done - 1u) & 1u);   // generation produced by the latest hidden op
             sa = smem_u32(s_act + kb * kBlkBytes);
           } else {
             if (!in_ready) { mbar_wait(in_full, in_phase); in_ready = true; }
@@ -612,7 +618,7 @@ chain_fwd_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__
         }
         umma_commit(&tfull[buf]);
         if (L.last_in_use) umma_commit(in_empty);
-        if (L.kb_act) act_phase ^= 1;
+        if (L.kind == 0) ++hidden_done;
         if (++buf == 2) { buf = 0; tphase ^= 1; }
       }
       in_phase ^= 1;
@@ -625,27 +631,52 @@ chain_fwd_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__
     for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int r_in_tile = q * 32 + lane;
       const int64_t row = tile * kBM + r_in_tile;
-      for (int l = 0; l < p.num_layers; ++l) {
-        const ChainLayer& L = p.layer[l];
+      const bool row_ok = row < p.m;
+      for (int l = 0; l < p.num_ops; ++l) {
+        const ChainOp& L = p.op[l];
+        const bool hidden = L.kind == 0;
+        if (hidden && L.mode == 0) {
+          // stage this op's bias in shared memory (the 4 epilogue warps only: named barrier 1)
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          const int t = threadIdx.x - 128;
+          reinterpret_cast<float2*>(bias_s)[t] = __ldg(reinterpret_cast<const float2*>(L.bias) + t);
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+        }
         mbar_wait(&tfull[buf], tphase);
         tc_fence_after();
         const uint32_t taddr = tmem_base + (uint32_t)buf * 256u + ((uint32_t)(q * 32) << 16);
-        if (l + 1 < p.num_layers) {
-          // hidden layer: 4 chunks of 64 columns -> swizzled K blocks of the activation tile
+        if (hidden) {
+          // 4 chunks of 64 columns -> swizzled K blocks of the activation tile
           for (int j = 0; j < 4; ++j) {
             uint32_t r[64];
+            uint32_t mk[32];
             tmem_ld32(taddr + (uint32_t)(j * 64), r);
             tmem_ld32(taddr + (uint32_t)(j * 64 + 32), r + 32);
+            if (L.mode == 1 && row_ok) {
+              const uint16_t* mp = L.mask + (size_t)row * 256 + j * 64;
+#pragma unroll
+              for (int c = 0; c < 4; ++c) ldg256(mp + c * 16, mk + 8 * c);
+            }
             tmem_ld_wait();
             uint32_t packed[32];
-            const float4* b4 = reinterpret_cast<const float4*>(L.bias + j * 64);
+            if (L.mode == 0) {
+              const float4* b4 = reinterpret_cast<const float4*>(bias_s + j * 64);
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              const float4 b = __ldg(b4 + i);
-              const float v0 = fmaxf(__uint_as_float(r[4 * i]) + b.x, 0.f), v1 = fmaxf(__uint_as_float(r[4 * i + 1]) + b.y, 0.f);
-              const float v2 = fmaxf(__uint_as_float(r[4 * i + 2]) + b.z, 0.f), v3 = fmaxf(__uint_as_float(r[4 * i + 3]) + b.w, 0.f);
-              packed[2 * i] = (uint32_t)float_to_bf16_bits(v0) | ((uint32_t)float_to_bf16_bits(v1) << 16);
-              packed[2 * i + 1] = (uint32_t)float_to_bf16_bits(v2) | ((uint32_t)float_to_bf16_bits(v3) << 16);
+              for (int i = 0; i < 16; ++i) {
+                const float4 b = b4[i];
+                const float v0 = fmaxf(__uint_as_float(r[4 * i]) + b.x, 0.f), v1 = fmaxf(__uint_as_float(r[4 * i + 1]) + b.y, 0.f);
+                const float v2 = fmaxf(__uint_as_float(r[4 * i + 2]) + b.z, 0.f), v3 = fmaxf(__uint_as_float(r[4 * i + 3]) + b.w, 0.f);
+                packed[2 * i] = (uint32_t)float_to_bf16_bits(v0) | ((uint32_t)float_to_bf16_bits(v1) << 16);
+                packed[2 * i + 1] = (uint32_t)float_to_bf16_bits(v2) | ((uint32_t)float_to_bf16_bits(v3) << 16);
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) {
+                const uint32_t mlo = mk[i] & 0xffffu, mhi = mk[i] >> 16;
+                const bool plo = row_ok && mlo != 0u && mlo < 0x8000u, phi = row_ok && mhi != 0u && mhi < 0x8000u;
+                const float v0 = plo ? __uint_as_float(r[2 * i]) : 0.f, v1 = phi ? __uint_as_float(r[2 * i + 1]) : 0.f;
+                packed[i] = (uint32_t)float_to_bf16_bits(v0) | ((uint32_t)float_to_bf16_bits(v1) << 16);
+              }
             }
             uint8_t* blk = s_act + j * kBlkBytes + r_in_tile * 128;
 #pragma unroll
@@ -656,25 +687,26 @@ chain_fwd_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__
             fence_proxy_async();   // make the generic-proxy smem writes visible to the tensor core (async proxy)
             __syncwarp();
             if (lane == 0) mbar_arrive(&a_ready[j]);
-            if (L.save_hi && row < p.m) {
+            if (L.save_hi && row_ok) {
               uint16_t* g = reinterpret_cast<uint16_t*>(L.save_hi) + (size_t)row * 256 + j * 64;
 #pragma unroll
               for (int c = 0; c < 4; ++c) stg256(g + c * 16, packed + 8 * c);
             }
           }
         } else {
+          const GemmEpilogue& ge = p.gepi[L.gepi];
           for (int c0 = 0; c0 < L.n; c0 += 32) {
             uint32_t r[32];
             tmem_ld32(taddr + (uint32_t)c0, r);
             tmem_ld_wait();
-            if (row < p.m) {
+            if (row_ok) {
 #pragma unroll
               for (int h = 0; h < 2; ++h) {
                 if (c0 + 16 * h < L.n) {
                   float v[16];
 #pragma unroll
                   for (int e = 0; e < 16; ++e) v[e] = __uint_as_float(r[16 * h + e]);
-                  epi_store16<RN_PREC_BF16>(p.final_epi, (size_t)row, c0 + 16 * h, v, nullptr);
+                  epi_store16<RN_PREC_BF16>(ge, (size_t)row, c0 + 16 * h, v, nullptr);
                 }
               }
             }
@@ -779,54 +811,56 @@ int launch_gemm_tc(const GemmArgs& g, cudaStream_t st) {
   return RN_OK;
 }
 
-int launch_chain_fwd(const ChainArgs& a, cudaStream_t st) {
+int launch_chain(const ChainArgs& a, cudaStream_t st) {
   if (a.m <= 0) return RN_OK;
-  if (a.num_layers < 2 || a.num_layers > kChainMaxLayers) return rn_set_error(RN_ERR_ARG, "chain: 2..9 layers");
-  if (a.in_cols != 128 && a.in_cols != 256) return rn_set_error(RN_ERR_ARG, "chain: input tile must be 128 or 256 columns");
+  if (a.num_ops < 1 || a.num_ops > kChainMaxOps) return rn_set_error(RN_ERR_ARG, "chain: 1..12 ops");
+  if (a.in_cols % 64 || a.in_cols < 64 || a.in_cols > 256) return rn_set_error(RN_ERR_ARG, "chain: input tile must be 64..256 columns");
   ChainMaps maps;
   ChainParams p;
   memset(&p, 0, sizeof(p));
   int rc;
-  if ((rc = make_map(&maps.in, a.in.hi, a.m, a.in_cols, a.in.ld, kBM))) return rc;
-  p.num_layers = a.num_layers;
+  if ((rc = make_map(&maps.in, a.in.hi, a.m, a.in_valid, a.in.ld, kBM))) return rc;
+  p.num_ops = a.num_ops;
   p.in_kb = a.in_cols / kBK;
   p.m = a.m;
   int last_in = 0;
-  for (int l = 0; l < a.num_layers; ++l)
-    if (a.layer[l].kb_in) last_in = l;
-  for (int l = 0; l < kChainMaxLayers; ++l) {
-    if (l < a.num_layers) {
-      const ChainLayerArgs& L = a.layer[l];
-      if (L.n % 16 || L.n > 256 || (l + 1 < a.num_layers && L.n != 256)) return rn_set_error(RN_ERR_ARG, "chain: bad layer width");
-      if ((l == 0) != (L.kb_act == 0) || (L.kb_act != 0 && L.kb_act != 4) || (L.kb_in != 0 && L.kb_in != p.in_kb))
+  for (int l = 0; l < a.num_ops; ++l)
+    if (a.op[l].kb_in) last_in = l;
+  for (int l = 0; l < kChainMaxOps; ++l) {
+    if (l < a.num_ops) {
+      const ChainOpArgs& L = a.op[l];
+      if (L.n % 16 || L.n > 256 || (L.kind == 0 && L.n != 256)) return rn_set_error(RN_ERR_ARG, "chain: bad op width");
+      if ((L.kb_act != 0 && L.kb_act != 4) || (L.kb_in != 0 && L.kb_in != p.in_kb) || L.kb_act + L.kb_in == 0 ||
+          (l == 0 && L.kb_act != 0))
         return rn_set_error(RN_ERR_ARG, "chain: bad K structure");
       const int ktot = (L.kb_act + L.kb_in) * kBK;
       if ((rc = make_map(&maps.w[l], L.w, L.n, ktot, L.w_ld, L.n))) return rc;
-      p.layer[l].n = L.n;
-      p.layer[l].kb_act = L.kb_act;
-      p.layer[l].kb_in = L.kb_in;
-      p.layer[l].last_in_use = (l == last_in) ? 1 : 0;
-      p.layer[l].bias = L.bias;
-      p.layer[l].save_hi = L.save_hi;
+      ChainOp& o = p.op[l];
+      o.n = L.n; o.kb_act = L.kb_act; o.kb_in = L.kb_in; o.last_in_use = (l == last_in) ? 1 : 0;
+      o.kind = L.kind; o.mode = L.mode; o.gepi = L.gepi; o.bias = L.bias;
+      o.mask = reinterpret_cast<const uint16_t*>(L.mask); o.save_hi = L.save_hi;
+      if (L.kind == 0 && L.mode == 0 && !L.bias) return rn_set_error(RN_ERR_ARG, "chain: forward op without bias");
+      if (L.kind == 0 && L.mode == 1 && !L.mask) return rn_set_error(RN_ERR_ARG, "chain: backward op without mask");
     } else {
       memset(&maps.w[l], 0, sizeof(CUtensorMap));
     }
   }
-  p.final_epi = a.final_epi;
+  p.gepi[0] = a.gepi[0];
+  p.gepi[1] = a.gepi[1];
   const int fixed = 4 * kBM * kBK * 2 + p.in_kb * kBM * kBK * 2;
-  p.stages = (232448 - 1024 - 512 - fixed) / (256 * kBK * 2);
+  p.stages = (232448 - 1024 - 1280 - fixed) / (256 * kBK * 2);
   if (p.stages > 8) p.stages = 8;
   if (p.stages < 2) return rn_set_error(RN_ERR_ARG, "chain: not enough shared memory for the weight ring");
-  const int smem = fixed + p.stages * 256 * kBK * 2 + 1024 + 512;
-  static int smem_set = 0;
-  if (smem_set < smem) {
-    if ((rc = set_smem(chain_fwd_kernel, 232448))) return rc;
-    smem_set = 232448;
+  const int smem = fixed + p.stages * 256 * kBK * 2 + 1024 + 1280;
+  static bool smem_set = false;
+  if (!smem_set) {
+    if ((rc = set_smem(chain_kernel, 232448))) return rc;
+    smem_set = true;
   }
   const int64_t tiles = (a.m + kBM - 1) / kBM;
   const unsigned grid = (unsigned)(tiles < num_sms() ? tiles : num_sms());
   rn_prof_begin(RN_PROF_CHAIN_TC, st, a.algo_flops);
-  chain_fwd_kernel<<<grid, 256, smem, st>>>(maps, p);
+  chain_kernel<<<grid, 256, smem, st>>>(maps, p);
   rn_prof_end(RN_PROF_CHAIN_TC, st);
   RN_CUDA_CHECK_LAUNCH();
   return RN_OK;

@@ -150,7 +150,7 @@ struct Carver {
 };
 
 struct Workspace {
-  ActBuf x0, v0, sp[8], vw[8], g[2], d_bott, d_scal, d_rgb_raw;
+  ActBuf x0, v0, sp[8], vw[8], g[2], gs[8], dheads, d_bott, d_scal, d_rgb_raw;
   float *heads_raw, *rgb_raw, *gx0, *dv0f, *dcolor;
   float* gW[kNumLayers];
   float* gB[kNumLayers];
@@ -172,16 +172,24 @@ Workspace carve(void* base, int prec, int64_t rc, int mode) {
   for (int i = 0; i < w.nvw; ++i) w.vw[i] = c.act(prec, rc, 256);
   w.heads_raw = (float*)c.take((size_t)rc * 16 * 4);
   w.rgb_raw = (float*)c.take((size_t)rc * 4 * 4);
-  if (mode >= 1) {
+  if (mode == 1) {
     w.g[0] = c.act(prec, rc, 256);
     w.g[1] = c.act(prec, rc, 256);
-    w.gx0 = (float*)c.take((size_t)rc * 128 * 4);
   }
+  if (mode >= 1) w.gx0 = (float*)c.take((size_t)rc * 128 * 4);
   if (mode == 2) {
+    for (int i = 0; i < 8; ++i) w.gs[i] = c.act(prec, rc, 256);   // dY of the 8 layers of the net being back-propagated
+    w.g[0] = w.gs[0];
+    w.g[1] = w.gs[1];
     w.dv0f = (float*)c.take((size_t)rc * 256 * 4);
     w.dcolor = (float*)c.take((size_t)rc * 8 * 4);
-    w.d_bott = c.act(prec, rc, 128);
-    w.d_scal = c.act(prec, rc, 16);
+    // d heads = [d bottleneck (128) | d scalar heads (11, padded to 16) | unused]: one 192-wide buffer so the
+    // heads dgrad reads it as a single K extent
+    w.dheads = c.act(prec, rc, 192);
+    w.d_bott = w.dheads;
+    w.d_scal = w.dheads;
+    w.d_scal.hi = reinterpret_cast<uint8_t*>(w.dheads.hi) + 128 * elem_bytes(prec);
+    if (w.dheads.lo) w.d_scal.lo = reinterpret_cast<uint8_t*>(w.dheads.lo) + 128 * 2;
     w.d_rgb_raw = c.act(prec, rc, 16);
     for (int l = 0; l < kNumLayers; ++l) {
       LayerDef d = layer_def(l);
@@ -274,6 +282,12 @@ GemmEpilogue epi_f32(float* p, int ld, int cols, int accum) {
   return e;
 }
 
+double op_flops(int64_t rows, int l, bool skip_part, bool both) {
+  LayerDef d = layer_def(l);
+  const int k = both ? d.k1_real + d.k2_real : (skip_part ? d.k2_real : d.k1_real);
+  return 2.0 * (double)rows * d.n_real * k;
+}
+
 // layers [l0, l0+8) + the head layer `lh` as one fused launch; `keep` != null saves every hidden activation
 int chain_layers(const Ctx& c, int l0, int lh, int64_t rows, ActBuf in, int in_cols, Workspace* keep, bool spatial,
                  GemmEpilogue final_epi) {
@@ -281,25 +295,75 @@ int chain_layers(const Ctx& c, int l0, int lh, int64_t rows, ActBuf in, int in_c
   a.m = rows;
   a.in = in;
   a.in_cols = in_cols;
-  a.num_layers = 9;
+  a.in_valid = in_cols;
+  a.num_ops = 9;
   double flops = 0.0;
   for (int i = 0; i < 9; ++i) {
     const int l = i < 8 ? l0 + i : lh;
     LayerDef d = layer_def(l);
-    ChainLayerArgs& L = a.layer[i];
+    ChainOpArgs& L = a.op[i];
     L.n = d.n_pad;
     L.kb_act = i == 0 ? 0 : 4;
     L.kb_in = (i == 0 ? d.k1_pad : d.k2_pad) / 64;
+    L.kind = i < 8 ? 0 : 1;
+    L.mode = 0;
+    L.gepi = 0;
     L.w = c.pk.wf_hi(l);
     L.w_ld = d.k_tot();
     L.bias = c.pk.bias(l);
     L.save_hi = (keep && i < 8) ? (spatial ? keep->a(i + 1).hi : keep->b(i + 1).hi) : nullptr;
-    flops += 2.0 * (double)rows * d.n_real * (d.k1_real + d.k2_real);
+    flops += op_flops(rows, l, false, true);
   }
   final_epi.bias = c.pk.bias(lh);
-  a.final_epi = final_epi;
+  a.gepi[0] = final_epi;
   a.algo_flops = c.algo ? flops : 0.0;
-  return launch_chain_fwd(a, c.st);
+  return launch_chain(a, c.st);
+}
+
+// one backward (dgrad) op of a fused chain for layer l: rows [row0, ..) of the transposed weights
+ChainOpArgs bwd_op(const Ctx& c, int l, int in_row0, int n, int kb_act, int kb_in, const void* mask, void* save) {
+  ChainOpArgs L;
+  L.n = n;
+  L.kb_act = kb_act;
+  L.kb_in = kb_in;
+  L.kind = mask ? 0 : 1;
+  L.mode = 1;
+  L.w = c.pk.wt_hi(l, in_row0);
+  L.w_ld = layer_def(l).nt_pad;
+  L.mask = mask;
+  L.save_hi = save;
+  return L;
+}
+
+// d raw_density / d x0 through the 8 spatial layers, fused (seed tile = w.g[0])
+int normals_chain(const Ctx& c, Workspace& w, int64_t rows) {
+  ChainArgs a;
+  a.m = rows;
+  a.in = w.g[0];
+  a.in_cols = 256;
+  a.in_valid = 256;
+  int n = 0;
+  double flops = 0.0;
+  for (int l = 7; l >= 1; --l) {
+    if (l == 5) {
+      a.op[n] = bwd_op(c, 5, 256, kEncPad, 4, 0, nullptr, nullptr);
+      a.op[n].gepi = 0;
+      flops += op_flops(rows, 5, true, false);
+      ++n;
+    }
+    a.op[n] = bwd_op(c, l, 0, 256, l == 7 ? 0 : 4, l == 7 ? 4 : 0, w.a(l).hi, nullptr);
+    flops += op_flops(rows, l, false, false);
+    ++n;
+  }
+  a.op[n] = bwd_op(c, 0, 0, kEncPad, 4, 0, nullptr, nullptr);
+  a.op[n].gepi = 1;
+  flops += op_flops(rows, 0, false, false);
+  ++n;
+  a.num_ops = n;
+  a.gepi[0] = epi_f32(w.gx0, 128, 128, 0);
+  a.gepi[1] = epi_f32(w.gx0, 128, 128, 1);
+  a.algo_flops = c.algo ? flops : 0.0;
+  return launch_chain(a, c.st);
 }
 
 // forward for one chunk; normals_out != nullptr runs the in-forward density-gradient pass
@@ -322,14 +386,18 @@ int forward_chunk(const Ctx& c, Workspace& w, int64_t row0, int64_t rows, const 
   if (want_normals) {
     // d raw_density / d x0 through the spatial net (models.py:603-609); result is a constant
     RN_TRY(launch_density_grad_seed(prec, w.a(8), c.pk.wd(), w.g[0], rows, c.st));
-    int cur = 0;
-    for (int l = 7; l >= 1; --l) {
-      if (l == 5)
-        RN_TRY(dgrad_layer(c, l, rows, w.g[cur], 256, 256, none, 0, 0, 256, kEncPad, epi_f32(w.gx0, 128, 128, 0)));
-      RN_TRY(dgrad_layer(c, l, rows, w.g[cur], 256, 256, none, 0, 0, 0, 256, epi_masked(w.g[cur ^ 1], w.a(l))));
-      cur ^= 1;
+    if (c.chain) {
+      RN_TRY(normals_chain(c, w, rows));
+    } else {
+      int cur = 0;
+      for (int l = 7; l >= 1; --l) {
+        if (l == 5)
+          RN_TRY(dgrad_layer(c, l, rows, w.g[cur], 256, 256, none, 0, 0, 256, kEncPad, epi_f32(w.gx0, 128, 128, 0)));
+        RN_TRY(dgrad_layer(c, l, rows, w.g[cur], 256, 256, none, 0, 0, 0, 256, epi_masked(w.g[cur ^ 1], w.a(l))));
+        cur ^= 1;
+      }
+      RN_TRY(dgrad_layer(c, 0, rows, w.g[cur], 256, 256, none, 0, 0, 0, kEncPad, epi_f32(w.gx0, 128, 128, 1)));
     }
-    RN_TRY(dgrad_layer(c, 0, rows, w.g[cur], 256, 256, none, 0, 0, 0, kEncPad, epi_f32(w.gx0, 128, 128, 1)));
     RN_TRY(launch_ipe_grad_normals(w.gx0, 128, c.tdist, c.origins, c.dirs, c.radii, c.s, row0, rows,
                                    o.normals + row0 * 3, c.st));
   }
@@ -370,6 +438,92 @@ int wgrad_layer(const Ctx& c, Workspace& w, int l, int64_t rows, ActBuf dy, int 
       g.algo_flops = 2.0 * (double)rows * nslab * d.k2_real;
       RN_TRY(launch_wgrad(g, c.st));
     }
+  }
+  return RN_OK;
+}
+
+// backward of one chunk with fused dgrad chains (bf16): the chains save dY of every layer, the wgrads follow
+int backward_chunk_chain(const Ctx& c, Workspace& w, int64_t row0, int64_t rows, const RnMlpOutputs& g) {
+  const int prec = c.cfg->prec;
+  const ActBuf none = {nullptr, nullptr, 0};
+  auto off = [&](const float* p, int per) -> const float* { return p ? p + row0 * per : nullptr; };
+  RN_TRY(launch_color_bwd(prec, w.rgb_raw, w.heads_raw, rows, c.sc, off(g.rgb, 3), off(g.diffuse, 3), off(g.specular, 3),
+                          w.d_rgb_raw, w.dcolor, c.st));
+  {  // view net: rgb head, V7..V0
+    ChainArgs a;
+    a.m = rows;
+    a.in = w.d_rgb_raw;
+    a.in_cols = 64;
+    a.in_valid = 16;
+    int n = 0;
+    double flops = op_flops(rows, kLayerC, false, false);
+    a.op[n++] = bwd_op(c, kLayerC, 0, 256, 0, 1, w.b(8).hi, w.gs[7].hi);
+    for (int l = 7; l >= 1; --l) {
+      const int L = kLayerV0 + l;
+      if (l == 5) {
+        a.op[n] = bwd_op(c, L, 256, 256, 4, 0, nullptr, nullptr);
+        a.op[n].gepi = 0;
+        flops += op_flops(rows, L, true, false);
+        ++n;
+      }
+      a.op[n++] = bwd_op(c, L, 0, 256, 4, 0, w.b(l).hi, w.gs[l - 1].hi);
+      flops += op_flops(rows, L, false, false);
+    }
+    a.op[n] = bwd_op(c, kLayerV0, 0, 256, 4, 0, nullptr, nullptr);
+    a.op[n].gepi = 1;
+    flops += op_flops(rows, kLayerV0, false, false);
+    ++n;
+    a.num_ops = n;
+    a.gepi[0] = epi_f32(w.dv0f, 256, 256, 0);
+    a.gepi[1] = epi_f32(w.dv0f, 256, 256, 1);
+    a.algo_flops = flops;
+    RN_TRY(launch_chain(a, c.st));
+  }
+  RN_TRY(wgrad_layer(c, w, kLayerC, rows, w.d_rgb_raw, 16, 3, w.b(8), none));
+  RN_TRY(launch_colsum(prec, w.d_rgb_raw, rows, 16, w.gB[kLayerC], c.st));
+  for (int l = 7; l >= 0; --l) {
+    const int L = kLayerV0 + l;
+    RN_TRY(wgrad_layer(c, w, L, rows, w.gs[l], 256, 256, l == 0 ? w.v0 : w.b(l), l == 5 ? w.v0 : none));
+    RN_TRY(launch_colsum(prec, w.gs[l], rows, 256, w.gB[L], c.st));
+  }
+  RN_TRY(launch_f32_to_act(prec, w.dv0f, 256, 0, rows, 128, w.d_bott, c.st));
+  RN_TRY(launch_heads_prologue_bwd(prec, w.heads_raw, c.viewdirs, c.s, row0, rows, c.sc, w.dv0f, w.dcolor,
+                                   off(g.density, 1), off(g.normals_pred, 3), off(g.grad_pred, 3), off(g.roughness, 1),
+                                   off(g.tint, 3), w.d_scal, c.st));
+  {  // spatial net: heads, S7..S1 (no gradient w.r.t. x0 is needed: sdist is detached)
+    ChainArgs a;
+    a.m = rows;
+    a.in = w.dheads;
+    a.in_cols = 192;
+    a.in_valid = 144;
+    int n = 0;
+    double flops = op_flops(rows, kLayerH, false, false);
+    a.op[n++] = bwd_op(c, kLayerH, 0, 256, 0, 3, w.a(8).hi, w.gs[7].hi);
+    for (int l = 7; l >= 1; --l) {
+      a.op[n++] = bwd_op(c, l, 0, 256, 4, 0, w.a(l).hi, w.gs[l - 1].hi);
+      flops += op_flops(rows, l, false, false);
+    }
+    a.num_ops = n;
+    a.algo_flops = flops;
+    RN_TRY(launch_chain(a, c.st));
+  }
+  {
+    LayerDef d = layer_def(kLayerH);
+    WgradArgs a;
+    a.prec = prec; a.impl = c.impl; a.m = rows;
+    a.x = w.a(8); a.x_valid = 256; a.kx = 256; a.k_real = 256; a.out_ld = d.k_tot();
+    a.dy = w.d_bott; a.dy_valid = 128; a.n0 = 0; a.n_real = 128; a.out = w.gW[kLayerH];
+    a.algo_flops = 2.0 * (double)rows * 128 * 256;
+    RN_TRY(launch_wgrad(a, c.st));
+    a.dy = w.d_scal; a.dy_valid = 16; a.n0 = 0; a.n_real = kHeadScalars; a.out = w.gW[kLayerH] + (size_t)128 * d.k_tot();
+    a.algo_flops = 2.0 * (double)rows * kHeadScalars * 256;
+    RN_TRY(launch_wgrad(a, c.st));
+    RN_TRY(launch_colsum(prec, w.d_bott, rows, 128, w.gB[kLayerH], c.st));
+    RN_TRY(launch_colsum(prec, w.d_scal, rows, 16, w.gB[kLayerH] + 128, c.st));
+  }
+  for (int l = 7; l >= 0; --l) {
+    RN_TRY(wgrad_layer(c, w, l, rows, w.gs[l], 256, 256, l == 0 ? w.x0 : w.a(l), l == 5 ? w.x0 : none));
+    RN_TRY(launch_colsum(prec, w.gs[l], rows, 256, w.gB[l], c.st));
   }
   return RN_OK;
 }
@@ -569,7 +723,11 @@ extern "C" int rn_mlp_backward(const RnMlpConfig* cfg, const void* packed, const
     c.algo = false;
     RN_TRY(forward_chunk(c, w, row0, rows, tmp, false, false));
     c.algo = true;
-    RN_TRY(backward_chunk(c, w, row0, rows, *g));
+    if (c.chain) {
+      RN_TRY(backward_chunk_chain(c, w, row0, rows, *g));
+    } else {
+      RN_TRY(backward_chunk(c, w, row0, rows, *g));
+    }
   }
   // packed-layout gradients -> parameter gradients (+=)
   for (int l = 0; l < kNumLayers; ++l) {

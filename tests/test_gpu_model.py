@@ -151,6 +151,27 @@ def test_fused_chain_matches_per_layer_gemms():
             assert torch.equal(ra[lvl]['rgb'], rb[lvl]['rgb'])
 
 
+def test_fused_backward_chain_matches_per_layer_gemms():
+    """bf16 backward: fused dgrad chains vs per-layer kernels (same arithmetic; only the wgrad atomics reorder)."""
+    from refnerf_pl_b200 import synthetic, train_utils
+    p = O.init_params(seed=5, bias_std=0.1, weight_scale=1.2)
+    rays = synthetic.blender_rays(600, seed=10)
+    gt = torch.tensor(synthetic.gt_rgb(600, 10), device=DEV)
+    grads = {}
+    for impl in (0, 2):
+        model, cfg = build_model('bf16', mlp_kwargs=dict(gemm_impl=impl, chunk_rows=32768))
+        load_params(model, p)
+        model.train(True)
+        r = rays_obj(rays)
+        rend, hist = model(r, 1.0, True)
+        loss, _ = train_utils.total_loss(model, r.viewdirs, r.lossmult, gt, rend, hist, cfg)
+        loss.backward()
+        grads[impl] = {k: v.grad.clone() for k, v in model.nerf_mlp.named_parameters()}
+    for k in grads[0]:
+        a, b = grads[0][k].double(), grads[2][k].double()
+        assert float((a - b).norm()) <= 1e-4 * float(b.norm()) + 1e-12, (k, float((a - b).norm() / b.norm()))
+
+
 def test_checkpoint_names_match_reference():
     model, _ = build_model('fp32')
     sd = model.state_dict()
