@@ -48,6 +48,8 @@ struct WgradArgs {
   int k_real = 0;
   float* out = nullptr;  // dW (fp32), row-major [.., out_ld], element (n, j) at out[n*out_ld + j]
   int out_ld = 0;
+  int all_slabs = 0;          // bf16 tcgen05 only: cover every 128-wide slab of dY (n_real <= 256) in one launch
+  float* bias_out = nullptr;  // with all_slabs: also accumulate the bias gradient (column sums of dY) here
   double algo_flops = 0.0;
 };
 

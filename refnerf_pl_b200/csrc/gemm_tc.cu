@@ -480,6 +480,143 @@ wgrad_tc_kernel(const __grid_constant__ WgMaps maps, int64_t m, int64_t rows_per
 }
 
 
+
+// ---------------------------------------------------------------------------------------------
+// wgrad, bf16, full dY width in one pass: dW[0:n_real, 0:kx] += dY^T X with up to two 128-feature slabs
+// of dY accumulating into separate TMEM buffers (X is read once), and the bias gradient (column sums
+// of dY) computed by the otherwise idle epilogue warps straight from the staged dY tiles.
+// ---------------------------------------------------------------------------------------------
+template <int NSLAB>
+__global__ void __launch_bounds__(256, 1)
+wgrad2_tc_kernel(const __grid_constant__ WgMaps maps, int64_t m, int64_t rows_per_cta, int n_real, int kx, int k_real,
+                 int stages, float* __restrict__ out, int out_ld, float* __restrict__ bias_out) {
+  constexpr int kRowBlk = 64;
+  constexpr int kBoxBytes = kRowBlk * 128;
+  constexpr int kDyBytes = 2 * NSLAB * kBoxBytes;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int xboxes = kx / 64;
+  const int stage_bytes = kDyBytes + xboxes * kBoxBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + stages * stage_bytes);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + 8;
+  uint64_t* tfull = bars + 16;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 17);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t r_begin = (int64_t)blockIdx.x * rows_per_cta;
+  const int64_t r_end = min(m, r_begin + rows_per_cta);
+  const int nblk = r_end > r_begin ? (int)((r_end - r_begin + kRowBlk - 1) / kRowBlk) : 0;
+  const bool do_bias = bias_out != nullptr;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&maps.dy_hi);
+    tma_prefetch_desc(&maps.x_hi);
+    for (int i = 0; i < stages; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], do_bias ? 5 : 1);
+    }
+    mbar_init(&tfull[0], 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, NSLAB * 256);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  if (nblk > 0) {
+    if (warp == 0 && lane == 0) {
+      const uint32_t stage_tx = (uint32_t)stage_bytes;
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int b = 0; b < nblk; ++b) {
+        mbar_wait(&empty[stage], phase ^ 1);
+        uint8_t* sbase = smem + stage * stage_bytes;
+        mbar_arrive_expect_tx(&full[stage], stage_tx);
+        const int r0 = (int)(r_begin + (int64_t)b * kRowBlk);
+        for (int i = 0; i < 2 * NSLAB; ++i) tma_load_2d(sbase + i * kBoxBytes, &maps.dy_hi, &full[stage], i * 64, r0);
+        for (int i = 0; i < xboxes; ++i) tma_load_2d(sbase + kDyBytes + i * kBoxBytes, &maps.x_hi, &full[stage], i * 64, r0);
+        if (++stage == stages) { stage = 0; phase ^= 1; }
+      }
+    } else if (warp == 1 && lane == 0) {
+      const uint32_t idesc = make_idesc(kx, 1, 1);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int b = 0; b < nblk; ++b) {
+        mbar_wait(&full[stage], phase);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem + stage * stage_bytes);
+        const uint32_t sb = sa + kDyBytes;
+#pragma unroll
+        for (int kk = 0; kk < kRowBlk / kUmmaK; ++kk) {
+          const uint32_t koff = kk * kUmmaK * 128;
+          const uint64_t db = make_desc(sb + koff, kBoxBytes, 1024);
+#pragma unroll
+          for (int sl = 0; sl < NSLAB; ++sl)
+            umma_bf16(tmem_base + sl * 256, make_desc(sa + sl * 2 * kBoxBytes + koff, kBoxBytes, 1024), db, idesc,
+                      (b | kk) ? 1u : 0u);
+        }
+        umma_commit(&empty[stage]);
+        if (++stage == stages) { stage = 0; phase ^= 1; }
+      }
+      umma_commit(&tfull[0]);
+    } else if (warp >= 4) {
+      const int q = warp - 4;
+      if (do_bias) {
+        // column sums of dY from the staged (128B-swizzled) tiles: thread t owns features 2t, 2t+1
+        const int t = threadIdx.x - 128;
+        const bool active = t < NSLAB * 64;
+        const int f = 2 * t;
+        const int box = f >> 6, fi = f & 63;
+        float s0 = 0.f, s1 = 0.f;
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int b = 0; b < nblk; ++b) {
+          mbar_wait(&full[stage], phase);
+          if (active) {
+            const uint8_t* base = smem + stage * stage_bytes + box * kBoxBytes + (fi & 7) * 2;
+#pragma unroll 8
+            for (int r = 0; r < kRowBlk; ++r) {
+              const uint32_t v = *reinterpret_cast<const uint32_t*>(base + r * 128 + ((((fi >> 3) ^ (r & 7))) << 4));
+              s0 += __uint_as_float(v << 16);
+              s1 += __uint_as_float(v & 0xffff0000u);
+            }
+          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&empty[stage]);
+          if (++stage == stages) { stage = 0; phase ^= 1; }
+        }
+        if (active) {
+          if (f < n_real) atomicAdd(bias_out + f, s0);
+          if (f + 1 < n_real) atomicAdd(bias_out + f + 1, s1);
+        }
+      }
+      mbar_wait(&tfull[0], 0);
+      tc_fence_after();
+#pragma unroll
+      for (int sl = 0; sl < NSLAB; ++sl) {
+        const int nrow = sl * 128 + q * 32 + lane;
+        const uint32_t taddr = tmem_base + sl * 256 + ((uint32_t)(q * 32) << 16);
+        for (int c0 = 0; c0 < kx; c0 += 32) {
+          uint32_t r[32];
+          tmem_ld32(taddr + (uint32_t)c0, r);
+          tmem_ld_wait();
+          if (nrow < n_real) {
+#pragma unroll
+            for (int e = 0; e < 32; ++e) {
+              const int j = c0 + e;
+              if (j < k_real) atomicAdd(out + (size_t)nrow * out_ld + j, __uint_as_float(r[e]));
+            }
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, NSLAB * 256);
+}
+
 // ---------------------------------------------------------------------------------------------
 // Fused forward chain (bf16): up to 9 GEMM layers over one 128-row tile with the activations resident
 // in shared memory.  Hidden layers: TMEM accumulator -> bias + ReLU -> bf16 -> written back (128B
@@ -866,9 +1003,46 @@ int launch_chain(const ChainArgs& a, cudaStream_t st) {
   return RN_OK;
 }
 
+int launch_wgrad2_tc(const WgradArgs& g, cudaStream_t st) {
+  WgMaps maps;
+  int rc;
+  if ((rc = make_map(&maps.dy_hi, g.dy.hi, g.m, g.dy_valid, g.dy.ld, 64))) return rc;
+  if ((rc = make_map(&maps.x_hi, g.x.hi, g.m, g.x_valid, g.x.ld, 64))) return rc;
+  memset(&maps.dy_lo, 0, sizeof(CUtensorMap));
+  memset(&maps.x_lo, 0, sizeof(CUtensorMap));
+  const int nslab = g.n_real > 128 ? 2 : 1;
+  const int stage_bytes = (2 * nslab + g.kx / 64) * 8192;
+  int stages = (232448 - 1024 - 512) / stage_bytes;
+  if (stages > 6) stages = 6;
+  const int smem = stages * stage_bytes + 1024 + 512;
+  int ctas = num_sms();
+  int64_t blocks64 = (g.m + 63) / 64;
+  if (ctas > blocks64) ctas = (int)blocks64;
+  int64_t rows_per = ((blocks64 + ctas - 1) / ctas) * 64;
+  const unsigned grid = (unsigned)((g.m + rows_per - 1) / rows_per);
+  static bool once = false;
+  if (!once) {
+    if ((rc = set_smem(wgrad2_tc_kernel<1>, 232448))) return rc;
+    if ((rc = set_smem(wgrad2_tc_kernel<2>, 232448))) return rc;
+    once = true;
+  }
+  rn_prof_begin(RN_PROF_WGRAD_TC, st, g.algo_flops);
+  if (nslab == 2)
+    wgrad2_tc_kernel<2><<<grid, 256, smem, st>>>(maps, g.m, rows_per, g.n_real, g.kx, g.k_real, stages, g.out, g.out_ld, g.bias_out);
+  else
+    wgrad2_tc_kernel<1><<<grid, 256, smem, st>>>(maps, g.m, rows_per, g.n_real, g.kx, g.k_real, stages, g.out, g.out_ld, g.bias_out);
+  rn_prof_end(RN_PROF_WGRAD_TC, st);
+  RN_CUDA_CHECK_LAUNCH();
+  return RN_OK;
+}
+
 int launch_wgrad_tc(const WgradArgs& g, cudaStream_t st) {
   if (g.m <= 0) return RN_OK;
   if (g.prec != RN_PREC_BF16 && g.prec != RN_PREC_BF16X3) return rn_set_error(RN_ERR_ARG, "wgrad_tc: bf16 modes only");
+  if (g.all_slabs) {
+    if (g.prec != RN_PREC_BF16 || g.n0 != 0 || g.n_real > 256) return rn_set_error(RN_ERR_ARG, "wgrad_tc: all_slabs needs bf16, n0 = 0, n_real <= 256");
+    return launch_wgrad2_tc(g, st);
+  }
   const bool x3 = g.prec == RN_PREC_BF16X3;
   WgMaps maps;
   int rc;

@@ -421,6 +421,28 @@ int forward_chunk(const Ctx& c, Workspace& w, int64_t row0, int64_t rows, const 
 int wgrad_layer(const Ctx& c, Workspace& w, int l, int64_t rows, ActBuf dy, int dy_valid, int n_real_total, ActBuf x1,
                 ActBuf x2) {
   LayerDef d = layer_def(l);
+  if (c.chain) {
+    // bf16 tcgen05: one launch per X source covers all of dY; the first one also produces the bias gradient
+    WgradArgs g;
+    g.prec = c.cfg->prec;
+    g.impl = c.impl;
+    g.m = rows;
+    g.dy = dy; g.dy_valid = dy_valid; g.n0 = 0; g.n_real = n_real_total;
+    g.all_slabs = 1;
+    g.bias_out = w.gB[l];
+    g.x = x1; g.x_valid = d.k1_pad; g.kx = d.k1_pad; g.k_real = d.k1_real;
+    g.out = w.gW[l]; g.out_ld = d.k_tot();
+    g.algo_flops = 2.0 * (double)rows * n_real_total * d.k1_real;
+    RN_TRY(launch_wgrad(g, c.st));
+    if (d.k2_pad) {
+      g.bias_out = nullptr;
+      g.x = x2; g.x_valid = d.k2_pad; g.kx = d.k2_pad; g.k_real = d.k2_real;
+      g.out = w.gW[l] + d.k1_pad;
+      g.algo_flops = 2.0 * (double)rows * n_real_total * d.k2_real;
+      RN_TRY(launch_wgrad(g, c.st));
+    }
+    return RN_OK;
+  }
   for (int n0 = 0; n0 < n_real_total; n0 += 128) {
     WgradArgs g;
     g.prec = c.cfg->prec;
@@ -479,12 +501,10 @@ int backward_chunk_chain(const Ctx& c, Workspace& w, int64_t row0, int64_t rows,
     a.algo_flops = flops;
     RN_TRY(launch_chain(a, c.st));
   }
-  RN_TRY(wgrad_layer(c, w, kLayerC, rows, w.d_rgb_raw, 16, 3, w.b(8), none));
-  RN_TRY(launch_colsum(prec, w.d_rgb_raw, rows, 16, w.gB[kLayerC], c.st));
+  RN_TRY(wgrad_layer(c, w, kLayerC, rows, w.d_rgb_raw, 16, 3, w.b(8), none));   // bias gradient fused
   for (int l = 7; l >= 0; --l) {
     const int L = kLayerV0 + l;
     RN_TRY(wgrad_layer(c, w, L, rows, w.gs[l], 256, 256, l == 0 ? w.v0 : w.b(l), l == 5 ? w.v0 : none));
-    RN_TRY(launch_colsum(prec, w.gs[l], rows, 256, w.gB[L], c.st));
   }
   RN_TRY(launch_f32_to_act(prec, w.dv0f, 256, 0, rows, 128, w.d_bott, c.st));
   RN_TRY(launch_heads_prologue_bwd(prec, w.heads_raw, c.viewdirs, c.s, row0, rows, c.sc, w.dv0f, w.dcolor,
@@ -507,24 +527,9 @@ int backward_chunk_chain(const Ctx& c, Workspace& w, int64_t row0, int64_t rows,
     a.algo_flops = flops;
     RN_TRY(launch_chain(a, c.st));
   }
-  {
-    LayerDef d = layer_def(kLayerH);
-    WgradArgs a;
-    a.prec = prec; a.impl = c.impl; a.m = rows;
-    a.x = w.a(8); a.x_valid = 256; a.kx = 256; a.k_real = 256; a.out_ld = d.k_tot();
-    a.dy = w.d_bott; a.dy_valid = 128; a.n0 = 0; a.n_real = 128; a.out = w.gW[kLayerH];
-    a.algo_flops = 2.0 * (double)rows * 128 * 256;
-    RN_TRY(launch_wgrad(a, c.st));
-    a.dy = w.d_scal; a.dy_valid = 16; a.n0 = 0; a.n_real = kHeadScalars; a.out = w.gW[kLayerH] + (size_t)128 * d.k_tot();
-    a.algo_flops = 2.0 * (double)rows * kHeadScalars * 256;
-    RN_TRY(launch_wgrad(a, c.st));
-    RN_TRY(launch_colsum(prec, w.d_bott, rows, 128, w.gB[kLayerH], c.st));
-    RN_TRY(launch_colsum(prec, w.d_scal, rows, 16, w.gB[kLayerH] + 128, c.st));
-  }
-  for (int l = 7; l >= 0; --l) {
+  RN_TRY(wgrad_layer(c, w, kLayerH, rows, w.dheads, kHeadsPad, kHeadsReal, w.a(8), none));   // packed head rows 0..138
+  for (int l = 7; l >= 0; --l)
     RN_TRY(wgrad_layer(c, w, l, rows, w.gs[l], 256, 256, l == 0 ? w.x0 : w.a(l), l == 5 ? w.x0 : none));
-    RN_TRY(launch_colsum(prec, w.gs[l], rows, 256, w.gB[l], c.st));
-  }
   return RN_OK;
 }
 
