@@ -99,6 +99,14 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
         "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
       : "r"(taddr));
 }
+__device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ float4 lds128f(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // Shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout), 128B swizzle:
@@ -651,7 +659,7 @@ struct ChainMaps {
   CUtensorMap w[kChainMaxOps];
 };
 
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(384, 1)
 chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__ ChainParams p) {
   constexpr int kStageBytes = 256 * kBK * 2;  // 32 KB weight K block
   constexpr int kBlkBytes = kBM * kBK * 2;    // 16 KB activation K block
@@ -681,10 +689,10 @@ chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__ Cha
       mbar_init(&w_full[i], 1);
       mbar_init(&w_empty[i], 1);
     }
-    for (int i = 0; i < 4; ++i) mbar_init(&a_ready[i], 4);
+    for (int i = 0; i < 4; ++i) mbar_init(&a_ready[i], 8);
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull[i], 1);
-      mbar_init(&tempty[i], 4);
+      mbar_init(&tempty[i], 8);
     }
     mbar_init(in_full, 1);
     mbar_init(in_empty, 1);
@@ -761,10 +769,13 @@ chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__ Cha
       in_phase ^= 1;
     }
   } else if (warp >= 4) {
-    // ===== epilogue warps =====
-    const int q = warp - 4;
+    // ===== epilogue warps: 8 warps = 4 TMEM lane quadrants x 2 column halves of every 64-column chunk =====
+    const int q = (warp - 4) & 3;
+    const int half = (warp - 4) >> 2;
     int buf = 0;
     uint32_t tphase = 0;
+    const uint32_t s_act_u32 = smem_u32(s_act);
+    const uint32_t bias_u32 = smem_u32(bias_s);
     for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int r_in_tile = q * 32 + lane;
       const int64_t row = tile * kBM + r_in_tile;
@@ -773,66 +784,69 @@ chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__ Cha
         const ChainOp& L = p.op[l];
         const bool hidden = L.kind == 0;
         if (hidden && L.mode == 0) {
-          // stage this op's bias in shared memory (the 4 epilogue warps only: named barrier 1)
-          asm volatile("bar.sync 1, 128;" ::: "memory");
+          // stage this op's bias in shared memory (the 8 epilogue warps only: named barrier 1)
+          asm volatile("bar.sync 1, 256;" ::: "memory");
           const int t = threadIdx.x - 128;
-          reinterpret_cast<float2*>(bias_s)[t] = __ldg(reinterpret_cast<const float2*>(L.bias) + t);
-          asm volatile("bar.sync 1, 128;" ::: "memory");
+          if (t < 128) {
+            const float2 bv = __ldg(reinterpret_cast<const float2*>(L.bias) + t);
+            asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(bias_u32 + 8u * t), "f"(bv.x), "f"(bv.y) : "memory");
+          }
+          asm volatile("bar.sync 1, 256;" ::: "memory");
         }
         mbar_wait(&tfull[buf], tphase);
         tc_fence_after();
         const uint32_t taddr = tmem_base + (uint32_t)buf * 256u + ((uint32_t)(q * 32) << 16);
         if (hidden) {
-          // 4 chunks of 64 columns -> swizzled K blocks of the activation tile
+          // 4 chunks of 64 columns (this warp: 32 of them) -> swizzled K blocks of the activation tile
           for (int j = 0; j < 4; ++j) {
-            uint32_t r[64];
-            uint32_t mk[32];
-            tmem_ld32(taddr + (uint32_t)(j * 64), r);
-            tmem_ld32(taddr + (uint32_t)(j * 64 + 32), r + 32);
+            const int col0 = j * 64 + half * 32;
+            uint32_t r[32];
+            uint32_t mk[16];
+            tmem_ld32(taddr + (uint32_t)col0, r);
             if (L.mode == 1 && row_ok) {
-              const uint16_t* mp = L.mask + (size_t)row * 256 + j * 64;
-#pragma unroll
-              for (int c = 0; c < 4; ++c) ldg256(mp + c * 16, mk + 8 * c);
+              const uint16_t* mp = L.mask + (size_t)row * 256 + col0;
+              ldg256(mp, mk);
+              ldg256(mp + 16, mk + 8);
             }
             tmem_ld_wait();
-            uint32_t packed[32];
+            uint32_t packed[16];
             if (L.mode == 0) {
-              const float4* b4 = reinterpret_cast<const float4*>(bias_s + j * 64);
+              const uint32_t baddr = bias_u32 + (uint32_t)col0 * 4u;
 #pragma unroll
-              for (int i = 0; i < 16; ++i) {
-                const float4 b = b4[i];
+              for (int i = 0; i < 8; ++i) {
+                const float4 b = lds128f(baddr + 16u * i);
                 const float v0 = fmaxf(__uint_as_float(r[4 * i]) + b.x, 0.f), v1 = fmaxf(__uint_as_float(r[4 * i + 1]) + b.y, 0.f);
                 const float v2 = fmaxf(__uint_as_float(r[4 * i + 2]) + b.z, 0.f), v3 = fmaxf(__uint_as_float(r[4 * i + 3]) + b.w, 0.f);
-                packed[2 * i] = (uint32_t)float_to_bf16_bits(v0) | ((uint32_t)float_to_bf16_bits(v1) << 16);
-                packed[2 * i + 1] = (uint32_t)float_to_bf16_bits(v2) | ((uint32_t)float_to_bf16_bits(v3) << 16);
+                packed[2 * i] = pack_bf16x2(v0, v1);
+                packed[2 * i + 1] = pack_bf16x2(v2, v3);
               }
             } else {
 #pragma unroll
-              for (int i = 0; i < 32; ++i) {
+              for (int i = 0; i < 16; ++i) {
                 const uint32_t mlo = mk[i] & 0xffffu, mhi = mk[i] >> 16;
                 const bool plo = row_ok && mlo != 0u && mlo < 0x8000u, phi = row_ok && mhi != 0u && mhi < 0x8000u;
                 const float v0 = plo ? __uint_as_float(r[2 * i]) : 0.f, v1 = phi ? __uint_as_float(r[2 * i + 1]) : 0.f;
-                packed[i] = (uint32_t)float_to_bf16_bits(v0) | ((uint32_t)float_to_bf16_bits(v1) << 16);
+                packed[i] = pack_bf16x2(v0, v1);
               }
             }
-            uint8_t* blk = s_act + j * kBlkBytes + r_in_tile * 128;
+            const uint32_t blk = s_act_u32 + (uint32_t)(j * kBlkBytes + r_in_tile * 128);
 #pragma unroll
-            for (int c = 0; c < 8; ++c) {
-              const int pos = c ^ (r_in_tile & 7);
-              *reinterpret_cast<uint4*>(blk + pos * 16) = make_uint4(packed[4 * c], packed[4 * c + 1], packed[4 * c + 2], packed[4 * c + 3]);
+            for (int c = 0; c < 4; ++c) {
+              const uint32_t pos = (uint32_t)((half * 4 + c) ^ (r_in_tile & 7));
+              sts128(blk + pos * 16u, packed[4 * c], packed[4 * c + 1], packed[4 * c + 2], packed[4 * c + 3]);
             }
             fence_proxy_async();   // make the generic-proxy smem writes visible to the tensor core (async proxy)
             __syncwarp();
             if (lane == 0) mbar_arrive(&a_ready[j]);
             if (L.save_hi && row_ok) {
-              uint16_t* g = reinterpret_cast<uint16_t*>(L.save_hi) + (size_t)row * 256 + j * 64;
-#pragma unroll
-              for (int c = 0; c < 4; ++c) stg256(g + c * 16, packed + 8 * c);
+              uint16_t* g = reinterpret_cast<uint16_t*>(L.save_hi) + (size_t)row * 256 + col0;
+              stg256(g, packed);
+              stg256(g + 16, packed + 8);
             }
           }
         } else {
           const GemmEpilogue& ge = p.gepi[L.gepi];
-          for (int c0 = 0; c0 < L.n; c0 += 32) {
+          for (int c0 = half * 32; c0 < L.n; c0 += 64) {
             uint32_t r[32];
             tmem_ld32(taddr + (uint32_t)c0, r);
             tmem_ld_wait();
@@ -997,7 +1011,7 @@ int launch_chain(const ChainArgs& a, cudaStream_t st) {
   const int64_t tiles = (a.m + kBM - 1) / kBM;
   const unsigned grid = (unsigned)(tiles < num_sms() ? tiles : num_sms());
   rn_prof_begin(RN_PROF_CHAIN_TC, st, a.algo_flops);
-  chain_kernel<<<grid, 256, smem, st>>>(maps, p);
+  chain_kernel<<<grid, 384, smem, st>>>(maps, p);
   rn_prof_end(RN_PROF_CHAIN_TC, st);
   RN_CUDA_CHECK_LAUNCH();
   return RN_OK;

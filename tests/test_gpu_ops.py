@@ -71,7 +71,7 @@ def test_resample_large_properties(ops):
     u = O.sample_grid(128).expand(n, 128)
     assert torch.equal(idx.long(), O.interval_index(u, cw))
     ref = O.sample_intervals(t[:4096], O.resample_logits(t[:4096], w[:4096], 0.01), 128)
-    assert (so[:4096] - ref).abs().max() <= 5e-6
+    assert (so[:4096] - ref).abs().max() <= 2e-5   # CDF ulps divided by narrow CDF steps
 
 
 def test_encode_matches_oracle(ops, gold):
