@@ -1,0 +1,521 @@
+// Fused GEMM chain on CTA pairs (sm_100a, tcgen05.mma cta_group::2).
+//
+// One cluster of two CTAs (one per SM of a TPC) walks "super tiles" of 512 rows = 2 row tiles (A, B) x 256
+// rows, each CTA holding 128 rows of each tile.  Per chain op (one Linear layer of the NerfMLP, forward or
+// dgrad) the pair issues UMMA M=256 x N<=256 x K=16 instructions: every CTA supplies its 128 rows of the
+// A operand (the running activation, resident in its shared memory) and HALF of the weight rows (N/2),
+// so each SM stages only half of every weight K block and the pair shares it.
+//
+//   * ping-pong: the two row tiles alternate on the tensor pipe.  While the MMAs of tile B run, the eight
+//     epilogue warps of both CTAs drain tile A's TMEM accumulator (bias + ReLU / ReLU mask, bf16) and
+//     write it back as the next op's A operand (128B-swizzled, K-major), and vice versa; TMEM holds
+//     exactly the two 256-column fp32 accumulators.
+//   * weight ring: 16 KB stages; the K blocks of an op stay resident while tile A and then tile B consume
+//     them, so one L2 -> SMEM weight transfer serves 512 rows.  Input-tile K blocks (layer 0 and the skip
+//     layer) stream through the same ring just in time.
+//   * saves for the wgrad kernels (training) leave as TMA stores straight from the swizzled activation
+//     tile; eval touches HBM only for the chain input and the head outputs.
+//
+// Roles per CTA (384 threads): warp 0 TMA producer, warp 1 MMA issuer (leader CTA only), warp 2 TMEM
+// allocator, warps 4-11 epilogue (warp % 4 = TMEM lane quadrant, (warp - 4) / 4 = column half).
+#include "tc_common.cuh"
+
+namespace rn {
+namespace {
+using namespace tc;
+
+constexpr int kMaxOps = 12;
+constexpr int kRingStages = 6;
+constexpr int kStageBytes = 16384;            // one ring item: [128 x 64] bf16
+constexpr int kBlkBytes = kBM * kBK * 2;      // 16 KB activation K block
+constexpr int kActBytes = 4 * kBlkBytes;      // 64 KB activation tile
+constexpr int kSmemRing = 2 * kActBytes;
+constexpr int kSmemBars = kSmemRing + kRingStages * kStageBytes;
+constexpr int kSmemBias = kSmemBars + 256;
+constexpr int kSmemTotal = kSmemBias + 2 * 1024;
+static_assert(kSmemTotal <= 232448, "shared memory budget");
+
+// ---- cluster / 2-CTA PTX ---------------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t map_to_cta(uint32_t local_addr, uint32_t cta) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(cta));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  for (int spin = 0; spin < kSpinLimit; ++spin) {
+    uint32_t done;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (done) return;
+  }
+  __trap();
+}
+__device__ __forceinline__ void tmem_alloc2(uint32_t* dst_smem, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(cols));
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+}
+__device__ __forceinline__ void tmem_dealloc2(uint32_t taddr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols));
+}
+// TMA load whose transaction bytes are credited to the barrier at `bar_cluster_addr` (the leader CTA's)
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t smem_dst, const CUtensorMap* map, uint32_t bar_cluster_addr, int c0,
+                                                 int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_dst), "l"(map), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t smem_src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map), "r"(smem_src),
+               "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void tma_store_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+// D[tmem, both CTAs] (+)= A[smem, 128 rows per CTA] * B[smem, N/2 rows per CTA]^T
+__device__ __forceinline__ void umma2_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accum)
+      : "memory");
+}
+// arrive (once the MMAs issued so far have completed) on the barrier at the same offset in both CTAs
+__device__ __forceinline__ void umma2_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                   smem_u32(bar)),
+               "h"((uint16_t)3)
+               : "memory");
+}
+__device__ __forceinline__ uint32_t make_idesc2(int n) {
+  uint32_t d = 0;
+  d |= 1u << 4;                       // c_format = F32
+  d |= 1u << 7;                       // a_format = BF16
+  d |= 1u << 10;                      // b_format = BF16
+  d |= (uint32_t)(n >> 3) << 17;
+  d |= (uint32_t)(256 >> 4) << 24;    // M = 256 across the pair
+  return d;
+}
+
+// epilogue for 16 consecutive columns of one row of a global (non-hidden) op; v holds the fp32 accumulators
+__device__ __forceinline__ void epi_global16(const GemmEpilogue& e, size_t row, int col, float* v) {
+  if (e.bias) {
+    const float4* b4 = reinterpret_cast<const float4*>(e.bias + col);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float4 b = __ldg(b4 + i);
+      v[4 * i] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w;
+    }
+  }
+  if (e.relu) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
+  }
+  if (e.out.hi && col < e.out_cols) {
+    uint32_t h[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) h[i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);
+    stg256(reinterpret_cast<uint16_t*>(e.out.hi) + row * e.out.ld + col, h);
+  }
+  if (e.f32 && col + 16 > e.f32_col0 && col < e.f32_col0 + e.f32_cols) {
+    const int c0 = col - e.f32_col0;
+    float* p = e.f32 + row * e.f32_ld + c0;
+    if (c0 >= 0 && c0 + 16 <= e.f32_cols && (e.f32_ld & 7) == 0) {
+      uint32_t a[8];
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        if (e.f32_accum) {
+          ldg256(p + 8 * half, a);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) a[i] = __float_as_uint(__uint_as_float(a[i]) + v[8 * half + i]);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) a[i] = __float_as_uint(v[8 * half + i]);
+        }
+        stg256(p + 8 * half, a);
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const int c = c0 + i;
+        if (c >= 0 && c < e.f32_cols) p[i] = e.f32_accum ? (p[i] + v[i]) : v[i];
+      }
+    }
+  }
+}
+
+struct PairOp {
+  int n;           // MMA N = output columns (multiple of 16)
+  int kb_act;      // K blocks read from the resident activation tile (0 or 4)
+  int kb_in;       // K blocks read from the chain input tile (streamed through the ring)
+  int kind;        // 0: hidden (result -> activation tile [+ TMA save]); 1: global epilogue
+  int mode;        // hidden transform: 0 = bias + ReLU (forward), 1 = ReLU mask from a saved activation (backward)
+  int gepi;        // kind 1: which global epilogue
+  int save;        // hidden: TMA-store the result through maps.save[op]
+  const float* bias;       // mode 0
+  const uint16_t* mask;    // mode 1: bf16 [m,256]; positive entries pass the gradient
+};
+struct PairParams {
+  int num_ops;
+  int in_kb;
+  int64_t m;
+  PairOp op[kMaxOps];
+  GemmEpilogue gepi[2];
+};
+struct PairMaps {
+  CUtensorMap in;
+  CUtensorMap w[kMaxOps];
+  CUtensorMap save[kMaxOps];
+};
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
+chain_pair_kernel(const __grid_constant__ PairMaps maps, const __grid_constant__ PairParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kSmemBars);
+  uint64_t* ring_full = bars;          // [8]  leader's are used (TMA bytes of both CTAs land there)
+  uint64_t* ring_empty = bars + 8;     // [8]  per CTA, signalled by the multicast MMA commit
+  uint64_t* acc_full = bars + 16;      // [2]  per CTA, multicast MMA commit
+  uint64_t* acc_free = bars + 18;      // [2]  leader's: 16 arrivals (8 epilogue warps x 2 CTAs)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
+  float* bias_s = reinterpret_cast<float*>(smem + kSmemBias);   // [2][256]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int64_t num_super = (p.m + 511) / 512;
+  const int64_t cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
+  const uint32_t smem_base = smem_u32(smem);
+
+  if (threadIdx.x == 0) {
+    if (smem_base & 1023u) __trap();
+    tma_prefetch_desc(&maps.in);
+    for (int i = 0; i < p.num_ops; ++i) tma_prefetch_desc(&maps.w[i]);
+    for (int i = 0; i < kRingStages; ++i) {
+      mbar_init(&ring_full[i], 1);
+      mbar_init(&ring_empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&acc_full[i], 1);
+      mbar_init(&acc_free[i], 16);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc2(tmem_slot, kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0 && lane == 0) {
+    // ===== TMA producer: this CTA's half of every weight K block and its rows of the input K blocks =====
+    uint32_t pos = 0;
+    auto acquire = [&](uint32_t total_bytes) -> uint32_t {
+      const uint32_t s = pos % kRingStages, ph = (pos / kRingStages) & 1u;
+      mbar_wait(&ring_empty[s], ph ^ 1u);
+      if (rank == 0) mbar_arrive_expect_tx(&ring_full[s], total_bytes);
+      ++pos;
+      return s;
+    };
+    for (int64_t st = cluster_id; st < num_super; st += num_clusters) {
+      for (int l = 0; l < p.num_ops; ++l) {
+        const PairOp& L = p.op[l];
+        const int nh = L.n >> 1;
+        for (int kb = 0; kb < L.kb_act; ++kb) {
+          const uint32_t s = acquire((uint32_t)L.n * 128u);
+          tma_load_2d_pair(smem_base + kSmemRing + s * kStageBytes, &maps.w[l], map_to_cta(smem_u32(&ring_full[s]), 0),
+                           kb * kBK, (int)rank * nh);
+        }
+        for (int kb = 0; kb < L.kb_in; ++kb) {
+          for (int t = 0; t < 2; ++t) {
+            const uint32_t s = acquire(2u * kStageBytes);
+            const int64_t row0 = st * 512 + t * 256 + (int64_t)rank * 128;
+            tma_load_2d_pair(smem_base + kSmemRing + s * kStageBytes, &maps.in, map_to_cta(smem_u32(&ring_full[s]), 0),
+                             kb * kBK, (int)row0);
+            if (t == 0) {
+              const uint32_t sw = acquire((uint32_t)L.n * 128u);
+              tma_load_2d_pair(smem_base + kSmemRing + sw * kStageBytes, &maps.w[l],
+                               map_to_cta(smem_u32(&ring_full[sw]), 0), (L.kb_act + kb) * kBK, (int)rank * nh);
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1 && lane == 0 && rank == 0) {
+    // ===== MMA issuer (leader CTA) =====
+    uint32_t pos = 0;       // ring position, mirrors the producer's item order
+    uint32_t opcount = 0;   // ops issued so far on each tile
+    auto wait_full = [&](uint32_t q) {
+      mbar_wait(&ring_full[q % kRingStages], (q / kRingStages) & 1u);
+    };
+    auto stage_addr = [&](uint32_t q) -> uint32_t { return smem_base + kSmemRing + (q % kRingStages) * kStageBytes; };
+    auto mma_kblock = [&](uint32_t tmem_d, uint32_t sa, uint32_t sb, uint32_t idesc, bool first) {
+#pragma unroll
+      for (int kk = 0; kk < kBK / kUmmaK; ++kk) {
+        const uint32_t koff = kk * kUmmaK * 2;
+        umma2_bf16(tmem_d, make_desc(sa + koff, 16, 1024), make_desc(sb + koff, 16, 1024), idesc, (!first || kk) ? 1u : 0u);
+      }
+    };
+    for (int64_t st = cluster_id; st < num_super; st += num_clusters) {
+      for (int l = 0; l < p.num_ops; ++l, ++opcount) {
+        const PairOp& L = p.op[l];
+        const uint32_t idesc = make_idesc2(L.n);
+        const uint32_t free_parity = (opcount & 1u) ^ 1u;
+        // --- K blocks from the resident activation tiles: tile 0 then tile 1 over the same weight stages
+        const uint32_t pos_w = pos;
+        for (int t = 0; t < 2; ++t) {
+          if (L.kb_act) {
+            mbar_wait_cluster(&acc_free[t], free_parity);
+            tc_fence_after();
+          }
+          const uint32_t tmem_d = tmem_base + (uint32_t)t * 256u;
+          for (int kb = 0; kb < L.kb_act; ++kb) {
+            if (t == 0) {
+              wait_full(pos_w + kb);
+              tc_fence_after();
+            }
+            mma_kblock(tmem_d, smem_base + t * kActBytes + kb * kBlkBytes, stage_addr(pos_w + kb), idesc, kb == 0);
+            if (t == 1) umma2_commit(&ring_empty[(pos_w + kb) % kRingStages]);
+          }
+          if (L.kb_act && !L.kb_in) umma2_commit(&acc_full[t]);
+        }
+        pos += L.kb_act;
+        // --- K blocks from the chain input: x(tile 0), W, x(tile 1) per K block
+        for (int kb = 0; kb < L.kb_in; ++kb) {
+          const uint32_t px0 = pos, pw = pos + 1, px1 = pos + 2;
+          pos += 3;
+          for (int t = 0; t < 2; ++t) {
+            if (!L.kb_act && kb == 0) {
+              mbar_wait_cluster(&acc_free[t], free_parity);
+              tc_fence_after();
+            }
+            const uint32_t px = t ? px1 : px0;
+            wait_full(px);
+            if (t == 0) wait_full(pw);
+            tc_fence_after();
+            mma_kblock(tmem_base + (uint32_t)t * 256u, stage_addr(px), stage_addr(pw), idesc, !L.kb_act && kb == 0);
+            umma2_commit(&ring_empty[px % kRingStages]);
+            if (t == 1) umma2_commit(&ring_empty[pw % kRingStages]);
+            if (kb == L.kb_in - 1) umma2_commit(&acc_full[t]);
+          }
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===== epilogue warps: q = TMEM lane quadrant (32 rows), h = column half (128 columns = chunks 2h, 2h+1) =====
+    const int q = (warp - 4) & 3;
+    const int h = (warp - 4) >> 2;
+    const int r_in_tile = q * 32 + lane;
+    const uint32_t bias_u32 = smem_u32(bias_s);
+    const uint32_t free_addr0 = map_to_cta(smem_u32(&acc_free[0]), 0);   // leader's acc_free[0]; [1] is 8 bytes on
+    uint32_t opcount = 0;
+    // TMA-store bookkeeping (warp-uniform): has_group[t] = a committed bulk group may still be reading this warp's
+    // part of act[t]; newer[t] = bulk groups committed after it (0 or 1, the tiles alternate)
+    uint32_t has_group = 0, newer = 0;   // bit t
+    bool any_store = false;
+    for (int64_t st = cluster_id; st < num_super; st += num_clusters) {
+      for (int l = 0; l < p.num_ops; ++l, ++opcount) {
+        const PairOp& L = p.op[l];
+        const bool hidden = L.kind == 0;
+        const uint32_t bias_buf = bias_u32 + (opcount & 1u) * 1024u;
+        if (hidden && L.mode == 0) {
+          // stage this op's bias (double-buffered by op parity; one named barrier among the 8 epilogue warps)
+          const int tid = threadIdx.x - 128;
+          if (tid < 64) {
+            const float4 bv = __ldg(reinterpret_cast<const float4*>(L.bias) + tid);
+            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(bias_buf + 16u * tid), "f"(bv.x), "f"(bv.y), "f"(bv.z),
+                         "f"(bv.w)
+                         : "memory");
+          }
+          asm volatile("bar.sync 1, 256;" ::: "memory");
+        }
+        for (int t = 0; t < 2; ++t) {
+          const int64_t row = st * 512 + t * 256 + (int64_t)rank * 128 + r_in_tile;
+          const bool row_ok = row < p.m;
+          mbar_wait(&acc_full[t], opcount & 1u);
+          tc_fence_after();
+          const uint32_t taddr = tmem_base + (uint32_t)t * 256u + ((uint32_t)(q * 32) << 16);
+          if (hidden) {
+            if (has_group >> t & 1u) {
+              // the TMA stores that read this warp's part of act[t] must have drained it before it is overwritten
+              if (lane == 0) {
+                if (newer >> t & 1u) tma_store_wait_read<1>(); else tma_store_wait_read<0>();
+              }
+              __syncwarp();
+              has_group &= ~(1u << t);
+            }
+            const uint32_t act_row = smem_base + (uint32_t)(t * kActBytes + r_in_tile * 128);
+#pragma unroll 1
+            for (int cc = 0; cc < 2; ++cc) {
+              const int c = 2 * h + cc;   // 64-column chunk = activation K block c
+#pragma unroll
+              for (int half = 0; half < 2; ++half) {
+                const int col0 = c * 64 + half * 32;
+                uint32_t r[32];
+                uint32_t mk[16];
+                tmem_ld32(taddr + (uint32_t)col0, r);
+                if (L.mode == 1 && row_ok) {
+                  const uint16_t* mp = L.mask + (size_t)row * 256 + col0;
+                  ldg256(mp, mk);
+                  ldg256(mp + 16, mk + 8);
+                }
+                tmem_ld_wait();
+                uint32_t packed[16];
+                if (L.mode == 0) {
+                  const uint32_t baddr = bias_buf + (uint32_t)col0 * 4u;
+#pragma unroll
+                  for (int i = 0; i < 8; ++i) {
+                    const float4 b = lds128f(baddr + 16u * i);
+                    const float v0 = fmaxf(__uint_as_float(r[4 * i]) + b.x, 0.f), v1 = fmaxf(__uint_as_float(r[4 * i + 1]) + b.y, 0.f);
+                    const float v2 = fmaxf(__uint_as_float(r[4 * i + 2]) + b.z, 0.f), v3 = fmaxf(__uint_as_float(r[4 * i + 3]) + b.w, 0.f);
+                    packed[2 * i] = pack_bf16x2(v0, v1);
+                    packed[2 * i + 1] = pack_bf16x2(v2, v3);
+                  }
+                } else {
+#pragma unroll
+                  for (int i = 0; i < 16; ++i) {
+                    const uint32_t mlo = mk[i] & 0xffffu, mhi = mk[i] >> 16;
+                    const bool plo = row_ok && mlo != 0u && mlo < 0x8000u, phi = row_ok && mhi != 0u && mhi < 0x8000u;
+                    const float v0 = plo ? __uint_as_float(r[2 * i]) : 0.f, v1 = phi ? __uint_as_float(r[2 * i + 1]) : 0.f;
+                    packed[i] = pack_bf16x2(v0, v1);
+                  }
+                }
+                const uint32_t blk = act_row + (uint32_t)(c * kBlkBytes);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                  const uint32_t pos16 = (uint32_t)((half * 4 + u) ^ (r_in_tile & 7));
+                  sts128(blk + pos16 * 16u, packed[4 * u], packed[4 * u + 1], packed[4 * u + 2], packed[4 * u + 3]);
+                }
+              }
+            }
+            fence_proxy_async();   // generic-proxy smem writes -> visible to the tensor core and to TMA stores
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+              mbar_arrive_remote(free_addr0 + 8u * t);
+              if (L.save) {
+                const int64_t row_w = st * 512 + t * 256 + (int64_t)rank * 128 + q * 32;
+                if (row_w < p.m) {
+                  for (int cc = 0; cc < 2; ++cc) {
+                    const int c = 2 * h + cc;
+                    tma_store_2d(&maps.save[l], smem_base + (uint32_t)(t * kActBytes + c * kBlkBytes + q * 32 * 128), c * 64,
+                                 (int)row_w);
+                  }
+                }
+                tma_store_commit();
+              }
+            }
+            if (L.save) {
+              has_group |= 1u << t;
+              newer &= ~(1u << t);
+              if (has_group >> (t ^ 1) & 1u) newer |= 1u << (t ^ 1);
+              any_store = true;
+            }
+          } else {
+            const GemmEpilogue& ge = p.gepi[L.gepi];
+            for (int c0 = h * 32; c0 < L.n; c0 += 64) {
+              uint32_t r[32];
+              tmem_ld32(taddr + (uint32_t)c0, r);
+              tmem_ld_wait();
+              if (row_ok) {
+#pragma unroll
+                for (int hh = 0; hh < 2; ++hh) {
+                  if (c0 + 16 * hh < L.n) {
+                    float v[16];
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) v[e] = __uint_as_float(r[16 * hh + e]);
+                    epi_global16(ge, (size_t)row, c0 + 16 * hh, v);
+                  }
+                }
+              }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_remote(free_addr0 + 8u * t);
+          }
+        }
+      }
+    }
+    if (any_store && lane == 0) tma_store_wait_all();
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 2) tmem_dealloc2(tmem_base, kTmemCols);
+}
+
+}  // namespace
+
+int launch_chain_pair(const ChainArgs& a, cudaStream_t st) {
+  if (a.m <= 0) return RN_OK;
+  if (a.num_ops < 1 || a.num_ops > kMaxOps) return rn_set_error(RN_ERR_ARG, "chain: 1..12 ops");
+  if (a.in_cols % 64 || a.in_cols < 64 || a.in_cols > 256) return rn_set_error(RN_ERR_ARG, "chain: input tile must be 64..256 columns");
+  if (a.m + 512 > 0x7fffffffLL) return rn_set_error(RN_ERR_ARG, "chain: too many rows for one launch");
+  PairMaps maps;
+  PairParams p;
+  memset(&p, 0, sizeof(p));
+  int rc;
+  if ((rc = tc::make_map(&maps.in, a.in.hi, a.m, a.in_valid, a.in.ld, kBM))) return rc;
+  p.num_ops = a.num_ops;
+  p.in_kb = a.in_cols / kBK;
+  p.m = a.m;
+  for (int l = 0; l < kMaxOps; ++l) {
+    memset(&maps.w[l], 0, sizeof(CUtensorMap));
+    memset(&maps.save[l], 0, sizeof(CUtensorMap));
+    if (l >= a.num_ops) continue;
+    const ChainOpArgs& L = a.op[l];
+    if (L.n % 16 || L.n < 16 || L.n > 256 || (L.kind == 0 && L.n != 256)) return rn_set_error(RN_ERR_ARG, "chain: bad op width");
+    if ((L.kb_act != 0 && L.kb_act != 4) || (L.kb_in != 0 && L.kb_in != p.in_kb) || L.kb_act + L.kb_in == 0 ||
+        (l == 0 && L.kb_act != 0))
+      return rn_set_error(RN_ERR_ARG, "chain: bad K structure");
+    const int ktot = (L.kb_act + L.kb_in) * kBK;
+    if ((rc = tc::make_map(&maps.w[l], L.w, L.n, ktot, L.w_ld, L.n / 2))) return rc;
+    PairOp& o = p.op[l];
+    o.n = L.n; o.kb_act = L.kb_act; o.kb_in = L.kb_in;
+    o.kind = L.kind; o.mode = L.mode; o.gepi = L.gepi; o.bias = L.bias;
+    o.mask = reinterpret_cast<const uint16_t*>(L.mask);
+    o.save = (L.kind == 0 && L.save_hi) ? 1 : 0;
+    if (o.save && (rc = tc::make_map(&maps.save[l], L.save_hi, a.m, 256, 256, 32))) return rc;
+    if (L.kind == 0 && L.mode == 0 && !L.bias) return rn_set_error(RN_ERR_ARG, "chain: forward op without bias");
+    if (L.kind == 0 && L.mode == 1 && !L.mask) return rn_set_error(RN_ERR_ARG, "chain: backward op without mask");
+  }
+  p.gepi[0] = a.gepi[0];
+  p.gepi[1] = a.gepi[1];
+  static bool smem_set = false;
+  if (!smem_set) {
+    if ((rc = tc::set_smem(chain_pair_kernel, kSmemTotal))) return rc;
+    smem_set = true;
+  }
+  const int64_t supers = (a.m + 511) / 512;
+  const int max_clusters = tc::num_sms() / 2;
+  const unsigned grid = 2u * (unsigned)(supers < max_clusters ? supers : max_clusters);
+  rn_prof_begin(RN_PROF_CHAIN_TC, st, a.algo_flops);
+  chain_pair_kernel<<<grid, 384, kSmemTotal, st>>>(maps, p);
+  rn_prof_end(RN_PROF_CHAIN_TC, st);
+  RN_CUDA_CHECK_LAUNCH();
+  return RN_OK;
+}
+
+}  // namespace rn

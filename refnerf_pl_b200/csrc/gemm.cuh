@@ -80,7 +80,9 @@ struct ChainArgs {
   GemmEpilogue gepi[2];
   double algo_flops = 0.0;
 };
-int launch_chain(const ChainArgs& a, cudaStream_t st);
+int launch_chain(const ChainArgs& a, cudaStream_t st);        // dispatch (rn_set_chain_impl)
+int launch_chain_pair(const ChainArgs& a, cudaStream_t st);   // chain_pair.cu: CTA pairs, cta_group::2, two row tiles in flight
+int launch_chain_single(const ChainArgs& a, cudaStream_t st); // gemm_tc.cu: one CTA per tile (kept as an A/B reference)
 
 int launch_gemm(const GemmArgs& g, cudaStream_t st);
 int launch_wgrad(const WgradArgs& g, cudaStream_t st);

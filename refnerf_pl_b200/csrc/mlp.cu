@@ -59,6 +59,18 @@ void rn_prof_end(int cls, cudaStream_t st) {
   p.used += 2;
 }
 
+static int g_chain_impl = 0;
+extern "C" int rn_set_chain_impl(int impl) {
+  if (impl < 0 || impl > 1) return rn_set_error(RN_ERR_ARG, "rn_set_chain_impl: 0 = CTA-pair kernel, 1 = single-CTA kernel");
+  g_chain_impl = impl;
+  return RN_OK;
+}
+namespace rn {
+int launch_chain(const ChainArgs& a, cudaStream_t st) {
+  return g_chain_impl == 1 ? launch_chain_single(a, st) : launch_chain_pair(a, st);
+}
+}  // namespace rn
+
 extern "C" int64_t rn_launch_count(void) { return (int64_t)g_launches.load(); }
 extern "C" int rn_prof_enable(int on) {
   std::lock_guard<std::mutex> lk(g_prof_mu);
