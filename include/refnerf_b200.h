@@ -115,9 +115,14 @@ typedef struct RnMlpConfig {
   int gemm_impl;            /* 0 = default (fused chains in bf16), 1 = SIMT GEMMs, 2 = per-layer tcgen05 */
 } RnMlpConfig;
 
-/* bytes of the packed-weight blob / of the scratch workspace for the given chunk size */
+/* bytes of the packed-weight blob / of the scratch workspace for the given chunk size.
+ * training: 0 = eval forward, 1 = training forward + backward that recomputes the activations per chunk,
+ * 2 = training forward + backward that share a "saved" region (rn_mlp_saved_bytes) instead of recomputing. */
 RN_API size_t rn_mlp_packed_bytes(int prec);
 RN_API size_t rn_mlp_workspace_bytes(const RnMlpConfig* cfg, int training);
+/* bytes of the saved-activation region for n_rows = n_rays * s rows (chain inputs, every hidden activation and
+ * the raw head outputs): written by rn_mlp_forward, read by rn_mlp_backward of the same call */
+RN_API size_t rn_mlp_saved_bytes(const RnMlpConfig* cfg, int64_t n_rows);
 /* fp32 parameters -> padded (hi/lo bf16 or fp32) GEMM operands incl. transposed copies for dgrad */
 RN_API int rn_mlp_pack(const float* const* params, void* packed, int prec, void* stream);
 
@@ -137,15 +142,17 @@ typedef struct RnMlpOutputs {
  * out->normals != NULL) + reflect/IDE/n.v + view net + colour combine. */
 RN_API int rn_mlp_forward(const RnMlpConfig* cfg, const void* packed, const float* tdist, const float* origins,
                    const float* dirs, const float* viewdirs, const float* radii, int64_t n_rays, int s,
-                   const RnMlpOutputs* out, void* workspace, size_t workspace_bytes, void* stream);
+                   const RnMlpOutputs* out, void* workspace, size_t workspace_bytes, void* saved, size_t saved_bytes,
+                   void* stream);
 
 /* Backward: upstream gradients in `g` (same shapes as RnMlpOutputs; NULL members = zero; normals
  * is a detached constant in the reference and is ignored).  Accumulates (+=) into
- * grads[RN_MLP_NUM_PARAMS] (fp32, shapes of the parameters). */
+ * grads[RN_MLP_NUM_PARAMS] (fp32, shapes of the parameters).  `saved` = the region the training forward
+ * filled (NULL: the activations are recomputed chunk by chunk). */
 RN_API int rn_mlp_backward(const RnMlpConfig* cfg, const void* packed, const float* tdist, const float* origins,
                     const float* dirs, const float* viewdirs, const float* radii, int64_t n_rays, int s,
                     const RnMlpOutputs* g, float* const* grads, void* workspace, size_t workspace_bytes,
-                    void* stream);
+                    const void* saved, size_t saved_bytes, void* stream);
 
 /* ---- GEMM building block, exposed for unit tests and the roofline bench ---------------------
  * C[M,N] (fp32, ldc) = act( A[M,K] * B[N,K]^T + bias ), A/B fp32 row-major, converted per `prec`

@@ -44,10 +44,11 @@ _SIGNATURES = {
     'rn_mlp_packed_bytes': (c_size_t, [c_int]),
     'rn_mlp_workspace_bytes': (c_size_t, [POINTER(RnMlpConfig), c_int]),
     'rn_mlp_pack': (c_int, [POINTER(c_void_p), _P, c_int, _P]),
+    'rn_mlp_saved_bytes': (c_size_t, [POINTER(RnMlpConfig), c_int64]),
     'rn_mlp_forward': (c_int, [POINTER(RnMlpConfig), _P, _P, _P, _P, _P, _P, c_int64, c_int, POINTER(RnMlpOutputs), _P,
-                               c_size_t, _P]),
+                               c_size_t, _P, c_size_t, _P]),
     'rn_mlp_backward': (c_int, [POINTER(RnMlpConfig), _P, _P, _P, _P, _P, _P, c_int64, c_int, POINTER(RnMlpOutputs),
-                                POINTER(c_void_p), _P, c_size_t, _P]),
+                                POINTER(c_void_p), _P, c_size_t, _P, c_size_t, _P]),
     'rn_gemm_scratch_bytes': (c_size_t, [c_int64, c_int, c_int]),
     'rn_gemm_test': (c_int, [_P, _P, _P, c_int64, c_int, c_int, c_int, c_int, c_int, _P, _P, c_size_t, _P]),
     'rn_wgrad_test': (c_int, [_P, _P, c_int64, c_int, c_int, c_int, c_int, _P, _P, c_size_t, _P]),

@@ -172,18 +172,46 @@ struct Workspace {
   ActBuf& b(int i) { return vw[(i - 1) % nvw]; }   // view activation
 };
 
-// mode 0: eval forward, 1: training forward (+normals pass), 2: backward
-Workspace carve(void* base, int prec, int64_t rc, int mode) {
+// Activations a training forward keeps for its backward (no recompute): chain inputs, every hidden activation
+// and the raw head outputs, for ALL rows of the call (chunks index into it by row).
+struct Saved {
+  ActBuf x0, v0, sp[8], vw[8];
+  float *heads_raw, *rgb_raw;
+  size_t bytes;
+};
+Saved carve_saved(void* base, int prec, int64_t rows) {
+  Saved s;
+  Carver c{reinterpret_cast<uint8_t*>(base)};
+  s.x0 = c.act(prec, rows, kEncPad);
+  s.v0 = c.act(prec, rows, kViewPad);
+  for (int i = 0; i < 8; ++i) s.sp[i] = c.act(prec, rows, 256);
+  for (int i = 0; i < 8; ++i) s.vw[i] = c.act(prec, rows, 256);
+  s.heads_raw = (float*)c.take((size_t)rows * 16 * 4);
+  s.rgb_raw = (float*)c.take((size_t)rows * 4 * 4);
+  s.bytes = c.off;
+  return s;
+}
+ActBuf rows_from(ActBuf b, int prec, int64_t row0) {
+  if (b.hi) b.hi = reinterpret_cast<uint8_t*>(b.hi) + (size_t)row0 * b.ld * elem_bytes(prec);
+  if (b.lo) b.lo = reinterpret_cast<uint8_t*>(b.lo) + (size_t)row0 * b.ld * 2;
+  return b;
+}
+
+// mode 0: eval forward, 1: training forward (+normals pass), 2: backward.  With `external` the chain inputs,
+// hidden activations and raw head outputs live in a Saved region (see use_saved) instead of the workspace.
+Workspace carve(void* base, int prec, int64_t rc, int mode, bool external = false) {
   Workspace w;
   Carver c{reinterpret_cast<uint8_t*>(base)};
-  w.nsp = mode == 0 ? 2 : 8;
-  w.nvw = mode == 2 ? 8 : 2;
-  w.x0 = c.act(prec, rc, kEncPad);
-  w.v0 = c.act(prec, rc, kViewPad);
-  for (int i = 0; i < w.nsp; ++i) w.sp[i] = c.act(prec, rc, 256);
-  for (int i = 0; i < w.nvw; ++i) w.vw[i] = c.act(prec, rc, 256);
-  w.heads_raw = (float*)c.take((size_t)rc * 16 * 4);
-  w.rgb_raw = (float*)c.take((size_t)rc * 4 * 4);
+  w.nsp = (mode == 0 && !external) ? 2 : 8;
+  w.nvw = (mode == 2 || external) ? 8 : 2;
+  if (!external) {
+    w.x0 = c.act(prec, rc, kEncPad);
+    w.v0 = c.act(prec, rc, kViewPad);
+    for (int i = 0; i < w.nsp; ++i) w.sp[i] = c.act(prec, rc, 256);
+    for (int i = 0; i < w.nvw; ++i) w.vw[i] = c.act(prec, rc, 256);
+    w.heads_raw = (float*)c.take((size_t)rc * 16 * 4);
+    w.rgb_raw = (float*)c.take((size_t)rc * 4 * 4);
+  }
   if (mode == 1) {
     w.g[0] = c.act(prec, rc, 256);
     w.g[1] = c.act(prec, rc, 256);
@@ -211,6 +239,17 @@ Workspace carve(void* base, int prec, int64_t rc, int mode) {
   }
   w.bytes = c.off;
   return w;
+}
+// point the chunk's activation buffers at rows [row0, ..) of the saved region
+void use_saved(Workspace& w, const Saved& s, int prec, int64_t row0) {
+  w.x0 = rows_from(s.x0, prec, row0);
+  w.v0 = rows_from(s.v0, prec, row0);
+  for (int i = 0; i < 8; ++i) {
+    w.sp[i] = rows_from(s.sp[i], prec, row0);
+    w.vw[i] = rows_from(s.vw[i], prec, row0);
+  }
+  w.heads_raw = s.heads_raw + (size_t)row0 * 16;
+  w.rgb_raw = s.rgb_raw + (size_t)row0 * 4;
 }
 
 struct Packed {
@@ -626,7 +665,7 @@ int make_ctx(Ctx& c, const RnMlpConfig* cfg, const void* packed, const float* td
 using namespace rn;
 
 extern "C" const char* rn_last_error(void) { return g_err; }
-extern "C" int rn_abi_version(void) { return 1; }
+extern "C" int rn_abi_version(void) { return 2; }
 extern "C" const char* rn_mlp_param_name(int i) { return (i >= 0 && i < RN_MLP_NUM_PARAMS) ? kParamNames[i] : nullptr; }
 extern "C" int64_t rn_mlp_param_numel(int i) { return (i >= 0 && i < RN_MLP_NUM_PARAMS) ? param_numel(i) : -1; }
 
@@ -637,13 +676,19 @@ extern "C" size_t rn_mlp_packed_bytes(int prec) {
 
 extern "C" size_t rn_mlp_workspace_bytes(const RnMlpConfig* cfg, int training) {
   if (!cfg || cfg->chunk_rows <= 0) return 0;
-  size_t b = carve(nullptr, cfg->prec, cfg->chunk_rows, training ? 2 : 0).bytes;
+  const bool ext = training == 2;
+  size_t b = carve(nullptr, cfg->prec, cfg->chunk_rows, training ? 2 : 0, ext).bytes;
   if (training) {
-    size_t b1 = carve(nullptr, cfg->prec, cfg->chunk_rows, 1).bytes;
+    size_t b1 = carve(nullptr, cfg->prec, cfg->chunk_rows, 1, ext).bytes;
     if (b1 > b) b = b1;
     b += (size_t)cfg->chunk_rows * 16 * 4;  // scratch head outputs of the recompute pass
   }
   return b;
+}
+
+extern "C" size_t rn_mlp_saved_bytes(const RnMlpConfig* cfg, int64_t n_rows) {
+  if (!cfg || n_rows <= 0) return 0;
+  return carve_saved(nullptr, cfg->prec, n_rows).bytes;
 }
 
 extern "C" int rn_mlp_pack(const float* const* params, void* packed, int prec, void* stream) {
@@ -687,7 +732,8 @@ extern "C" int rn_mlp_pack(const float* const* params, void* packed, int prec, v
 
 extern "C" int rn_mlp_forward(const RnMlpConfig* cfg, const void* packed, const float* tdist, const float* origins,
                               const float* dirs, const float* viewdirs, const float* radii, int64_t n_rays, int s,
-                              const RnMlpOutputs* out, void* workspace, size_t workspace_bytes, void* stream) {
+                              const RnMlpOutputs* out, void* workspace, size_t workspace_bytes, void* saved,
+                              size_t saved_bytes, void* stream) {
   Ctx c;
   RN_TRY(make_ctx(c, cfg, packed, tdist, origins, dirs, viewdirs, radii, s, stream));
   if (!out || !out->density || !out->rgb || !out->normals_pred || !out->grad_pred || !out->tint || !out->diffuse ||
@@ -696,10 +742,16 @@ extern "C" int rn_mlp_forward(const RnMlpConfig* cfg, const void* packed, const 
   const bool want_normals = out->normals != nullptr;
   const int64_t rows_total = n_rays * s;
   const int64_t rc = cfg->chunk_rows;
-  Workspace w = carve(workspace, cfg->prec, rc, want_normals ? 1 : 0);
+  Workspace w = carve(workspace, cfg->prec, rc, want_normals ? 1 : 0, saved != nullptr);
   if (w.bytes > workspace_bytes) return rn_set_error(RN_ERR_ARG, "rn_mlp_forward: workspace too small");
+  Saved sv;
+  if (saved) {
+    sv = carve_saved(saved, cfg->prec, rows_total);
+    if (sv.bytes > saved_bytes) return rn_set_error(RN_ERR_ARG, "rn_mlp_forward: saved region too small");
+  }
   for (int64_t row0 = 0; row0 < rows_total; row0 += rc) {
     const int64_t rows = rows_total - row0 < rc ? rows_total - row0 : rc;
+    if (saved) use_saved(w, sv, cfg->prec, row0);
     RN_TRY(forward_chunk(c, w, row0, rows, *out, want_normals, true));
   }
   return RN_OK;
@@ -708,13 +760,18 @@ extern "C" int rn_mlp_forward(const RnMlpConfig* cfg, const void* packed, const 
 extern "C" int rn_mlp_backward(const RnMlpConfig* cfg, const void* packed, const float* tdist, const float* origins,
                                const float* dirs, const float* viewdirs, const float* radii, int64_t n_rays, int s,
                                const RnMlpOutputs* g, float* const* grads, void* workspace, size_t workspace_bytes,
-                               void* stream) {
+                               const void* saved, size_t saved_bytes, void* stream) {
   Ctx c;
   RN_TRY(make_ctx(c, cfg, packed, tdist, origins, dirs, viewdirs, radii, s, stream));
   if (!g || !grads) return rn_set_error(RN_ERR_ARG, "rn_mlp_backward: null gradients");
   const int64_t rows_total = n_rays * s;
   const int64_t rc = cfg->chunk_rows;
-  Workspace w = carve(workspace, cfg->prec, rc, 2);
+  Workspace w = carve(workspace, cfg->prec, rc, 2, saved != nullptr);
+  Saved sv;
+  if (saved) {
+    sv = carve_saved(const_cast<void*>(saved), cfg->prec, rows_total);
+    if (sv.bytes > saved_bytes) return rn_set_error(RN_ERR_ARG, "rn_mlp_backward: saved region too small");
+  }
   const size_t scratch_off = w.bytes;
   if (w.bytes + (size_t)rc * 16 * 4 > workspace_bytes) return rn_set_error(RN_ERR_ARG, "rn_mlp_backward: workspace too small");
   // scratch destinations for the per-sample head outputs of the recompute pass (density 1, normals_pred 3,
@@ -737,9 +794,13 @@ extern "C" int rn_mlp_backward(const RnMlpConfig* cfg, const void* packed, const
     tmp.normals_pred = scratch + 2 * rc - row0 * 3;
     tmp.grad_pred = scratch + 5 * rc - row0 * 3;
     tmp.tint = scratch + 8 * rc - row0 * 3;
-    c.algo = false;
-    RN_TRY(forward_chunk(c, w, row0, rows, tmp, false, false));
-    c.algo = true;
+    if (saved) {
+      use_saved(w, sv, cfg->prec, row0);
+    } else {
+      c.algo = false;
+      RN_TRY(forward_chunk(c, w, row0, rows, tmp, false, false));
+      c.algo = true;
+    }
     if (c.chain) {
       RN_TRY(backward_chunk_chain(c, w, row0, rows, *g));
     } else {

@@ -170,7 +170,7 @@ class MLP(nn.Module):
                               _lib.PREC_BY_NAME[self.precision], self.srgb_mapping, self.srgb_mapping_normalization,
                               float(self.density_bias), float(self.roughness_bias), float(self.rgb_premultiplier),
                               float(self.rgb_bias), float(self.rgb_padding), int(self.chunk_rows), int(self.gemm_impl))
-        density, rgb, normals, npred, gpred, tint, diffuse, spec, rough = out
+        density, rgb, normals, npred, gpred, tint, diffuse, spec, rough, _saved = out
         v3 = lambda t: t.reshape(lead + (s, 3))
         return dict(density=density.reshape(lead + (s,)), rgb=v3(rgb), normals=v3(normals) if training else None,
                     normals_pred=v3(npred), grad_pred=v3(gpred), tint=v3(tint), diffuse=v3(diffuse),

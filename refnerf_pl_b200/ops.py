@@ -274,9 +274,17 @@ def _mlp_config(prec, srgb_mapping, srgb_norm, density_bias, roughness_bias, rgb
                             rgb_bias, rgb_padding, chunk_rows, gemm_impl)
 
 
-def default_chunk_rows(n_rows):
+def default_chunk_rows(n_rows, training=False):
+    """Rows per internal chunk.  Training keeps whole levels in flight (the saved-activation region is sized for all
+    rows anyway, and the wgrad kernels amortise their fp32 reduction over the rows of one launch); eval only needs
+    enough rows to fill the machine."""
     rows = (n_rows + 127) // 128 * 128
-    return max(128, min(rows, 262144))
+    return max(128, min(rows, 2097152 if training else 262144))
+
+
+# Training keeps every activation of the forward for the backward (no recompute) while that fits comfortably in
+# HBM; beyond this many bytes per level the backward recomputes chunk by chunk instead.
+SAVED_BYTES_CAP = 48 << 30
 
 
 @torch.library.custom_op(f'{NS}::mlp_pack', mutates_args=(), device_types='cuda')
@@ -298,7 +306,8 @@ def mlp_forward(tdist: Tensor, origins: Tensor, dirs: Tensor, viewdirs: Tensor, 
                 roughness_bias: float, rgb_premultiplier: float, rgb_bias: float, rgb_padding: float, chunk_rows: int,
                 gemm_impl: int) -> List[Tensor]:
     """-> [density [N,S], rgb, normals (empty in eval), normals_pred, grad_pred, tint, diffuse, specular [N,S,3],
-    roughness [N,S,1]].  `params` only carries autograd edges; the arithmetic reads `packed`."""
+    roughness [N,S,1], saved (uint8: activations kept for the backward; empty in eval / when over the cap)].
+    `params` only carries autograd edges; the arithmetic reads `packed`."""
     lib = _lib.load()
     n, s1 = tdist.shape
     s = s1 - 1
@@ -308,17 +317,22 @@ def mlp_forward(tdist: Tensor, origins: Tensor, dirs: Tensor, viewdirs: Tensor, 
     rgb, npred, gpred, tint, diffuse, spec = (f(n, s, 3) for _ in range(6))
     normals = f(n, s, 3) if training else f(0)
     if chunk_rows <= 0:
-        chunk_rows = default_chunk_rows(n * s)
+        chunk_rows = default_chunk_rows(n * s, training)
     cfg = _mlp_config(prec, srgb_mapping, srgb_norm, density_bias, roughness_bias, rgb_premultiplier, rgb_bias,
                       rgb_padding, chunk_rows, gemm_impl)
-    ws_bytes = lib.rn_mlp_workspace_bytes(ctypes.byref(cfg), 1 if training else 0)
+    saved_bytes = lib.rn_mlp_saved_bytes(ctypes.byref(cfg), n * s) if training else 0
+    if saved_bytes > SAVED_BYTES_CAP:
+        saved_bytes = 0
+    saved = torch.empty((saved_bytes,), device=dev, dtype=torch.uint8)
+    ws_bytes = lib.rn_mlp_workspace_bytes(ctypes.byref(cfg), (2 if saved_bytes else 1) if training else 0)
     ws = torch.empty((ws_bytes,), device=dev, dtype=torch.uint8)
     outs = _lib.RnMlpOutputs(density.data_ptr(), rgb.data_ptr(), normals.data_ptr() if training else None,
                              npred.data_ptr(), gpred.data_ptr(), tint.data_ptr(), diffuse.data_ptr(), spec.data_ptr(),
                              rough.data_ptr())
     _lib.check(lib.rn_mlp_forward(ctypes.byref(cfg), _ptr(packed), _ptr(tdist), _ptr(origins), _ptr(dirs),
-                                  _ptr(viewdirs), _ptr(radii), n, s, ctypes.byref(outs), _ptr(ws), ws_bytes, _stream()))
-    return [density, rgb, normals, npred, gpred, tint, diffuse, spec, rough]
+                                  _ptr(viewdirs), _ptr(radii), n, s, ctypes.byref(outs), _ptr(ws), ws_bytes,
+                                  _ptr(saved) if saved_bytes else None, saved_bytes, _stream()))
+    return [density, rgb, normals, npred, gpred, tint, diffuse, spec, rough, saved]
 
 
 @mlp_forward.register_fake
@@ -328,12 +342,12 @@ def _(tdist, origins, dirs, viewdirs, radii, params, packed, training, prec, srg
     s = s1 - 1
     f = lambda *shape: tdist.new_empty(shape)
     return [f(n, s), f(n, s, 3), f(n, s, 3) if training else f(0), f(n, s, 3), f(n, s, 3), f(n, s, 3), f(n, s, 3),
-            f(n, s, 3), f(n, s, 1)]
+            f(n, s, 3), f(n, s, 1), tdist.new_empty((0,), dtype=torch.uint8)]
 
 
 @torch.library.custom_op(f'{NS}::mlp_backward', mutates_args=(), device_types='cuda')
 def mlp_backward(tdist: Tensor, origins: Tensor, dirs: Tensor, viewdirs: Tensor, radii: Tensor, packed: Tensor,
-                 grads: Sequence[Tensor], prec: int, srgb_mapping: bool, srgb_norm: bool, density_bias: float,
+                 saved: Tensor, grads: Sequence[Tensor], prec: int, srgb_mapping: bool, srgb_norm: bool, density_bias: float,
                  roughness_bias: float, rgb_premultiplier: float, rgb_bias: float, rgb_padding: float, chunk_rows: int,
                  gemm_impl: int) -> List[Tensor]:
     """grads: [g_density, g_rgb, g_normals_pred, g_grad_pred, g_tint, g_diffuse, g_specular, g_roughness] (empty = 0)
@@ -343,10 +357,11 @@ def mlp_backward(tdist: Tensor, origins: Tensor, dirs: Tensor, viewdirs: Tensor,
     s = s1 - 1
     dev = tdist.device
     if chunk_rows <= 0:
-        chunk_rows = default_chunk_rows(n * s)
+        chunk_rows = default_chunk_rows(n * s, True)
     cfg = _mlp_config(prec, srgb_mapping, srgb_norm, density_bias, roughness_bias, rgb_premultiplier, rgb_bias,
                       rgb_padding, chunk_rows, gemm_impl)
-    ws_bytes = lib.rn_mlp_workspace_bytes(ctypes.byref(cfg), 1)
+    saved_bytes = saved.numel()
+    ws_bytes = lib.rn_mlp_workspace_bytes(ctypes.byref(cfg), 2 if saved_bytes else 1)
     ws = torch.empty((ws_bytes,), device=dev, dtype=torch.uint8)
     g = [_f32c(x) for x in grads]
     pg = lambda t: t.data_ptr() if t.numel() else None
@@ -355,12 +370,12 @@ def mlp_backward(tdist: Tensor, origins: Tensor, dirs: Tensor, viewdirs: Tensor,
     arr = (ctypes.c_void_p * _lib.NUM_PARAMS)(*[t.data_ptr() for t in out])
     _lib.check(lib.rn_mlp_backward(ctypes.byref(cfg), _ptr(packed), _ptr(tdist), _ptr(origins), _ptr(dirs),
                                    _ptr(viewdirs), _ptr(radii), n, s, ctypes.byref(gs), arr, _ptr(ws), ws_bytes,
-                                   _stream()))
+                                   _ptr(saved) if saved_bytes else None, saved_bytes, _stream()))
     return out
 
 
 @mlp_backward.register_fake
-def _(tdist, origins, dirs, viewdirs, radii, packed, grads, prec, srgb_mapping, srgb_norm, density_bias, roughness_bias,
+def _(tdist, origins, dirs, viewdirs, radii, packed, saved, grads, prec, srgb_mapping, srgb_norm, density_bias, roughness_bias,
       rgb_premultiplier, rgb_bias, rgb_padding, chunk_rows, gemm_impl):
     lib = _lib.load()
     return [tdist.new_empty((lib.rn_mlp_param_numel(i),)) for i in range(_lib.NUM_PARAMS)]
@@ -368,19 +383,19 @@ def _(tdist, origins, dirs, viewdirs, radii, packed, grads, prec, srgb_mapping, 
 
 def _mlp_setup(ctx, inputs, output):
     (tdist, origins, dirs, viewdirs, radii, params, packed, training, *scalars) = inputs
-    ctx.save_for_backward(tdist, origins, dirs, viewdirs, radii, packed)
+    ctx.save_for_backward(tdist, origins, dirs, viewdirs, radii, packed, output[9])
     ctx.scalars = scalars
     ctx.param_shapes = [p.shape for p in params]
-    ctx.mark_non_differentiable(output[2])  # density-gradient normals are a constant
+    ctx.mark_non_differentiable(output[2], output[9])  # density-gradient normals are a constant
     ctx.set_materialize_grads(False)
 
 
 def _mlp_backward(ctx, grads):
-    tdist, origins, dirs, viewdirs, radii, packed = ctx.saved_tensors
+    tdist, origins, dirs, viewdirs, radii, packed, saved = ctx.saved_tensors
     empty = tdist.new_empty((0,))
     order = (0, 1, 3, 4, 5, 6, 7, 8)  # density, rgb, normals_pred, grad_pred, tint, diffuse, specular, roughness
     g = [grads[i] if grads[i] is not None else empty for i in order]
-    pg = mlp_backward(tdist, origins, dirs, viewdirs, radii, packed, g, *ctx.scalars)
+    pg = mlp_backward(tdist, origins, dirs, viewdirs, radii, packed, saved, g, *ctx.scalars)
     pg = [t.view(shape) for t, shape in zip(pg, ctx.param_shapes)]
     return (None, None, None, None, None, pg, None, None) + (None,) * len(ctx.scalars)
 

@@ -172,6 +172,31 @@ def test_fused_backward_chain_matches_per_layer_gemms():
         assert float((a - b).norm()) <= 1e-4 * float(b.norm()) + 1e-12, (k, float((a - b).norm() / b.norm()))
 
 
+def test_saved_activation_backward_matches_recompute(monkeypatch):
+    """Training keeps the activations of the forward for the backward; above ops.SAVED_BYTES_CAP the backward
+    recomputes them chunk by chunk instead.  Same arithmetic either way (only the wgrad atomics reorder)."""
+    from refnerf_pl_b200 import ops, synthetic, train_utils
+    p = O.init_params(seed=6, bias_std=0.1, weight_scale=1.2)
+    rays = synthetic.blender_rays(520, seed=11)
+    gt = torch.tensor(synthetic.gt_rgb(520, 11), device=DEV)
+    default_cap = ops.SAVED_BYTES_CAP
+    for prec in ('bf16', 'bf16x3'):
+        grads = {}
+        for cap in (default_cap, 0):
+            monkeypatch.setattr(ops, 'SAVED_BYTES_CAP', cap)
+            model, cfg = build_model(prec, mlp_kwargs=dict(chunk_rows=16384))   # several chunks, ragged tail
+            load_params(model, p)
+            model.train(True)
+            r = rays_obj(rays)
+            rend, hist = model(r, 1.0, True)
+            loss, _ = train_utils.total_loss(model, r.viewdirs, r.lossmult, gt, rend, hist, cfg)
+            loss.backward()
+            grads[cap] = {k: v.grad.clone() for k, v in model.nerf_mlp.named_parameters()}
+        for k in grads[0]:
+            a, b = grads[default_cap][k].double(), grads[0][k].double()
+            assert float((a - b).norm()) <= 1e-4 * float(b.norm()) + 1e-12, (prec, k, float((a - b).norm() / b.norm()))
+
+
 def test_checkpoint_names_match_reference():
     model, _ = build_model('fp32')
     sd = model.state_dict()
