@@ -174,8 +174,6 @@ RN_API int rn_gemm_bench(int64_t m, int prec, int impl, int iters, float* ms_out
  * cls (0 = tcgen05 fwd/dgrad GEMM, 1 = tcgen05 wgrad, 2 = SIMT GEMMs, 3 = fused tcgen05 forward chain), the number of launches, their
  * summed device time in ms and the algorithmic FLOPs they carried, then clears the class. */
 RN_API int64_t rn_launch_count(void);
-/* fused-chain kernel selection (process-wide): 0 = CTA-pair kernel (cta_group::2, default), 1 = single-CTA kernel */
-RN_API int rn_set_chain_impl(int impl);
 RN_API int rn_prof_enable(int on);
 RN_API int rn_prof_summary(int cls, int64_t* launches, double* total_ms, double* algo_flops);
 

@@ -54,7 +54,6 @@ _SIGNATURES = {
     'rn_wgrad_test': (c_int, [_P, _P, c_int64, c_int, c_int, c_int, c_int, _P, _P, c_size_t, _P]),
     'rn_gemm_bench': (c_int, [c_int64, c_int, c_int, c_int, POINTER(c_float), _P, c_size_t, _P]),
     'rn_launch_count': (c_int64, []),
-    'rn_set_chain_impl': (c_int, [c_int]),
     'rn_prof_enable': (c_int, [c_int]),
     'rn_prof_summary': (c_int, [c_int, POINTER(c_int64), POINTER(c_double), POINTER(c_double)]),
 }

@@ -14,7 +14,8 @@
 //     them, so one L2 -> SMEM weight transfer serves 512 rows.  Input-tile K blocks (layer 0 and the skip
 //     layer) stream through the same ring just in time.
 //   * saves for the wgrad kernels (training) leave as TMA stores straight from the swizzled activation
-//     tile; eval touches HBM only for the chain input and the head outputs.
+//     tile; ReLU masks travel as 1 bit per activation (32 B per row and layer), written by the forward chain and
+//     prefetched one tile ahead by the dgrad chains; eval touches HBM only for the chain input and the head outputs.
 //
 // Roles per CTA (384 threads): warp 0 TMA producer, warp 1 MMA issuer (leader CTA only), warp 2 TMEM
 // allocator, warps 4-11 epilogue (warp % 4 = TMEM lane quadrant, (warp - 4) / 4 = column half).
@@ -120,16 +121,38 @@ __device__ __forceinline__ uint32_t make_idesc2(int n) {
   return d;
 }
 
-// epilogue for 16 consecutive columns of one row of a global (non-hidden) op; v holds the fp32 accumulators
-__device__ __forceinline__ void epi_global16(const GemmEpilogue& e, size_t row, int col, float* v) {
-  if (e.bias) {
-    const float4* b4 = reinterpret_cast<const float4*>(e.bias + col);
+__device__ __forceinline__ void mbar_arrive_cluster_addr(uint32_t cluster_addr) {
+  // default semantics (release at CTA scope), as CUTLASS' ClusterBarrier::arrive(cta_id): the data this signals is
+  // this CTA's own shared memory / TMEM, ordered by fence.proxy.async / tcgen05.fence before the arrive
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// two floats -> bf16x2 with ReLU folded into the conversion (one F2FP instruction)
+__device__ __forceinline__ uint32_t pack_relu_bf16x2(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+__device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t* r) { tmem_ld32(taddr, r); }
+
+// ReLU masks travel as 1 bit per activation: word w of a row covers columns [32w, 32w+32); inside a word the
+// packed bf16 pair i (columns 2i, 2i+1) owns bits i and 16+i.
+__device__ __forceinline__ uint32_t relu_bits_of(const uint32_t* packed /*16 bf16x2, non-negative*/) {
+  uint32_t bits = 0;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const float4 b = __ldg(b4 + i);
-      v[4 * i] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w;
-    }
-  }
+  for (int i = 0; i < 16; ++i) bits += __vminu2(packed[i], 0x00010001u) << i;   // 1 where the half is nonzero
+  return bits;
+}
+// keep / zero the two halves of packed pair i according to bits i and 16+i
+__device__ __forceinline__ uint32_t apply_relu_bits(uint32_t bits, int i, uint32_t packed) {
+  const uint32_t x = i <= 7 ? (bits << (7 - i)) : (bits >> (i - 7));   // bit i -> 7, bit 16+i -> 23
+  uint32_t m;   // prmt with selector msb set = replicate the sign bit of the selected byte (__byte_perm drops that bit)
+  asm("prmt.b32 %0, %1, %2, 0xAA88;" : "=r"(m) : "r"(x), "r"(0u));
+  return packed & m;
+}
+
+// epilogue for 16 consecutive columns of one row of a global (non-hidden) op; v holds the fp32 accumulators
+// (bias already added by the caller)
+__device__ __forceinline__ void epi_global16(const GemmEpilogue& e, size_t row, int col, float* v) {
   if (e.relu) {
 #pragma unroll
     for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
@@ -172,11 +195,11 @@ struct PairOp {
   int kb_act;      // K blocks read from the resident activation tile (0 or 4)
   int kb_in;       // K blocks read from the chain input tile (streamed through the ring)
   int kind;        // 0: hidden (result -> activation tile [+ TMA save]); 1: global epilogue
-  int mode;        // hidden transform: 0 = bias + ReLU (forward), 1 = ReLU mask from a saved activation (backward)
   int gepi;        // kind 1: which global epilogue
   int save;        // hidden: TMA-store the result through maps.save[op]
-  const float* bias;       // mode 0
-  const uint16_t* mask;    // mode 1: bf16 [m,256]; positive entries pass the gradient
+  const float* bias;       // forward hidden ops / global ops with a bias: [n] floats (padded to a multiple of 4)
+  const uint32_t* mask_bits;   // backward hidden ops: ReLU bits [m, 8]
+  uint32_t* save_bits;         // forward hidden ops: optional ReLU bits of the result [m, 8]
 };
 struct PairParams {
   int num_ops;
@@ -191,6 +214,8 @@ struct PairMaps {
   CUtensorMap save[kMaxOps];
 };
 
+// MODE 0: forward chain (hidden ops: bias + ReLU); MODE 1: backward / dgrad chain (hidden ops: ReLU bit mask)
+template <int MODE>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
 chain_pair_kernel(const __grid_constant__ PairMaps maps, const __grid_constant__ PairParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -200,7 +225,6 @@ chain_pair_kernel(const __grid_constant__ PairMaps maps, const __grid_constant__
   uint64_t* acc_full = bars + 16;      // [2]  per CTA, multicast MMA commit
   uint64_t* acc_free = bars + 18;      // [2]  leader's: 16 arrivals (8 epilogue warps x 2 CTAs)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
-  float* bias_s = reinterpret_cast<float*>(smem + kSmemBias);   // [2][256]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
@@ -324,39 +348,55 @@ chain_pair_kernel(const __grid_constant__ PairMaps maps, const __grid_constant__
       }
     }
   } else if (warp >= 4) {
-    // ===== epilogue warps: q = TMEM lane quadrant (32 rows), h = column half (128 columns = chunks 2h, 2h+1) =====
+    // ===== epilogue warps: q = TMEM lane quadrant (32 rows), h = column half (128 columns = K blocks 2h, 2h+1) =====
     const int q = (warp - 4) & 3;
     const int h = (warp - 4) >> 2;
     const int r_in_tile = q * 32 + lane;
-    const uint32_t bias_u32 = smem_u32(bias_s);
+    // bias staging: two buffers (op parity) x two column halves x 128 floats.  The four warps of a column half
+    // write identical values, so no cross-warp barrier is needed: every warp only relies on its own stores.
+    const uint32_t bias_half = smem_base + kSmemBias + (uint32_t)h * 512u;
     const uint32_t free_addr0 = map_to_cta(smem_u32(&acc_free[0]), 0);   // leader's acc_free[0]; [1] is 8 bytes on
     uint32_t opcount = 0;
-    // TMA-store bookkeeping (warp-uniform): has_group[t] = a committed bulk group may still be reading this warp's
-    // part of act[t]; newer[t] = bulk groups committed after it (0 or 1, the tiles alternate)
-    uint32_t has_group = 0, newer = 0;   // bit t
+    uint32_t has_group = 0, newer = 0;   // TMA-store bookkeeping, bit t (see below)
     bool any_store = false;
+    uint4 bits_next = make_uint4(0, 0, 0, 0);
+    auto load_bits = [&](int64_t st, int l, int t) -> uint4 {
+      // ReLU bits of this thread's row for op l (this warp's 128 columns = words 4h .. 4h+3)
+      uint4 b = make_uint4(0, 0, 0, 0);
+      if (l < p.num_ops && st < num_super && p.op[l].kind == 0) {
+        const int64_t row = st * 512 + t * 256 + (int64_t)rank * 128 + r_in_tile;
+        if (row < p.m) b = __ldg(reinterpret_cast<const uint4*>(p.op[l].mask_bits + (size_t)row * 8) + h);
+      }
+      return b;
+    };
+    if (MODE == 1) bits_next = load_bits(cluster_id, 0, 0);
     for (int64_t st = cluster_id; st < num_super; st += num_clusters) {
       for (int l = 0; l < p.num_ops; ++l, ++opcount) {
         const PairOp& L = p.op[l];
         const bool hidden = L.kind == 0;
-        const uint32_t bias_buf = bias_u32 + (opcount & 1u) * 1024u;
-        if (hidden && L.mode == 0) {
-          // stage this op's bias (double-buffered by op parity; one named barrier among the 8 epilogue warps)
-          const int tid = threadIdx.x - 128;
-          if (tid < 64) {
-            const float4 bv = __ldg(reinterpret_cast<const float4*>(L.bias) + tid);
-            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(bias_buf + 16u * tid), "f"(bv.x), "f"(bv.y), "f"(bv.z),
-                         "f"(bv.w)
-                         : "memory");
-          }
-          asm volatile("bar.sync 1, 256;" ::: "memory");
-        }
+        const float* bias_ptr = hidden ? (MODE == 0 ? L.bias : nullptr) : p.gepi[L.gepi].bias;
+        const uint32_t bias_buf = bias_half + (opcount & 1u) * 1024u;
+        float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (bias_ptr && h * 128 + 4 * lane < L.n) bv = __ldg(reinterpret_cast<const float4*>(bias_ptr + h * 128) + lane);
         for (int t = 0; t < 2; ++t) {
           const int64_t row = st * 512 + t * 256 + (int64_t)rank * 128 + r_in_tile;
           const bool row_ok = row < p.m;
+          uint4 bits_cur = bits_next;
+          if (MODE == 1) {
+            // prefetch the bits of the next (op, tile) this warp will process
+            if (t == 0) bits_next = load_bits(st, l, 1);
+            else if (l + 1 < p.num_ops) bits_next = load_bits(st, l + 1, 0);
+            else bits_next = load_bits(st + num_clusters, 0, 0);
+          }
           mbar_wait(&acc_full[t], opcount & 1u);
           tc_fence_after();
-          const uint32_t taddr = tmem_base + (uint32_t)t * 256u + ((uint32_t)(q * 32) << 16);
+          if (t == 0 && bias_ptr) {
+            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(bias_buf + 16u * lane), "f"(bv.x), "f"(bv.y), "f"(bv.z),
+                         "f"(bv.w)
+                         : "memory");
+            __syncwarp();
+          }
+          const uint32_t taddr = tmem_base + (uint32_t)t * 256u + ((uint32_t)(q * 32) << 16) + (uint32_t)(h * 128);
           if (hidden) {
             if (has_group >> t & 1u) {
               // the TMA stores that read this warp's part of act[t] must have drained it before it is overwritten
@@ -367,54 +407,44 @@ chain_pair_kernel(const __grid_constant__ PairMaps maps, const __grid_constant__
               has_group &= ~(1u << t);
             }
             const uint32_t act_row = smem_base + (uint32_t)(t * kActBytes + r_in_tile * 128);
-#pragma unroll 1
-            for (int cc = 0; cc < 2; ++cc) {
-              const int c = 2 * h + cc;   // 64-column chunk = activation K block c
+            const uint32_t bits_arr[4] = {bits_cur.x, bits_cur.y, bits_cur.z, bits_cur.w};
+            uint32_t bits_out[4];
+            uint32_t ra[32], rb[32];
+            tmem_ld32(taddr, ra);
 #pragma unroll
-              for (int half = 0; half < 2; ++half) {
-                const int col0 = c * 64 + half * 32;
-                uint32_t r[32];
-                uint32_t mk[16];
-                tmem_ld32(taddr + (uint32_t)col0, r);
-                if (L.mode == 1 && row_ok) {
-                  const uint16_t* mp = L.mask + (size_t)row * 256 + col0;
-                  ldg256(mp, mk);
-                  ldg256(mp + 16, mk + 8);
+            for (int g = 0; g < 4; ++g) {   // 32-column groups of this warp's 128 columns; TMEM loads run one group ahead
+              uint32_t* cur = (g & 1) ? rb : ra;
+              uint32_t* nxt = (g & 1) ? ra : rb;
+              tmem_ld_wait();
+              if (g < 3) tmem_ld32(taddr + (uint32_t)((g + 1) * 32), nxt);
+              uint32_t packed[16];
+              if (MODE == 0) {
+                const uint32_t baddr = bias_buf + (uint32_t)g * 128u;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                  const float4 b = lds128f(baddr + 16u * i);
+                  packed[2 * i] = pack_relu_bf16x2(__uint_as_float(cur[4 * i]) + b.x, __uint_as_float(cur[4 * i + 1]) + b.y);
+                  packed[2 * i + 1] = pack_relu_bf16x2(__uint_as_float(cur[4 * i + 2]) + b.z, __uint_as_float(cur[4 * i + 3]) + b.w);
                 }
-                tmem_ld_wait();
-                uint32_t packed[16];
-                if (L.mode == 0) {
-                  const uint32_t baddr = bias_buf + (uint32_t)col0 * 4u;
+                if (L.save_bits) bits_out[g] = relu_bits_of(packed);
+              } else {
 #pragma unroll
-                  for (int i = 0; i < 8; ++i) {
-                    const float4 b = lds128f(baddr + 16u * i);
-                    const float v0 = fmaxf(__uint_as_float(r[4 * i]) + b.x, 0.f), v1 = fmaxf(__uint_as_float(r[4 * i + 1]) + b.y, 0.f);
-                    const float v2 = fmaxf(__uint_as_float(r[4 * i + 2]) + b.z, 0.f), v3 = fmaxf(__uint_as_float(r[4 * i + 3]) + b.w, 0.f);
-                    packed[2 * i] = pack_bf16x2(v0, v1);
-                    packed[2 * i + 1] = pack_bf16x2(v2, v3);
-                  }
-                } else {
+                for (int i = 0; i < 16; ++i)
+                  packed[i] = apply_relu_bits(bits_arr[g], i, pack_bf16x2(__uint_as_float(cur[2 * i]), __uint_as_float(cur[2 * i + 1])));
+              }
+              const int c = 2 * h + (g >> 1);   // activation K block
+              const uint32_t blk = act_row + (uint32_t)(c * kBlkBytes);
 #pragma unroll
-                  for (int i = 0; i < 16; ++i) {
-                    const uint32_t mlo = mk[i] & 0xffffu, mhi = mk[i] >> 16;
-                    const bool plo = row_ok && mlo != 0u && mlo < 0x8000u, phi = row_ok && mhi != 0u && mhi < 0x8000u;
-                    const float v0 = plo ? __uint_as_float(r[2 * i]) : 0.f, v1 = phi ? __uint_as_float(r[2 * i + 1]) : 0.f;
-                    packed[i] = pack_bf16x2(v0, v1);
-                  }
-                }
-                const uint32_t blk = act_row + (uint32_t)(c * kBlkBytes);
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                  const uint32_t pos16 = (uint32_t)((half * 4 + u) ^ (r_in_tile & 7));
-                  sts128(blk + pos16 * 16u, packed[4 * u], packed[4 * u + 1], packed[4 * u + 2], packed[4 * u + 3]);
-                }
+              for (int u = 0; u < 4; ++u) {
+                const uint32_t pos16 = (uint32_t)(((g & 1) * 4 + u) ^ (r_in_tile & 7));
+                sts128(blk + pos16 * 16u, packed[4 * u], packed[4 * u + 1], packed[4 * u + 2], packed[4 * u + 3]);
               }
             }
             fence_proxy_async();   // generic-proxy smem writes -> visible to the tensor core and to TMA stores
             tc_fence_before();
             __syncwarp();
             if (lane == 0) {
-              mbar_arrive_remote(free_addr0 + 8u * t);
+              mbar_arrive_cluster_addr(free_addr0 + 8u * t);
               if (L.save) {
                 const int64_t row_w = st * 512 + t * 256 + (int64_t)rank * 128 + q * 32;
                 if (row_w < p.m) {
@@ -433,11 +463,14 @@ chain_pair_kernel(const __grid_constant__ PairMaps maps, const __grid_constant__
               if (has_group >> (t ^ 1) & 1u) newer |= 1u << (t ^ 1);
               any_store = true;
             }
+            if (MODE == 0 && L.save_bits && row_ok)
+              *(reinterpret_cast<uint4*>(L.save_bits + (size_t)row * 8) + h) = make_uint4(bits_out[0], bits_out[1], bits_out[2], bits_out[3]);
           } else {
             const GemmEpilogue& ge = p.gepi[L.gepi];
-            for (int c0 = h * 32; c0 < L.n; c0 += 64) {
+            const int c_end = L.n < h * 128 + 128 ? L.n : h * 128 + 128;
+            for (int c0 = h * 128; c0 < c_end; c0 += 32) {
               uint32_t r[32];
-              tmem_ld32(taddr + (uint32_t)c0, r);
+              tmem_ld32(taddr + (uint32_t)(c0 - h * 128), r);
               tmem_ld_wait();
               if (row_ok) {
 #pragma unroll
@@ -446,6 +479,14 @@ chain_pair_kernel(const __grid_constant__ PairMaps maps, const __grid_constant__
                     float v[16];
 #pragma unroll
                     for (int e = 0; e < 16; ++e) v[e] = __uint_as_float(r[16 * hh + e]);
+                    if (bias_ptr) {
+                      const uint32_t baddr = bias_buf + (uint32_t)(c0 - h * 128 + 16 * hh) * 4u;
+#pragma unroll
+                      for (int i = 0; i < 4; ++i) {
+                        const float4 b = lds128f(baddr + 16u * i);
+                        v[4 * i] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w;
+                      }
+                    }
                     epi_global16(ge, (size_t)row, c0 + 16 * hh, v);
                   }
                 }
@@ -453,7 +494,7 @@ chain_pair_kernel(const __grid_constant__ PairMaps maps, const __grid_constant__
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive_remote(free_addr0 + 8u * t);
+            if (lane == 0) mbar_arrive_cluster_addr(free_addr0 + 8u * t);
           }
         }
       }
@@ -468,7 +509,7 @@ chain_pair_kernel(const __grid_constant__ PairMaps maps, const __grid_constant__
 
 }  // namespace
 
-int launch_chain_pair(const ChainArgs& a, cudaStream_t st) {
+int launch_chain(const ChainArgs& a, cudaStream_t st) {
   if (a.m <= 0) return RN_OK;
   if (a.num_ops < 1 || a.num_ops > kMaxOps) return rn_set_error(RN_ERR_ARG, "chain: 1..12 ops");
   if (a.in_cols % 64 || a.in_cols < 64 || a.in_cols > 256) return rn_set_error(RN_ERR_ARG, "chain: input tile must be 64..256 columns");
@@ -477,6 +518,7 @@ int launch_chain_pair(const ChainArgs& a, cudaStream_t st) {
   PairParams p;
   memset(&p, 0, sizeof(p));
   int rc;
+  int mode = -1;
   if ((rc = tc::make_map(&maps.in, a.in.hi, a.m, a.in_valid, a.in.ld, kBM))) return rc;
   p.num_ops = a.num_ops;
   p.in_kb = a.in_cols / kBK;
@@ -494,25 +536,34 @@ int launch_chain_pair(const ChainArgs& a, cudaStream_t st) {
     if ((rc = tc::make_map(&maps.w[l], L.w, L.n, ktot, L.w_ld, L.n / 2))) return rc;
     PairOp& o = p.op[l];
     o.n = L.n; o.kb_act = L.kb_act; o.kb_in = L.kb_in;
-    o.kind = L.kind; o.mode = L.mode; o.gepi = L.gepi; o.bias = L.bias;
-    o.mask = reinterpret_cast<const uint16_t*>(L.mask);
+    o.kind = L.kind; o.gepi = L.gepi; o.bias = L.bias;
+    o.mask_bits = L.mask_bits; o.save_bits = L.save_bits;
     o.save = (L.kind == 0 && L.save_hi) ? 1 : 0;
     if (o.save && (rc = tc::make_map(&maps.save[l], L.save_hi, a.m, 256, 256, 32))) return rc;
-    if (L.kind == 0 && L.mode == 0 && !L.bias) return rn_set_error(RN_ERR_ARG, "chain: forward op without bias");
-    if (L.kind == 0 && L.mode == 1 && !L.mask) return rn_set_error(RN_ERR_ARG, "chain: backward op without mask");
+    if (L.kind == 0) {
+      if (mode < 0) mode = L.mode;
+      if (L.mode != mode) return rn_set_error(RN_ERR_ARG, "chain: forward and backward hidden ops cannot be mixed");
+      if (L.mode == 0 && !L.bias) return rn_set_error(RN_ERR_ARG, "chain: forward op without bias");
+      if (L.mode == 1 && !L.mask_bits) return rn_set_error(RN_ERR_ARG, "chain: backward op without ReLU bits");
+    }
   }
+  if (mode < 0) mode = 0;
   p.gepi[0] = a.gepi[0];
   p.gepi[1] = a.gepi[1];
   static bool smem_set = false;
   if (!smem_set) {
-    if ((rc = tc::set_smem(chain_pair_kernel, kSmemTotal))) return rc;
+    if ((rc = tc::set_smem(chain_pair_kernel<0>, kSmemTotal))) return rc;
+    if ((rc = tc::set_smem(chain_pair_kernel<1>, kSmemTotal))) return rc;
     smem_set = true;
   }
   const int64_t supers = (a.m + 511) / 512;
   const int max_clusters = tc::num_sms() / 2;
   const unsigned grid = 2u * (unsigned)(supers < max_clusters ? supers : max_clusters);
   rn_prof_begin(RN_PROF_CHAIN_TC, st, a.algo_flops);
-  chain_pair_kernel<<<grid, 384, kSmemTotal, st>>>(maps, p);
+  if (mode == 0)
+    chain_pair_kernel<0><<<grid, 384, kSmemTotal, st>>>(maps, p);
+  else
+    chain_pair_kernel<1><<<grid, 384, kSmemTotal, st>>>(maps, p);
   rn_prof_end(RN_PROF_CHAIN_TC, st);
   RN_CUDA_CHECK_LAUNCH();
   return RN_OK;

@@ -53,10 +53,10 @@ struct WgradArgs {
   double algo_flops = 0.0;
 };
 
-// Fused chain (bf16, tcgen05): a sequence of GEMM "ops" runs back to back on one 128-row tile with the
+// Fused chain (bf16, tcgen05): a sequence of GEMM "ops" runs back to back on 128-row tiles with the
 // running activation resident in shared memory.  Hidden ops turn the TMEM accumulator into the next A
-// operand (forward: bias + ReLU; backward: ReLU mask read from a saved activation) and may also save it
-// to global memory; global ops run an ordinary GemmEpilogue.  Only weights stream through the TMA ring.
+// operand (forward: bias + ReLU; backward: 1-bit ReLU mask written by the forward chain) and may also save it
+// to global memory; global ops run an ordinary GemmEpilogue.  Weights stream through the TMA ring.
 struct ChainOpArgs {
   int n = 0;                 // output columns; 256 for hidden ops
   int kb_act = 0;            // 64-wide K blocks from the running activation (0 or 4)
@@ -67,8 +67,9 @@ struct ChainOpArgs {
   const void* w = nullptr;   // bf16 weights [n, (kb_act + kb_in) * 64] K-major
   int w_ld = 0;
   const float* bias = nullptr;
-  const void* mask = nullptr;  // bf16 [m,256] saved activation
-  void* save_hi = nullptr;     // optional bf16 [m,256] copy of the hidden result
+  const uint32_t* mask_bits = nullptr;  // mode 1: ReLU bits of the matching forward activation, [m, 8] words
+  void* save_hi = nullptr;              // optional bf16 [m,256] copy of the hidden result (TMA store)
+  uint32_t* save_bits = nullptr;        // mode 0: optional ReLU bits of the result, [m, 8] words
 };
 struct ChainArgs {
   int64_t m = 0;
@@ -80,9 +81,7 @@ struct ChainArgs {
   GemmEpilogue gepi[2];
   double algo_flops = 0.0;
 };
-int launch_chain(const ChainArgs& a, cudaStream_t st);        // dispatch (rn_set_chain_impl)
-int launch_chain_pair(const ChainArgs& a, cudaStream_t st);   // chain_pair.cu: CTA pairs, cta_group::2, two row tiles in flight
-int launch_chain_single(const ChainArgs& a, cudaStream_t st); // gemm_tc.cu: one CTA per tile (kept as an A/B reference)
+int launch_chain(const ChainArgs& a, cudaStream_t st);   // chain_pair.cu: CTA pairs, cta_group::2, two row tiles in flight
 
 int launch_gemm(const GemmArgs& g, cudaStream_t st);
 int launch_wgrad(const WgradArgs& g, cudaStream_t st);

@@ -497,259 +497,6 @@ wgrad2_tc_kernel(const __grid_constant__ WgMaps maps, int64_t m, int64_t rows_pe
   if (warp == 2) tmem_dealloc(tmem_base, NSLAB * 256);
 }
 
-// ---------------------------------------------------------------------------------------------
-// Fused forward chain (bf16): up to 9 GEMM layers over one 128-row tile with the activations resident
-// in shared memory.  Hidden layers: TMEM accumulator -> bias + ReLU -> bf16 -> written back (128B
-// swizzle, K-major) as the next layer's A operand, 64 columns (= one K block) at a time so the next
-// layer's MMAs start as soon as its first K block exists.  Weights stream through a TMA ring; the
-// input tile (x0 / v0) stays resident for layer 0 and the skip layer.  Only the last layer (heads /
-// rgb head) and, in training, the optional activation saves touch global memory.
-// ---------------------------------------------------------------------------------------------
-constexpr int kChainMaxOps = 12;
-struct ChainOp {
-  int n;           // MMA N = output columns (multiple of 16)
-  int kb_act;      // K blocks read from the resident activation tile (0 or 4)
-  int kb_in;       // K blocks read from the resident input tile
-  int last_in_use; // this op is the last reader of the input tile
-  int kind;        // 0: hidden (result -> next activation tile in smem [+ global save]); 1: global epilogue
-  int mode;        // hidden transform: 0 = bias + ReLU (forward), 1 = ReLU mask from a saved activation (backward)
-  int gepi;        // kind 1: which global epilogue
-  const float* bias;       // mode 0
-  const uint16_t* mask;    // mode 1: bf16 [m,256]; positive entries pass the gradient
-  void* save_hi;           // optional bf16 [m,256] copy of the hidden result
-};
-struct ChainParams {
-  int num_ops;
-  int in_kb;       // K blocks of the input tile (1..4)
-  int stages;
-  int64_t m;
-  ChainOp op[kChainMaxOps];
-  GemmEpilogue gepi[2];
-};
-struct ChainMaps {
-  CUtensorMap in;
-  CUtensorMap w[kChainMaxOps];
-};
-
-__global__ void __launch_bounds__(384, 1)
-chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__ ChainParams p) {
-  constexpr int kStageBytes = 256 * kBK * 2;  // 32 KB weight K block
-  constexpr int kBlkBytes = kBM * kBK * 2;    // 16 KB activation K block
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint8_t* s_act = smem;                               // 4 K blocks
-  uint8_t* s_in = s_act + 4 * kBlkBytes;               // in_kb K blocks
-  uint8_t* s_w = s_in + p.in_kb * kBlkBytes;           // weight ring
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_w + p.stages * kStageBytes);
-  uint64_t* w_full = bars;            // [stages]
-  uint64_t* w_empty = bars + 8;       // [stages]
-  uint64_t* a_ready = bars + 16;      // [4]
-  uint64_t* tfull = bars + 20;        // [2]
-  uint64_t* tempty = bars + 22;       // [2]
-  uint64_t* in_full = bars + 24;
-  uint64_t* in_empty = bars + 25;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 26);
-  float* bias_s = reinterpret_cast<float*>(bars + 32);  // [256] bias of the op being drained
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int64_t num_tiles = (p.m + kBM - 1) / kBM;
-
-  if (threadIdx.x == 0) {
-    tma_prefetch_desc(&maps.in);
-    for (int i = 0; i < p.num_ops; ++i) tma_prefetch_desc(&maps.w[i]);
-    for (int i = 0; i < p.stages; ++i) {
-      mbar_init(&w_full[i], 1);
-      mbar_init(&w_empty[i], 1);
-    }
-    for (int i = 0; i < 4; ++i) mbar_init(&a_ready[i], 8);
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&tfull[i], 1);
-      mbar_init(&tempty[i], 8);
-    }
-    mbar_init(in_full, 1);
-    mbar_init(in_empty, 1);
-    fence_barrier_init();
-  }
-  if (warp == 2) tmem_alloc(tmem_slot, kTmemCols);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-
-  if (warp == 0 && lane == 0) {
-    // ===== TMA producer: input tile, then the weight K blocks of every op in order =====
-    int stage = 0;
-    uint32_t phase = 0, in_phase = 0;
-    for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int m0 = (int)(tile * kBM);
-      mbar_wait(in_empty, in_phase ^ 1);
-      mbar_arrive_expect_tx(in_full, (uint32_t)(p.in_kb * kBlkBytes));
-      for (int kb = 0; kb < p.in_kb; ++kb) tma_load_2d(s_in + kb * kBlkBytes, &maps.in, in_full, kb * kBK, m0);
-      in_phase ^= 1;
-      for (int l = 0; l < p.num_ops; ++l) {
-        const int nkb = p.op[l].kb_act + p.op[l].kb_in;
-        const uint32_t tx = (uint32_t)p.op[l].n * kBK * 2;
-        for (int kb = 0; kb < nkb; ++kb) {
-          mbar_wait(&w_empty[stage], phase ^ 1);
-          mbar_arrive_expect_tx(&w_full[stage], tx);
-          tma_load_2d(s_w + stage * kStageBytes, &maps.w[l], &w_full[stage], kb * kBK, 0);
-          if (++stage == p.stages) { stage = 0; phase ^= 1; }
-        }
-      }
-    }
-  } else if (warp == 1 && lane == 0) {
-    // ===== MMA issuer =====
-    int stage = 0;
-    uint32_t phase = 0, in_phase = 0;
-    uint32_t hidden_done = 0;  // hidden ops issued so far == activation generations requested
-    int buf = 0;
-    uint32_t tphase = 0;
-    for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      bool in_ready = false;
-      for (int l = 0; l < p.num_ops; ++l) {
-        const ChainOp& L = p.op[l];
-        const uint32_t idesc = make_idesc(L.n, 0, 0);
-        mbar_wait(&tempty[buf], tphase ^ 1);
-        tc_fence_after();
-        const uint32_t tmem_d = tmem_base + (uint32_t)buf * 256u;
-        const int nkb = L.kb_act + L.kb_in;
-        for (int kb = 0; kb < nkb; ++kb) {
-          uint32_t sa;
-          if (kb < L.kb_act) {
-            mbar_wait(&a_ready[kb], (hidden_done - 1u) & 1u);   // generation produced by the latest hidden op
-            sa = smem_u32(s_act + kb * kBlkBytes);
-          } else {
-            if (!in_ready) { mbar_wait(in_full, in_phase); in_ready = true; }
-            sa = smem_u32(s_in + (kb - L.kb_act) * kBlkBytes);
-          }
-          mbar_wait(&w_full[stage], phase);
-          tc_fence_after();
-          const uint32_t sb = smem_u32(s_w + stage * kStageBytes);
-#pragma unroll
-          for (int kk = 0; kk < kBK / kUmmaK; ++kk) {
-            const uint32_t koff = kk * kUmmaK * 2;
-            umma_bf16(tmem_d, make_desc(sa + koff, 16, 1024), make_desc(sb + koff, 16, 1024), idesc, (kb | kk) ? 1u : 0u);
-          }
-          umma_commit(&w_empty[stage]);
-          if (++stage == p.stages) { stage = 0; phase ^= 1; }
-        }
-        umma_commit(&tfull[buf]);
-        if (L.last_in_use) umma_commit(in_empty);
-        if (L.kind == 0) ++hidden_done;
-        if (++buf == 2) { buf = 0; tphase ^= 1; }
-      }
-      in_phase ^= 1;
-    }
-  } else if (warp >= 4) {
-    // ===== epilogue warps: 8 warps = 4 TMEM lane quadrants x 2 column halves of every 64-column chunk =====
-    const int q = (warp - 4) & 3;
-    const int half = (warp - 4) >> 2;
-    int buf = 0;
-    uint32_t tphase = 0;
-    const uint32_t s_act_u32 = smem_u32(s_act);
-    const uint32_t bias_u32 = smem_u32(bias_s);
-    for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int r_in_tile = q * 32 + lane;
-      const int64_t row = tile * kBM + r_in_tile;
-      const bool row_ok = row < p.m;
-      for (int l = 0; l < p.num_ops; ++l) {
-        const ChainOp& L = p.op[l];
-        const bool hidden = L.kind == 0;
-        if (hidden && L.mode == 0) {
-          // stage this op's bias in shared memory (the 8 epilogue warps only: named barrier 1)
-          asm volatile("bar.sync 1, 256;" ::: "memory");
-          const int t = threadIdx.x - 128;
-          if (t < 128) {
-            const float2 bv = __ldg(reinterpret_cast<const float2*>(L.bias) + t);
-            asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(bias_u32 + 8u * t), "f"(bv.x), "f"(bv.y) : "memory");
-          }
-          asm volatile("bar.sync 1, 256;" ::: "memory");
-        }
-        mbar_wait(&tfull[buf], tphase);
-        tc_fence_after();
-        const uint32_t taddr = tmem_base + (uint32_t)buf * 256u + ((uint32_t)(q * 32) << 16);
-        if (hidden) {
-          // 4 chunks of 64 columns (this warp: 32 of them) -> swizzled K blocks of the activation tile
-          for (int j = 0; j < 4; ++j) {
-            const int col0 = j * 64 + half * 32;
-            uint32_t r[32];
-            uint32_t mk[16];
-            tmem_ld32(taddr + (uint32_t)col0, r);
-            if (L.mode == 1 && row_ok) {
-              const uint16_t* mp = L.mask + (size_t)row * 256 + col0;
-              ldg256(mp, mk);
-              ldg256(mp + 16, mk + 8);
-            }
-            tmem_ld_wait();
-            uint32_t packed[16];
-            if (L.mode == 0) {
-              const uint32_t baddr = bias_u32 + (uint32_t)col0 * 4u;
-#pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                const float4 b = lds128f(baddr + 16u * i);
-                const float v0 = fmaxf(__uint_as_float(r[4 * i]) + b.x, 0.f), v1 = fmaxf(__uint_as_float(r[4 * i + 1]) + b.y, 0.f);
-                const float v2 = fmaxf(__uint_as_float(r[4 * i + 2]) + b.z, 0.f), v3 = fmaxf(__uint_as_float(r[4 * i + 3]) + b.w, 0.f);
-                packed[2 * i] = pack_bf16x2(v0, v1);
-                packed[2 * i + 1] = pack_bf16x2(v2, v3);
-              }
-            } else {
-#pragma unroll
-              for (int i = 0; i < 16; ++i) {
-                const uint32_t mlo = mk[i] & 0xffffu, mhi = mk[i] >> 16;
-                const bool plo = row_ok && mlo != 0u && mlo < 0x8000u, phi = row_ok && mhi != 0u && mhi < 0x8000u;
-                const float v0 = plo ? __uint_as_float(r[2 * i]) : 0.f, v1 = phi ? __uint_as_float(r[2 * i + 1]) : 0.f;
-                packed[i] = pack_bf16x2(v0, v1);
-              }
-            }
-            const uint32_t blk = s_act_u32 + (uint32_t)(j * kBlkBytes + r_in_tile * 128);
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-              const uint32_t pos = (uint32_t)((half * 4 + c) ^ (r_in_tile & 7));
-              sts128(blk + pos * 16u, packed[4 * c], packed[4 * c + 1], packed[4 * c + 2], packed[4 * c + 3]);
-            }
-            fence_proxy_async();   // make the generic-proxy smem writes visible to the tensor core (async proxy)
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&a_ready[j]);
-            if (L.save_hi && row_ok) {
-              uint16_t* g = reinterpret_cast<uint16_t*>(L.save_hi) + (size_t)row * 256 + col0;
-              stg256(g, packed);
-              stg256(g + 16, packed + 8);
-            }
-          }
-        } else {
-          const GemmEpilogue& ge = p.gepi[L.gepi];
-          for (int c0 = half * 32; c0 < L.n; c0 += 64) {
-            uint32_t r[32];
-            tmem_ld32(taddr + (uint32_t)c0, r);
-            tmem_ld_wait();
-            if (row_ok) {
-#pragma unroll
-              for (int h = 0; h < 2; ++h) {
-                if (c0 + 16 * h < L.n) {
-                  float v[16];
-#pragma unroll
-                  for (int e = 0; e < 16; ++e) v[e] = __uint_as_float(r[16 * h + e]);
-                  epi_store16<RN_PREC_BF16>(ge, (size_t)row, c0 + 16 * h, v, nullptr);
-                }
-              }
-            }
-          }
-        }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&tempty[buf]);
-        if (++buf == 2) { buf = 0; tphase ^= 1; }
-      }
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 2) tmem_dealloc(tmem_base, kTmemCols);
-}
-
-// ---------------------------------------------------------------------------------------------
-// host side: tensor maps + launches
-// ---------------------------------------------------------------------------------------------
 }  // namespace
 
 int launch_gemm_tc(const GemmArgs& g, cudaStream_t st) {
@@ -777,61 +524,6 @@ int launch_gemm_tc(const GemmArgs& g, cudaStream_t st) {
     gemm_tc_kernel<1><<<grid, 256, Cfg<1>::kSmemBytes, st>>>(maps, g.m, g.n, g.k1 / kBK, g.k2 / kBK, g.epi);
   }
   rn_prof_end(RN_PROF_GEMM_TC, st);
-  RN_CUDA_CHECK_LAUNCH();
-  return RN_OK;
-}
-
-int launch_chain_single(const ChainArgs& a, cudaStream_t st) {
-  if (a.m <= 0) return RN_OK;
-  if (a.num_ops < 1 || a.num_ops > kChainMaxOps) return rn_set_error(RN_ERR_ARG, "chain: 1..12 ops");
-  if (a.in_cols % 64 || a.in_cols < 64 || a.in_cols > 256) return rn_set_error(RN_ERR_ARG, "chain: input tile must be 64..256 columns");
-  ChainMaps maps;
-  ChainParams p;
-  memset(&p, 0, sizeof(p));
-  int rc;
-  if ((rc = make_map(&maps.in, a.in.hi, a.m, a.in_valid, a.in.ld, kBM))) return rc;
-  p.num_ops = a.num_ops;
-  p.in_kb = a.in_cols / kBK;
-  p.m = a.m;
-  int last_in = 0;
-  for (int l = 0; l < a.num_ops; ++l)
-    if (a.op[l].kb_in) last_in = l;
-  for (int l = 0; l < kChainMaxOps; ++l) {
-    if (l < a.num_ops) {
-      const ChainOpArgs& L = a.op[l];
-      if (L.n % 16 || L.n > 256 || (L.kind == 0 && L.n != 256)) return rn_set_error(RN_ERR_ARG, "chain: bad op width");
-      if ((L.kb_act != 0 && L.kb_act != 4) || (L.kb_in != 0 && L.kb_in != p.in_kb) || L.kb_act + L.kb_in == 0 ||
-          (l == 0 && L.kb_act != 0))
-        return rn_set_error(RN_ERR_ARG, "chain: bad K structure");
-      const int ktot = (L.kb_act + L.kb_in) * kBK;
-      if ((rc = make_map(&maps.w[l], L.w, L.n, ktot, L.w_ld, L.n))) return rc;
-      ChainOp& o = p.op[l];
-      o.n = L.n; o.kb_act = L.kb_act; o.kb_in = L.kb_in; o.last_in_use = (l == last_in) ? 1 : 0;
-      o.kind = L.kind; o.mode = L.mode; o.gepi = L.gepi; o.bias = L.bias;
-      o.mask = reinterpret_cast<const uint16_t*>(L.mask); o.save_hi = L.save_hi;
-      if (L.kind == 0 && L.mode == 0 && !L.bias) return rn_set_error(RN_ERR_ARG, "chain: forward op without bias");
-      if (L.kind == 0 && L.mode == 1 && !L.mask) return rn_set_error(RN_ERR_ARG, "chain: backward op without mask");
-    } else {
-      memset(&maps.w[l], 0, sizeof(CUtensorMap));
-    }
-  }
-  p.gepi[0] = a.gepi[0];
-  p.gepi[1] = a.gepi[1];
-  const int fixed = 4 * kBM * kBK * 2 + p.in_kb * kBM * kBK * 2;
-  p.stages = (232448 - 1024 - 1280 - fixed) / (256 * kBK * 2);
-  if (p.stages > 8) p.stages = 8;
-  if (p.stages < 2) return rn_set_error(RN_ERR_ARG, "chain: not enough shared memory for the weight ring");
-  const int smem = fixed + p.stages * 256 * kBK * 2 + 1024 + 1280;
-  static bool smem_set = false;
-  if (!smem_set) {
-    if ((rc = set_smem(chain_kernel, 232448))) return rc;
-    smem_set = true;
-  }
-  const int64_t tiles = (a.m + kBM - 1) / kBM;
-  const unsigned grid = (unsigned)(tiles < num_sms() ? tiles : num_sms());
-  rn_prof_begin(RN_PROF_CHAIN_TC, st, a.algo_flops);
-  chain_kernel<<<grid, 384, smem, st>>>(maps, p);
-  rn_prof_end(RN_PROF_CHAIN_TC, st);
   RN_CUDA_CHECK_LAUNCH();
   return RN_OK;
 }

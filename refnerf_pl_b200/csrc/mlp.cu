@@ -59,18 +59,6 @@ void rn_prof_end(int cls, cudaStream_t st) {
   p.used += 2;
 }
 
-static int g_chain_impl = 0;
-extern "C" int rn_set_chain_impl(int impl) {
-  if (impl < 0 || impl > 1) return rn_set_error(RN_ERR_ARG, "rn_set_chain_impl: 0 = CTA-pair kernel, 1 = single-CTA kernel");
-  g_chain_impl = impl;
-  return RN_OK;
-}
-namespace rn {
-int launch_chain(const ChainArgs& a, cudaStream_t st) {
-  return g_chain_impl == 1 ? launch_chain_single(a, st) : launch_chain_pair(a, st);
-}
-}  // namespace rn
-
 extern "C" int64_t rn_launch_count(void) { return (int64_t)g_launches.load(); }
 extern "C" int rn_prof_enable(int on) {
   std::lock_guard<std::mutex> lk(g_prof_mu);
@@ -96,6 +84,7 @@ extern "C" int rn_prof_summary(int cls, int64_t* launches, double* total_ms, dou
   p.flops = 0.0;
   return RN_OK;
 }
+
 
 namespace rn {
 namespace {
@@ -163,6 +152,7 @@ struct Carver {
 
 struct Workspace {
   ActBuf x0, v0, sp[8], vw[8], g[2], gs[8], dheads, d_bott, d_scal, d_rgb_raw;
+  uint32_t *msp[8], *mvw[8];   // ReLU bits of the hidden activations (fused chains), valid when nsp / nvw == 8
   float *heads_raw, *rgb_raw, *gx0, *dv0f, *dcolor;
   float* gW[kNumLayers];
   float* gB[kNumLayers];
@@ -170,12 +160,15 @@ struct Workspace {
   size_t bytes;
   ActBuf& a(int i) { return sp[(i - 1) % nsp]; }   // spatial activation a_i = relu(y_{i-1}), i = 1..8
   ActBuf& b(int i) { return vw[(i - 1) % nvw]; }   // view activation
+  uint32_t* ma(int i) { return nsp == 8 ? msp[i - 1] : nullptr; }
+  uint32_t* mb(int i) { return nvw == 8 ? mvw[i - 1] : nullptr; }
 };
 
 // Activations a training forward keeps for its backward (no recompute): chain inputs, every hidden activation
 // and the raw head outputs, for ALL rows of the call (chunks index into it by row).
 struct Saved {
   ActBuf x0, v0, sp[8], vw[8];
+  uint32_t *msp[8], *mvw[8];   // ReLU bits of sp / vw, [rows, 8] words (fused chains)
   float *heads_raw, *rgb_raw;
   size_t bytes;
 };
@@ -186,6 +179,8 @@ Saved carve_saved(void* base, int prec, int64_t rows) {
   s.v0 = c.act(prec, rows, kViewPad);
   for (int i = 0; i < 8; ++i) s.sp[i] = c.act(prec, rows, 256);
   for (int i = 0; i < 8; ++i) s.vw[i] = c.act(prec, rows, 256);
+  for (int i = 0; i < 8; ++i) s.msp[i] = (uint32_t*)c.take((size_t)rows * 32);
+  for (int i = 0; i < 8; ++i) s.mvw[i] = (uint32_t*)c.take((size_t)rows * 32);
   s.heads_raw = (float*)c.take((size_t)rows * 16 * 4);
   s.rgb_raw = (float*)c.take((size_t)rows * 4 * 4);
   s.bytes = c.off;
@@ -209,6 +204,8 @@ Workspace carve(void* base, int prec, int64_t rc, int mode, bool external = fals
     w.v0 = c.act(prec, rc, kViewPad);
     for (int i = 0; i < w.nsp; ++i) w.sp[i] = c.act(prec, rc, 256);
     for (int i = 0; i < w.nvw; ++i) w.vw[i] = c.act(prec, rc, 256);
+    for (int i = 0; i < 8; ++i) w.msp[i] = w.nsp == 8 ? (uint32_t*)c.take((size_t)rc * 32) : nullptr;
+    for (int i = 0; i < 8; ++i) w.mvw[i] = w.nvw == 8 ? (uint32_t*)c.take((size_t)rc * 32) : nullptr;
     w.heads_raw = (float*)c.take((size_t)rc * 16 * 4);
     w.rgb_raw = (float*)c.take((size_t)rc * 4 * 4);
   }
@@ -247,6 +244,8 @@ void use_saved(Workspace& w, const Saved& s, int prec, int64_t row0) {
   for (int i = 0; i < 8; ++i) {
     w.sp[i] = rows_from(s.sp[i], prec, row0);
     w.vw[i] = rows_from(s.vw[i], prec, row0);
+    w.msp[i] = s.msp[i] + (size_t)row0 * 8;
+    w.mvw[i] = s.mvw[i] + (size_t)row0 * 8;
   }
   w.heads_raw = s.heads_raw + (size_t)row0 * 16;
   w.rgb_raw = s.rgb_raw + (size_t)row0 * 4;
@@ -363,6 +362,7 @@ int chain_layers(const Ctx& c, int l0, int lh, int64_t rows, ActBuf in, int in_c
     L.w_ld = d.k_tot();
     L.bias = c.pk.bias(l);
     L.save_hi = (keep && i < 8) ? (spatial ? keep->a(i + 1).hi : keep->b(i + 1).hi) : nullptr;
+    L.save_bits = (keep && i < 8) ? (spatial ? keep->ma(i + 1) : keep->mb(i + 1)) : nullptr;
     flops += op_flops(rows, l, false, true);
   }
   final_epi.bias = c.pk.bias(lh);
@@ -372,7 +372,7 @@ int chain_layers(const Ctx& c, int l0, int lh, int64_t rows, ActBuf in, int in_c
 }
 
 // one backward (dgrad) op of a fused chain for layer l: rows [row0, ..) of the transposed weights
-ChainOpArgs bwd_op(const Ctx& c, int l, int in_row0, int n, int kb_act, int kb_in, const void* mask, void* save) {
+ChainOpArgs bwd_op(const Ctx& c, int l, int in_row0, int n, int kb_act, int kb_in, const uint32_t* mask, void* save) {
   ChainOpArgs L;
   L.n = n;
   L.kb_act = kb_act;
@@ -381,7 +381,7 @@ ChainOpArgs bwd_op(const Ctx& c, int l, int in_row0, int n, int kb_act, int kb_i
   L.mode = 1;
   L.w = c.pk.wt_hi(l, in_row0);
   L.w_ld = layer_def(l).nt_pad;
-  L.mask = mask;
+  L.mask_bits = mask;
   L.save_hi = save;
   return L;
 }
@@ -402,7 +402,7 @@ int normals_chain(const Ctx& c, Workspace& w, int64_t rows) {
       flops += op_flops(rows, 5, true, false);
       ++n;
     }
-    a.op[n] = bwd_op(c, l, 0, 256, l == 7 ? 0 : 4, l == 7 ? 4 : 0, w.a(l).hi, nullptr);
+    a.op[n] = bwd_op(c, l, 0, 256, l == 7 ? 0 : 4, l == 7 ? 4 : 0, w.ma(l), nullptr);
     flops += op_flops(rows, l, false, false);
     ++n;
   }
@@ -530,7 +530,7 @@ int backward_chunk_chain(const Ctx& c, Workspace& w, int64_t row0, int64_t rows,
     a.in_valid = 16;
     int n = 0;
     double flops = op_flops(rows, kLayerC, false, false);
-    a.op[n++] = bwd_op(c, kLayerC, 0, 256, 0, 1, w.b(8).hi, w.gs[7].hi);
+    a.op[n++] = bwd_op(c, kLayerC, 0, 256, 0, 1, w.mb(8), w.gs[7].hi);
     for (int l = 7; l >= 1; --l) {
       const int L = kLayerV0 + l;
       if (l == 5) {
@@ -539,7 +539,7 @@ int backward_chunk_chain(const Ctx& c, Workspace& w, int64_t row0, int64_t rows,
         flops += op_flops(rows, L, true, false);
         ++n;
       }
-      a.op[n++] = bwd_op(c, L, 0, 256, 4, 0, w.b(l).hi, w.gs[l - 1].hi);
+      a.op[n++] = bwd_op(c, L, 0, 256, 4, 0, w.mb(l), w.gs[l - 1].hi);
       flops += op_flops(rows, L, false, false);
     }
     a.op[n] = bwd_op(c, kLayerV0, 0, 256, 4, 0, nullptr, nullptr);
@@ -569,9 +569,9 @@ int backward_chunk_chain(const Ctx& c, Workspace& w, int64_t row0, int64_t rows,
     a.in_valid = 144;
     int n = 0;
     double flops = op_flops(rows, kLayerH, false, false);
-    a.op[n++] = bwd_op(c, kLayerH, 0, 256, 0, 3, w.a(8).hi, w.gs[7].hi);
+    a.op[n++] = bwd_op(c, kLayerH, 0, 256, 0, 3, w.ma(8), w.gs[7].hi);
     for (int l = 7; l >= 1; --l) {
-      a.op[n++] = bwd_op(c, l, 0, 256, 4, 0, w.a(l).hi, w.gs[l - 1].hi);
+      a.op[n++] = bwd_op(c, l, 0, 256, 4, 0, w.ma(l), w.gs[l - 1].hi);
       flops += op_flops(rows, l, false, false);
     }
     a.num_ops = n;
