@@ -163,6 +163,53 @@ def build_everything(precision, device):
     return model, cfg
 
 
+def load_traffic():
+    """Per-launch DRAM bytes of the profiled kernels (ncu --set full, profiles/r01_traffic.json), or {}."""
+    p = os.path.join(ROOT, 'profiles', 'r01_traffic.json')
+    return json.load(open(p)) if os.path.exists(p) else {}
+
+
+def time_hbm_kernels(dev, peaks):
+    """Achieved HBM GB/s of the warp-per-ray kernels (SURVEY 8(d) algorithmic bytes), inputs larger than L2."""
+    from refnerf_pl_b200 import ops
+    out = {}
+    g = torch.Generator(device=dev).manual_seed(0)
+    rnd = lambda *s: torch.rand(*s, device=dev, generator=g)
+
+    def timeit(fn, iters=20):
+        fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / iters * 1e-3
+
+    def entry(bytes_per_ray, n, sec):
+        gbs = bytes_per_ray * n / sec / 1e9
+        return {'gbs': gbs, 'frac': gbs / peaks['hbm_gbs'], 'bytes_per_ray': bytes_per_ray, 'rays': n, 'us': sec * 1e6}
+
+    n, s = 32768, 128        # 373 MB of inputs per launch (> 126 MB L2)
+    t = torch.sort(rnd(n, s + 1) * 4 + 2, dim=-1).values
+    dirs = rnd(n, 3) + 0.5
+    far = torch.full((n, 1), 6.0, device=dev)
+    dens, rough = rnd(n, s) * 3, rnd(n, s, 1)
+    c3 = [rnd(n, s, 3) for _ in range(6)]
+    sec = timeit(lambda: ops.composite_fwd(dens, t, dirs, far, c3[0], c3[1], c3[2], c3[3], c3[4], rough, c3[5], 1.0, True))
+    out['composite_fwd_extras'] = entry(11384, n, sec)
+    sec = timeit(lambda: ops.composite_fwd(dens, t, dirs, far, c3[0], c3[1], c3[2], c3[3], c3[4], rough, c3[5], 1.0, False))
+    out['composite_fwd'] = entry(6208, n, sec)
+    n2 = 131072              # 270 MB per launch
+    sd = torch.sort(rnd(n2, s + 1), dim=-1).values
+    w = rnd(n2, s)
+    near, far2 = torch.full((n2, 1), 2.0, device=dev), torch.full((n2, 1), 6.0, device=dev)
+    sec = timeit(lambda: ops.resample(sd, w, near, far2, s, 0.01, 1.0, 0.0, 1.0, False))
+    out['resample'] = entry(2060, n2, sec)
+    return out
+
+
 def run_b200(args):
     from refnerf_pl_b200 import _lib, parallel, synthetic, train_utils, utils
     rank, world, local_rank = parallel.init_distributed()
@@ -248,6 +295,33 @@ def run_b200(args):
     ms_e2e = timed(e2e_step, args.steps) / args.steps
     e2e_value = world * n / (ms_e2e * 1e-3)
 
+    # ---- 800x800 frame render (eval path, chunked): every rank renders a contiguous slice of the frame's rays ----
+    render = None
+    if not args.no_render:
+        from refnerf_pl_b200 import models
+        model.eval()
+        frame = synthetic.blender_rays(None, seed=7)
+        lo, hi = parallel.shard_range(640000, rank, world)
+        fr = utils.Rays(**{k: torch.from_numpy(v[lo:hi]).to(dev).reshape(hi - lo, 1, -1) for k, v in frame.items()})
+        cfg.render_chunk_size = args.render_chunk
+        fn = lambda r: model(r, 1.0, True)
+
+        def render_once():
+            out = models.render_image(fn, fr, cfg)
+            if world > 1:   # the frame is assembled on every rank (rgb + distance + acc, 5 floats per ray)
+                parallel.gather_rows(torch.cat([out['rgb'].reshape(-1, 3), out['distance'].reshape(-1, 1),
+                                                out['acc'].reshape(-1, 1)], dim=-1))
+            return out
+
+        with torch.no_grad():
+            render_once()
+            fms = timed(render_once, 2) / 2
+        render = {'ms_per_frame': fms, 'rays_per_s': 640000 / (fms * 1e-3), 'chunk_rays': args.render_chunk,
+                  'frame': '800x800', 'compute_extras': True, 'n_gpus': world,
+                  'sharding': 'contiguous ray slices per rank, outputs all-gathered' if world > 1 else 'single GPU',
+                  'mlp_tflops': FLOP_PER_SAMPLE_EVAL * SAMPLES_PER_RAY * 640000 / (fms * 1e-3) / 1e12}
+        model.train(True)
+
     if rank != 0:
         return
     # ---- roofline of the dominant kernel (tcgen05 fwd/dgrad GEMM; SIMT GEMM in fp32 mode) ----------
@@ -256,11 +330,22 @@ def run_b200(args):
     achieved = d['flops'] / (d['ms'] * 1e-3) / 1e12 if d['ms'] > 0 else 0.0
     peak = peaks['bf16_sustained']
     roofline = {'bound': 'tensor', 'kernel': dom, 'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s',
-                'frac': achieved / peak, 'traffic': None, 'peak_source': peaks['source'] + ' (sustained bf16)',
+                'frac': achieved / peak, 'traffic': load_traffic().get(dom),
+                'peak_source': peaks['source'] + ' (sustained bf16)',
                 'launches_per_step': d['launches'] / args.steps, 'avg_launch_ms': d['ms'] / max(1, d['launches']),
                 'kernel_share_of_step': d['ms'] / ms_total,
                 'algo_flops_per_launch': d['flops'] / max(1, d['launches'])}
     step_tflops = FLOP_PER_SAMPLE_TRAIN * SAMPLES_PER_RAY * n / (ms_step * 1e-3) / 1e12
+    # second kernel class: the wgrad GEMMs are HBM-bound by construction (every dY and X row is read once, bf16):
+    # 16 hidden layers + heads: 17 (dY, X) pairs of 256 bf16 columns per sample row = 1024 B per row and layer
+    # (the narrow rgb head and the skip-input operands are ignored)
+    wg = prof['wgrad_tc']
+    wg_bytes = 17 * 1024 * n * SAMPLES_PER_RAY * args.steps
+    wg_gbs = wg_bytes / (wg['ms'] * 1e-3) / 1e9 if wg['ms'] else 0.0
+    roofline_wgrad = {'bound': 'hbm', 'kernel': 'wgrad_tc', 'achieved': wg_gbs, 'peak': peaks['hbm_gbs'], 'unit': 'GB/s',
+                      'frac': wg_gbs / peaks['hbm_gbs'], 'traffic': load_traffic().get('wgrad_tc'),
+                      'kernel_share_of_step': wg['ms'] / ms_total}
+    hbm_kernels = time_hbm_kernels(dev, peaks)
 
     # ---- CPU baseline on this box's host cores (oracle port, bounded sample) -----------------------
     cpu = None
@@ -270,30 +355,6 @@ def run_b200(args):
         cpu = {'value': args.cpu_rays / sec, 'unit': UNIT, 'cores': cores, 'kind': 'port',
                'sample': f'{args.cpu_rays} rays of the {n}-ray batch, fwd+bwd, median of 2 after 1 warm-up; torch '
                          f'threads={cores}; {cpu_model_name()}'}
-
-    # ---- 800x800 frame render (eval path, chunked) ------------------------------------------------
-    render = None
-    if not args.no_render:
-        from refnerf_pl_b200 import models
-        model.eval()
-        frame = synthetic.blender_rays(None, seed=7)
-        lo, hi = parallel.shard_range(640000, 0, 1)
-        fr = utils.Rays(**{k: torch.from_numpy(v).to(dev).reshape(800, 800, -1) for k, v in frame.items()})
-        cfg.render_chunk_size = args.render_chunk
-        fn = lambda r: model(r, 1.0, True)
-        with torch.no_grad():
-            models.render_image(fn, fr, cfg)
-            torch.cuda.synchronize()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            for _ in range(2):
-                models.render_image(fn, fr, cfg)
-            e1.record()
-            torch.cuda.synchronize()
-        fms = e0.elapsed_time(e1) / 2
-        render = {'ms_per_frame': fms, 'rays_per_s': 640000 / (fms * 1e-3), 'chunk_rays': args.render_chunk,
-                  'frame': '800x800', 'compute_extras': True,
-                  'mlp_tflops': FLOP_PER_SAMPLE_EVAL * SAMPLES_PER_RAY * 640000 / (fms * 1e-3) / 1e12}
 
     line = {
         'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
@@ -310,6 +371,8 @@ def run_b200(args):
         'gpu_launches': int(launches),
         'clocks': clocks,
         'roofline': roofline,
+        'roofline_wgrad': roofline_wgrad,
+        'hbm_kernels': hbm_kernels,
         'cpu_baseline': cpu,
         'mlp_tflops_step': step_tflops,
         'mlp_frac_of_bf16_peak': step_tflops / peaks['bf16_sustained'],

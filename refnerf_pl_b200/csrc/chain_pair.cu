@@ -19,6 +19,9 @@
 //
 // Roles per CTA (384 threads): warp 0 TMA producer, warp 1 MMA issuer (leader CTA only), warp 2 TMEM
 // allocator, warps 4-11 epilogue (warp % 4 = TMEM lane quadrant, (warp - 4) / 4 = column half).
+#include <stdio.h>
+#include <stdlib.h>
+
 #include "tc_common.cuh"
 
 namespace rn {
@@ -205,6 +208,7 @@ struct PairParams {
   int num_ops;
   int in_kb;
   int64_t m;
+  long long* trace;   // debug timeline (RN_CHAIN_TRACE=<launches>): written by CTA 0 only
   PairOp op[kMaxOps];
   GemmEpilogue gepi[2];
 };
@@ -314,6 +318,7 @@ chain_pair_kernel(const __grid_constant__ PairMaps maps, const __grid_constant__
             mbar_wait_cluster(&acc_free[t], free_parity);
             tc_fence_after();
           }
+          if (p.trace && blockIdx.x == 0 && opcount < 64) p.trace[(opcount * 2 + t) * 8 + 0] = clock64();
           const uint32_t tmem_d = tmem_base + (uint32_t)t * 256u;
           for (int kb = 0; kb < L.kb_act; ++kb) {
             if (t == 0) {
@@ -324,6 +329,7 @@ chain_pair_kernel(const __grid_constant__ PairMaps maps, const __grid_constant__
             if (t == 1) umma2_commit(&ring_empty[(pos_w + kb) % kRingStages]);
           }
           if (L.kb_act && !L.kb_in) umma2_commit(&acc_full[t]);
+          if (p.trace && blockIdx.x == 0 && opcount < 64) p.trace[(opcount * 2 + t) * 8 + 1] = clock64();
         }
         pos += L.kb_act;
         // --- K blocks from the chain input: x(tile 0), W, x(tile 1) per K block
@@ -388,8 +394,11 @@ chain_pair_kernel(const __grid_constant__ PairMaps maps, const __grid_constant__
             else if (l + 1 < p.num_ops) bits_next = load_bits(st, l + 1, 0);
             else bits_next = load_bits(st + num_clusters, 0, 0);
           }
+          const bool tr = p.trace && blockIdx.x == 0 && warp == 4 && lane == 0 && opcount < 64;
+          if (tr) p.trace[(opcount * 2 + t) * 8 + 2] = clock64();
           mbar_wait(&acc_full[t], opcount & 1u);
           tc_fence_after();
+          if (tr) p.trace[(opcount * 2 + t) * 8 + 3] = clock64();
           if (t == 0 && bias_ptr) {
             asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(bias_buf + 16u * lane), "f"(bv.x), "f"(bv.y), "f"(bv.z),
                          "f"(bv.w)
@@ -443,6 +452,7 @@ chain_pair_kernel(const __grid_constant__ PairMaps maps, const __grid_constant__
             fence_proxy_async();   // generic-proxy smem writes -> visible to the tensor core and to TMA stores
             tc_fence_before();
             __syncwarp();
+            if (tr) p.trace[(opcount * 2 + t) * 8 + 4] = clock64();
             if (lane == 0) {
               mbar_arrive_cluster_addr(free_addr0 + 8u * t);
               if (L.save) {
@@ -559,6 +569,15 @@ int launch_chain(const ChainArgs& a, cudaStream_t st) {
   const int64_t supers = (a.m + 511) / 512;
   const int max_clusters = tc::num_sms() / 2;
   const unsigned grid = 2u * (unsigned)(supers < max_clusters ? supers : max_clusters);
+  // debug: RN_CHAIN_TRACE=<n> prints the per-(op, tile) timeline of CTA 0 for the first n launches
+  static long long* trace_buf = nullptr;
+  static int trace_left = getenv("RN_CHAIN_TRACE") ? atoi(getenv("RN_CHAIN_TRACE")) : 0;
+  p.trace = nullptr;
+  if (trace_left > 0) {
+    if (!trace_buf) cudaMalloc(&trace_buf, 64 * 2 * 8 * sizeof(long long));
+    cudaMemsetAsync(trace_buf, 0, 64 * 2 * 8 * sizeof(long long), st);
+    p.trace = trace_buf;
+  }
   rn_prof_begin(RN_PROF_CHAIN_TC, st, a.algo_flops);
   if (mode == 0)
     chain_pair_kernel<0><<<grid, 384, kSmemTotal, st>>>(maps, p);
@@ -566,6 +585,17 @@ int launch_chain(const ChainArgs& a, cudaStream_t st) {
     chain_pair_kernel<1><<<grid, 384, kSmemTotal, st>>>(maps, p);
   rn_prof_end(RN_PROF_CHAIN_TC, st);
   RN_CUDA_CHECK_LAUNCH();
+  if (p.trace) {
+    --trace_left;
+    cudaStreamSynchronize(st);
+    static long long h[64 * 2 * 8];
+    cudaMemcpy(h, trace_buf, sizeof(h), cudaMemcpyDeviceToHost);
+    const long long t0 = h[0];
+    printf("chain trace (mode %d, %d ops, m=%lld): per (op,tile): mma_wait_done mma_issued | epi_wait_begin epi_wait_end epi_end  [cycles since first]\n", mode, a.num_ops, (long long)a.m);
+    for (int i = 0; i < 40; ++i)
+      printf("  op %2d tile %d: %8lld %8lld | %8lld %8lld %8lld\n", i / 2, i % 2, h[i * 8] - t0, h[i * 8 + 1] - t0, h[i * 8 + 2] - t0, h[i * 8 + 3] - t0,
+             h[i * 8 + 4] - t0);
+  }
   return RN_OK;
 }
 

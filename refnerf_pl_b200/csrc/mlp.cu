@@ -436,7 +436,10 @@ int forward_chunk(const Ctx& c, Workspace& w, int64_t row0, int64_t rows, const 
   }
   if (want_normals) {
     // d raw_density / d x0 through the spatial net (models.py:603-609); result is a constant
-    RN_TRY(launch_density_grad_seed(prec, w.a(8), c.pk.wd(), w.g[0], rows, c.st));
+    if (c.chain)
+      RN_TRY(launch_density_grad_seed_bits(w.ma(8), c.pk.wd(), w.g[0], rows, c.st));
+    else
+      RN_TRY(launch_density_grad_seed(prec, w.a(8), c.pk.wd(), w.g[0], rows, c.st));
     if (c.chain) {
       RN_TRY(normals_chain(c, w, rows));
     } else {
