@@ -130,6 +130,152 @@ __device__ __forceinline__ void accum_vec3(const float* __restrict__ v, const fl
   }
 }
 
+// ---- S = 128 fast path --------------------------------------------------------------------------------------
+// Lane l owns the 4 consecutive samples 4l..4l+3: density / weights move as one float4 per lane, a [128,3] array
+// as three float4 per lane (12 floats = 4 samples x 3 channels, all indices compile-time), the transmittance scan
+// is 3 local adds + one warp scan, and the 22 per-ray sums are reduced through a shared-memory transpose (every
+// lane sums one value over the 32 lanes) instead of 22 shuffle trees.  No integer division, no shared-memory weights.
+constexpr int kFastVals = 22;   // rgb 0-2, diffuse 3-5, specular 6-8, dist 9, acc 10, logd 11, normals 12-14,
+                                // normals_pred 15-17, tint 18-20, roughness 21
+__device__ __forceinline__ void acc_samples4(const float* __restrict__ v, int lane, const float w[4], float acc[3]) {
+  const float4* p = reinterpret_cast<const float4*>(v) + 3 * lane;
+  const float4 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2);
+  acc[0] = w[0] * a.x + w[1] * a.w + w[2] * b.z + w[3] * c.y;
+  acc[1] = w[0] * a.y + w[1] * b.x + w[2] * b.w + w[3] * c.z;
+  acc[2] = w[0] * a.z + w[1] * b.y + w[2] * c.x + w[3] * c.w;
+}
+
+__global__ void __launch_bounds__(kWarps * 32)
+composite_fwd128_kernel(const float* __restrict__ density, const float* __restrict__ tdist, const float* __restrict__ dirs,
+                        const float* __restrict__ far_, const float* __restrict__ rgb, const float* __restrict__ diffuse,
+                        const float* __restrict__ specular, const float* __restrict__ normals,
+                        const float* __restrict__ normals_pred, const float* __restrict__ roughness,
+                        const float* __restrict__ tint, int64_t n_rays, float bg, float* __restrict__ weights_out,
+                        float* __restrict__ comp_out, float* __restrict__ extras_out, double* __restrict__ pct_out) {
+  constexpr int s = 128;
+  __shared__ float sm_t[kWarps][s + 4];
+  __shared__ __align__(16) float sm_w[kWarps][s + 4];   // rows stay 16-byte aligned for the float4 store
+  __shared__ float sm_cw[kWarps][s + 4];
+  __shared__ float sm_red[kWarps][kFastVals][33];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t ray = (int64_t)blockIdx.x * kWarps + warp;
+  if (ray >= n_rays) return;
+  float* ts = sm_t[warp];
+  float* ws = sm_w[warp];
+  float* cw = sm_cw[warp];
+
+  const float4 d4 = __ldg(reinterpret_cast<const float4*>(density + ray * s) + lane);
+  const float* tin = tdist + ray * (s + 1);
+  for (int i = lane; i <= s; i += 32) ts[i] = __ldg(tin + i);
+  const float dx = dirs[ray * 3 + 0], dy = dirs[ray * 3 + 1], dz = dirs[ray * 3 + 2];
+  const float dnorm = sqrtf(dx * dx + dy * dy + dz * dz);
+  __syncwarp();
+  float t[5];
+#pragma unroll
+  for (int k = 0; k < 5; ++k) t[k] = ts[4 * lane + k];
+  const float dens[4] = {d4.x, d4.y, d4.z, d4.w};
+  float dd[4], pre[4];
+  float run = 0.f;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    dd[k] = dens[k] * ((t[k + 1] - t[k]) * dnorm);
+    pre[k] = run;          // sum of this lane's earlier samples
+    run += dd[k];
+  }
+  const float off = warp_scan_incl(run, lane) - run;   // sum over earlier lanes
+  float w[4], vals[kFastVals];
+  float acc = 0.f, dist = 0.f, logd = 0.f;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    w[k] = (1.f - expf(-dd[k])) * expf(-(off + pre[k]));
+    const float tmid = 0.5f * (t[k] + t[k + 1]);
+    acc += w[k];
+    dist += w[k] * tmid;
+    logd += w[k] * logf(tmid);
+  }
+  *(reinterpret_cast<float4*>(weights_out + ray * s) + lane) = make_float4(w[0], w[1], w[2], w[3]);
+  acc_samples4(rgb + ray * 384, lane, w, vals + 0);
+  acc_samples4(diffuse + ray * 384, lane, w, vals + 3);
+  acc_samples4(specular + ray * 384, lane, w, vals + 6);
+  vals[9] = dist;
+  vals[10] = acc;
+  vals[11] = logd;
+  int nvals = 12;
+  if (extras_out) {
+    nvals = kFastVals;
+    if (normals) acc_samples4(normals + ray * 384, lane, w, vals + 12);
+    else vals[12] = vals[13] = vals[14] = 0.f;
+    if (normals_pred) acc_samples4(normals_pred + ray * 384, lane, w, vals + 15);
+    else vals[15] = vals[16] = vals[17] = 0.f;
+    if (tint) acc_samples4(tint + ray * 384, lane, w, vals + 18);
+    else vals[18] = vals[19] = vals[20] = 0.f;
+    vals[21] = 0.f;
+    if (roughness) {
+      const float4 r4 = __ldg(reinterpret_cast<const float4*>(roughness + ray * s) + lane);
+      vals[21] = w[0] * r4.x + w[1] * r4.y + w[2] * r4.z + w[3] * r4.w;
+    }
+  }
+  // transpose reduction: value v of lane l -> red[v][l]; lane v then sums row v
+#pragma unroll
+  for (int v = 0; v < kFastVals; ++v)
+    if (v < nvals) sm_red[warp][v][lane] = vals[v];
+  if (pct_out) *(reinterpret_cast<float4*>(ws) + lane) = make_float4(w[0], w[1], w[2], w[3]);
+  __syncwarp();
+  float total = 0.f;
+  if (lane < nvals) {
+#pragma unroll 8
+    for (int l = 0; l < 32; ++l) total += sm_red[warp][lane][l];
+  }
+  const float acc_t = __shfl_sync(RN_FULL, total, 10);
+  const float bg_w = fmaxf(0.f, 1.f - acc_t);
+  {
+    float o;
+    if (lane < 9) o = total + bg_w * bg;
+    else if (lane < 11) o = total;                 // 9 distance, 10 acc
+    else if (lane == 11) {
+      // distance_mean = clip(nan_to_num(exp(sum w log t_mid / max(eps, acc)), inf), t0, tS)  (render.py:232-238)
+      float dm = expf(total / fmaxf(RN_EPS32, acc_t));
+      if (dm != dm) dm = INFINITY;
+      o = fminf(fmaxf(dm, ts[0]), ts[s]);
+    } else o = (lane == 12) ? bg_w : 0.f;
+    if (lane < 16) comp_out[ray * 16 + lane] = o;
+  }
+  if (extras_out && lane >= 12 && lane < 24) extras_out[ray * 12 + (lane - 12)] = lane < kFastVals ? total : 0.f;
+  if (pct_out) {
+    // weighted_percentile (stepfun.py:294-307) on t_aug=[tdist, far], w_aug=[weights, bg_w]: see the generic kernel
+    float cr = 0.f, crmax = 0.f;
+    for (int base = 0; base < s; base += 32) {
+      const int i = base + lane;
+      float c = warp_scan_incl(ws[i], lane) + cr;
+      cr = __shfl_sync(RN_FULL, c, 31);
+      c = fmaxf(warp_scan_max(c, lane), crmax);
+      crmax = __shfl_sync(RN_FULL, c, 31);
+      cw[i + 1] = fminf(c, 1.f);
+    }
+    if (lane == 0) {
+      cw[0] = 0.f;
+      cw[s + 1] = 1.f;
+      ts[s + 1] = far_[ray];
+    }
+    __syncwarp();
+    const float ps[3] = {0.05f, 0.5f, 0.95f};
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      int cnt = 0;
+      for (int i = lane; i < s + 2; i += 32) cnt += (ps[k] >= cw[i]) ? 1 : 0;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(RN_FULL, cnt, o);
+      if (lane == k) {
+        int idx = min(max(cnt - 1, 0), s);
+        const double x0 = cw[idx], x1 = cw[idx + 1], f0 = ts[idx], f1 = ts[idx + 1];
+        const double mm = (f1 - f0) / (x1 - x0);
+        const double bb = f0 - mm * x0;
+        pct_out[ray * 3 + k] = mm * (double)ps[k] + bb;
+      }
+    }
+  }
+}
+
 __global__ void __launch_bounds__(kWarps * 32)
 composite_fwd_kernel(const float* __restrict__ density, const float* __restrict__ tdist, const float* __restrict__ dirs,
                      const float* __restrict__ far_, const float* __restrict__ rgb, const float* __restrict__ diffuse,
@@ -522,6 +668,13 @@ extern "C" int rn_composite_fwd(const float* density, const float* tdist, const 
                                 double* pct_out, void* stream) {
   if (n_rays < 0 || s < 1) return rn_set_error(RN_ERR_ARG, "rn_composite_fwd: bad sizes");
   if (n_rays == 0) return RN_OK;
+  if (s == 128) {
+    composite_fwd128_kernel<<<blocks_for(n_rays), kWarps * 32, 0, (cudaStream_t)stream>>>(
+        density, tdist, dirs, far_, rgb, diffuse, specular, normals, normals_pred, roughness, tint, n_rays, bg, weights_out,
+        comp_out, extras_out, pct_out);
+    RN_CUDA_CHECK_LAUNCH();
+    return RN_OK;
+  }
   size_t smem = (size_t)kWarps * 3 * (s + 2) * sizeof(float);
   if (int rc = ensure_smem(composite_fwd_kernel, smem)) return rc;
   composite_fwd_kernel<<<blocks_for(n_rays), kWarps * 32, smem, (cudaStream_t)stream>>>(
