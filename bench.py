@@ -157,6 +157,8 @@ def build_everything(precision, device):
     gin = os.path.join(ROOT, 'configs', 'blender_refnerf.gin')
     configs.parse_gin_files_and_bindings([gin])
     configs.bind('NerfMLP', precision=precision)
+    if os.environ.get('REFNERF_B200_GEMM_IMPL'):
+        configs.bind('NerfMLP', gemm_impl=int(os.environ['REFNERF_B200_GEMM_IMPL']))
     cfg = configs.Config()
     torch.manual_seed(0)
     model = models.Model(config=cfg).to(device)

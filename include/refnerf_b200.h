@@ -112,7 +112,7 @@ typedef struct RnMlpConfig {
   float rgb_bias;
   float rgb_padding;        /* models.py:729                                               */
   int chunk_rows;           /* rows processed per internal chunk (multiple of 128)         */
-  int gemm_impl;            /* 0 = default (fused chains in bf16), 1 = SIMT GEMMs, 2 = per-layer tcgen05 */
+  int gemm_impl;            /* 0 = default (fused SS chains in bf16), 1 = SIMT GEMMs, 2 = per-layer tcgen05, 3 = fused TS chains (A operand in TMEM) */
 } RnMlpConfig;
 
 /* bytes of the packed-weight blob / of the scratch workspace for the given chunk size.

@@ -22,13 +22,13 @@
 #include <stdio.h>
 #include <stdlib.h>
 
-#include "tc_common.cuh"
+#include "chain_common.cuh"
 
 namespace rn {
 namespace {
 using namespace tc;
+using namespace chain;
 
-constexpr int kMaxOps = 12;
 constexpr int kRingStages = 6;
 constexpr int kStageBytes = 16384;            // one ring item: [128 x 64] bf16
 constexpr int kBlkBytes = kBM * kBK * 2;      // 16 KB activation K block
@@ -39,179 +39,6 @@ constexpr int kSmemBias = kSmemBars + 256;
 constexpr int kSmemTotal = kSmemBias + 2 * 1024;
 static_assert(kSmemTotal <= 232448, "shared memory budget");
 
-// ---- cluster / 2-CTA PTX ---------------------------------------------------------------------
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
-}
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-__device__ __forceinline__ uint32_t map_to_cta(uint32_t local_addr, uint32_t cta) {
-  uint32_t r;
-  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(cta));
-  return r;
-}
-__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
-}
-__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
-  const uint32_t addr = smem_u32(bar);
-  for (int spin = 0; spin < kSpinLimit; ++spin) {
-    uint32_t done;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done)
-        : "r"(addr), "r"(parity)
-        : "memory");
-    if (done) return;
-  }
-  __trap();
-}
-__device__ __forceinline__ void tmem_alloc2(uint32_t* dst_smem, uint32_t cols) {
-  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(cols));
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
-}
-__device__ __forceinline__ void tmem_dealloc2(uint32_t taddr, uint32_t cols) {
-  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols));
-}
-// TMA load whose transaction bytes are credited to the barrier at `bar_cluster_addr` (the leader CTA's)
-__device__ __forceinline__ void tma_load_2d_pair(uint32_t smem_dst, const CUtensorMap* map, uint32_t bar_cluster_addr, int c0,
-                                                 int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-      ::"r"(smem_dst), "l"(map), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
-      : "memory");
-}
-__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t smem_src, int c0, int c1) {
-  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map), "r"(smem_src),
-               "r"(c0), "r"(c1)
-               : "memory");
-}
-__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void tma_store_wait_read() {
-  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
-}
-__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
-
-// D[tmem, both CTAs] (+)= A[smem, 128 rows per CTA] * B[smem, N/2 rows per CTA]^T
-__device__ __forceinline__ void umma2_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accum) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accum)
-      : "memory");
-}
-// arrive (once the MMAs issued so far have completed) on the barrier at the same offset in both CTAs
-__device__ __forceinline__ void umma2_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
-                   smem_u32(bar)),
-               "h"((uint16_t)3)
-               : "memory");
-}
-__device__ __forceinline__ uint32_t make_idesc2(int n) {
-  uint32_t d = 0;
-  d |= 1u << 4;                       // c_format = F32
-  d |= 1u << 7;                       // a_format = BF16
-  d |= 1u << 10;                      // b_format = BF16
-  d |= (uint32_t)(n >> 3) << 17;
-  d |= (uint32_t)(256 >> 4) << 24;    // M = 256 across the pair
-  return d;
-}
-
-__device__ __forceinline__ void mbar_arrive_cluster_addr(uint32_t cluster_addr) {
-  // default semantics (release at CTA scope), as CUTLASS' ClusterBarrier::arrive(cta_id): the data this signals is
-  // this CTA's own shared memory / TMEM, ordered by fence.proxy.async / tcgen05.fence before the arrive
-  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
-}
-// two floats -> bf16x2 with ReLU folded into the conversion (one F2FP instruction)
-__device__ __forceinline__ uint32_t pack_relu_bf16x2(float lo, float hi) {
-  uint32_t r;
-  asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
-  return r;
-}
-__device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t* r) { tmem_ld32(taddr, r); }
-
-// ReLU masks travel as 1 bit per activation: word w of a row covers columns [32w, 32w+32); inside a word the
-// packed bf16 pair i (columns 2i, 2i+1) owns bits i and 16+i.
-__device__ __forceinline__ uint32_t relu_bits_of(const uint32_t* packed /*16 bf16x2, non-negative*/) {
-  uint32_t bits = 0;
-#pragma unroll
-  for (int i = 0; i < 16; ++i) bits += __vminu2(packed[i], 0x00010001u) << i;   // 1 where the half is nonzero
-  return bits;
-}
-// keep / zero the two halves of packed pair i according to bits i and 16+i
-__device__ __forceinline__ uint32_t apply_relu_bits(uint32_t bits, int i, uint32_t packed) {
-  const uint32_t x = i <= 7 ? (bits << (7 - i)) : (bits >> (i - 7));   // bit i -> 7, bit 16+i -> 23
-  uint32_t m;   // prmt with selector msb set = replicate the sign bit of the selected byte (__byte_perm drops that bit)
-  asm("prmt.b32 %0, %1, %2, 0xAA88;" : "=r"(m) : "r"(x), "r"(0u));
-  return packed & m;
-}
-
-// epilogue for 16 consecutive columns of one row of a global (non-hidden) op; v holds the fp32 accumulators
-// (bias already added by the caller)
-__device__ __forceinline__ void epi_global16(const GemmEpilogue& e, size_t row, int col, float* v) {
-  if (e.relu) {
-#pragma unroll
-    for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
-  }
-  if (e.out.hi && col < e.out_cols) {
-    uint32_t h[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) h[i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);
-    stg256(reinterpret_cast<uint16_t*>(e.out.hi) + row * e.out.ld + col, h);
-  }
-  if (e.f32 && col + 16 > e.f32_col0 && col < e.f32_col0 + e.f32_cols) {
-    const int c0 = col - e.f32_col0;
-    float* p = e.f32 + row * e.f32_ld + c0;
-    if (c0 >= 0 && c0 + 16 <= e.f32_cols && (e.f32_ld & 7) == 0) {
-      uint32_t a[8];
-#pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        if (e.f32_accum) {
-          ldg256(p + 8 * half, a);
-#pragma unroll
-          for (int i = 0; i < 8; ++i) a[i] = __float_as_uint(__uint_as_float(a[i]) + v[8 * half + i]);
-        } else {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) a[i] = __float_as_uint(v[8 * half + i]);
-        }
-        stg256(p + 8 * half, a);
-      }
-    } else {
-#pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        const int c = c0 + i;
-        if (c >= 0 && c < e.f32_cols) p[i] = e.f32_accum ? (p[i] + v[i]) : v[i];
-      }
-    }
-  }
-}
-
-struct PairOp {
-  int n;           // MMA N = output columns (multiple of 16)
-  int kb_act;      // K blocks read from the resident activation tile (0 or 4)
-  int kb_in;       // K blocks read from the chain input tile (streamed through the ring)
-  int kind;        // 0: hidden (result -> activation tile [+ TMA save]); 1: global epilogue
-  int gepi;        // kind 1: which global epilogue
-  int save;        // hidden: TMA-store the result through maps.save[op]
-  const float* bias;       // forward hidden ops / global ops with a bias: [n] floats (padded to a multiple of 4)
-  const uint32_t* mask_bits;   // backward hidden ops: ReLU bits [m, 8]
-  uint32_t* save_bits;         // forward hidden ops: optional ReLU bits of the result [m, 8]
-};
-struct PairParams {
-  int num_ops;
-  int in_kb;
-  int64_t m;
-  long long* trace;   // debug timeline (RN_CHAIN_TRACE=<launches>): written by CTA 0 only
-  PairOp op[kMaxOps];
-  GemmEpilogue gepi[2];
-};
 struct PairMaps {
   CUtensorMap in;
   CUtensorMap w[kMaxOps];
@@ -230,7 +57,7 @@ chain_pair_kernel(const __grid_constant__ PairMaps maps, const __grid_constant__
   uint64_t* acc_free = bars + 18;      // [2]  leader's: 16 arrivals (8 epilogue warps x 2 CTAs)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
   const int64_t num_super = (p.m + 511) / 512;
   const int64_t cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
@@ -257,54 +84,67 @@ chain_pair_kernel(const __grid_constant__ PairMaps maps, const __grid_constant__
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 0 && lane == 0) {
-    // ===== TMA producer: this CTA's half of every weight K block and its rows of the input K blocks =====
+  if (warp == 0) {
+    // ===== TMA producer (whole warp, one elected lane issues): this CTA's half of every weight K block and its
+    // rows of the input K blocks =====
     uint32_t pos = 0;
+    const uint32_t ring_full_leader = map_to_cta(smem_u32(&ring_full[0]), 0);
     auto acquire = [&](uint32_t total_bytes) -> uint32_t {
       const uint32_t s = pos % kRingStages, ph = (pos / kRingStages) & 1u;
       mbar_wait(&ring_empty[s], ph ^ 1u);
-      if (rank == 0) mbar_arrive_expect_tx(&ring_full[s], total_bytes);
       ++pos;
       return s;
+    };
+    auto load = [&](uint32_t s, uint32_t total_bytes, const CUtensorMap* map, int c0, int c1) {
+      if (elect_one_sync()) {
+        if (rank == 0) mbar_arrive_expect_tx(&ring_full[s], total_bytes);
+        tma_load_2d_pair(smem_base + kSmemRing + s * kStageBytes, map, ring_full_leader + 8u * s, c0, c1);
+      }
+      __syncwarp();
     };
     for (int64_t st = cluster_id; st < num_super; st += num_clusters) {
       for (int l = 0; l < p.num_ops; ++l) {
         const PairOp& L = p.op[l];
         const int nh = L.n >> 1;
         for (int kb = 0; kb < L.kb_act; ++kb) {
-          const uint32_t s = acquire((uint32_t)L.n * 128u);
-          tma_load_2d_pair(smem_base + kSmemRing + s * kStageBytes, &maps.w[l], map_to_cta(smem_u32(&ring_full[s]), 0),
-                           kb * kBK, (int)rank * nh);
+          const uint32_t s = acquire(0);
+          load(s, (uint32_t)L.n * 128u, &maps.w[l], kb * kBK, (int)rank * nh);
         }
         for (int kb = 0; kb < L.kb_in; ++kb) {
           for (int t = 0; t < 2; ++t) {
-            const uint32_t s = acquire(2u * kStageBytes);
+            const uint32_t s = acquire(0);
             const int64_t row0 = st * 512 + t * 256 + (int64_t)rank * 128;
-            tma_load_2d_pair(smem_base + kSmemRing + s * kStageBytes, &maps.in, map_to_cta(smem_u32(&ring_full[s]), 0),
-                             kb * kBK, (int)row0);
+            load(s, 2u * kStageBytes, &maps.in, kb * kBK, (int)row0);
             if (t == 0) {
-              const uint32_t sw = acquire((uint32_t)L.n * 128u);
-              tma_load_2d_pair(smem_base + kSmemRing + sw * kStageBytes, &maps.w[l],
-                               map_to_cta(smem_u32(&ring_full[sw]), 0), (L.kb_act + kb) * kBK, (int)rank * nh);
+              const uint32_t sw = acquire(0);
+              load(sw, (uint32_t)L.n * 128u, &maps.w[l], (L.kb_act + kb) * kBK, (int)rank * nh);
             }
           }
         }
       }
     }
-  } else if (warp == 1 && lane == 0 && rank == 0) {
-    // ===== MMA issuer (leader CTA) =====
+  } else if (warp == 1 && rank == 0) {
+    // ===== MMA issuer (leader CTA; whole warp, one elected lane issues) =====
     uint32_t pos = 0;       // ring position, mirrors the producer's item order
     uint32_t opcount = 0;   // ops issued so far on each tile
     auto wait_full = [&](uint32_t q) {
       mbar_wait(&ring_full[q % kRingStages], (q / kRingStages) & 1u);
     };
     auto stage_addr = [&](uint32_t q) -> uint32_t { return smem_base + kSmemRing + (q % kRingStages) * kStageBytes; };
-    auto mma_kblock = [&](uint32_t tmem_d, uint32_t sa, uint32_t sb, uint32_t idesc, bool first) {
+    // 4 MMAs of one K block, then the commits that depend on them; issued by one elected lane
+    auto mma_kblock = [&](uint32_t tmem_d, uint32_t sa, uint32_t sb, uint32_t idesc, bool first, uint64_t* commit0,
+                          uint64_t* commit1, uint64_t* commit2) {
+      if (elect_one_sync()) {
 #pragma unroll
-      for (int kk = 0; kk < kBK / kUmmaK; ++kk) {
-        const uint32_t koff = kk * kUmmaK * 2;
-        umma2_bf16(tmem_d, make_desc(sa + koff, 16, 1024), make_desc(sb + koff, 16, 1024), idesc, (!first || kk) ? 1u : 0u);
+        for (int kk = 0; kk < kBK / kUmmaK; ++kk) {
+          const uint32_t koff = kk * kUmmaK * 2;
+          umma2_bf16(tmem_d, make_desc(sa + koff, 16, 1024), make_desc(sb + koff, 16, 1024), idesc, (!first || kk) ? 1u : 0u);
+        }
+        if (commit0) umma2_commit(commit0);
+        if (commit1) umma2_commit(commit1);
+        if (commit2) umma2_commit(commit2);
       }
+      __syncwarp();
     };
     for (int64_t st = cluster_id; st < num_super; st += num_clusters) {
       for (int l = 0; l < p.num_ops; ++l, ++opcount) {
@@ -318,18 +158,18 @@ chain_pair_kernel(const __grid_constant__ PairMaps maps, const __grid_constant__
             mbar_wait_cluster(&acc_free[t], free_parity);
             tc_fence_after();
           }
-          if (p.trace && blockIdx.x == 0 && opcount < 64) p.trace[(opcount * 2 + t) * 8 + 0] = clock64();
+          if (p.trace && blockIdx.x == 0 && opcount < 64 && lane == 0) p.trace[(opcount * 2 + t) * 8 + 0] = clock64();
           const uint32_t tmem_d = tmem_base + (uint32_t)t * 256u;
           for (int kb = 0; kb < L.kb_act; ++kb) {
             if (t == 0) {
               wait_full(pos_w + kb);
               tc_fence_after();
             }
-            mma_kblock(tmem_d, smem_base + t * kActBytes + kb * kBlkBytes, stage_addr(pos_w + kb), idesc, kb == 0);
-            if (t == 1) umma2_commit(&ring_empty[(pos_w + kb) % kRingStages]);
+            mma_kblock(tmem_d, smem_base + t * kActBytes + kb * kBlkBytes, stage_addr(pos_w + kb), idesc, kb == 0,
+                       t == 1 ? &ring_empty[(pos_w + kb) % kRingStages] : nullptr,
+                       (kb == L.kb_act - 1 && !L.kb_in) ? &acc_full[t] : nullptr, nullptr);
           }
-          if (L.kb_act && !L.kb_in) umma2_commit(&acc_full[t]);
-          if (p.trace && blockIdx.x == 0 && opcount < 64) p.trace[(opcount * 2 + t) * 8 + 1] = clock64();
+          if (p.trace && blockIdx.x == 0 && opcount < 64 && lane == 0) p.trace[(opcount * 2 + t) * 8 + 1] = clock64();
         }
         pos += L.kb_act;
         // --- K blocks from the chain input: x(tile 0), W, x(tile 1) per K block
@@ -345,10 +185,9 @@ chain_pair_kernel(const __grid_constant__ PairMaps maps, const __grid_constant__
             wait_full(px);
             if (t == 0) wait_full(pw);
             tc_fence_after();
-            mma_kblock(tmem_base + (uint32_t)t * 256u, stage_addr(px), stage_addr(pw), idesc, !L.kb_act && kb == 0);
-            umma2_commit(&ring_empty[px % kRingStages]);
-            if (t == 1) umma2_commit(&ring_empty[pw % kRingStages]);
-            if (kb == L.kb_in - 1) umma2_commit(&acc_full[t]);
+            mma_kblock(tmem_base + (uint32_t)t * 256u, stage_addr(px), stage_addr(pw), idesc, !L.kb_act && kb == 0,
+                       &ring_empty[px % kRingStages], t == 1 ? &ring_empty[pw % kRingStages] : nullptr,
+                       kb == L.kb_in - 1 ? &acc_full[t] : nullptr);
           }
         }
       }
@@ -520,6 +359,7 @@ chain_pair_kernel(const __grid_constant__ PairMaps maps, const __grid_constant__
 }  // namespace
 
 int launch_chain(const ChainArgs& a, cudaStream_t st) {
+  if (a.impl == 1) return launch_chain_ts(a, st);
   if (a.m <= 0) return RN_OK;
   if (a.num_ops < 1 || a.num_ops > kMaxOps) return rn_set_error(RN_ERR_ARG, "chain: 1..12 ops");
   if (a.in_cols % 64 || a.in_cols < 64 || a.in_cols > 256) return rn_set_error(RN_ERR_ARG, "chain: input tile must be 64..256 columns");

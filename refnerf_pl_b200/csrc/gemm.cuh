@@ -76,12 +76,14 @@ struct ChainArgs {
   ActBuf in = {nullptr, nullptr, 0};
   int in_cols = 0;           // K extent of the input tile: multiple of 64, <= 256
   int in_valid = 0;          // valid columns of the input buffer (beyond: zero)
+  int impl = 0;              // 0: chain_pair.cu (SS operands, two row tiles), 1: chain_ts.cu (A operand in TMEM)
   int num_ops = 0;
   ChainOpArgs op[12];
   GemmEpilogue gepi[2];
   double algo_flops = 0.0;
 };
-int launch_chain(const ChainArgs& a, cudaStream_t st);   // chain_pair.cu: CTA pairs, cta_group::2, two row tiles in flight
+int launch_chain(const ChainArgs& a, cudaStream_t st);      // chain_pair.cu: CTA pairs, cta_group::2, two row tiles in flight
+int launch_chain_ts(const ChainArgs& a, cudaStream_t st);   // chain_ts.cu: CTA pairs, A operand in TMEM, column halves
 
 int launch_gemm(const GemmArgs& g, cudaStream_t st);
 int launch_wgrad(const WgradArgs& g, cudaStream_t st);

@@ -277,6 +277,7 @@ struct Ctx {
   MlpScalars sc;
   int impl;
   bool chain = false;  // bf16: fused forward chains
+  int chain_impl = 0;  // ChainArgs::impl
   bool algo = true;  // launches carry algorithmic FLOPs (false while recomputing activations in backward)
 };
 
@@ -342,6 +343,7 @@ double op_flops(int64_t rows, int l, bool skip_part, bool both) {
 int chain_layers(const Ctx& c, int l0, int lh, int64_t rows, ActBuf in, int in_cols, Workspace* keep, bool spatial,
                  GemmEpilogue final_epi) {
   ChainArgs a;
+  a.impl = c.chain_impl;
   a.m = rows;
   a.in = in;
   a.in_cols = in_cols;
@@ -389,6 +391,7 @@ ChainOpArgs bwd_op(const Ctx& c, int l, int in_row0, int n, int kb_act, int kb_i
 // d raw_density / d x0 through the 8 spatial layers, fused (seed tile = w.g[0])
 int normals_chain(const Ctx& c, Workspace& w, int64_t rows) {
   ChainArgs a;
+  a.impl = c.chain_impl;
   a.m = rows;
   a.in = w.g[0];
   a.in_cols = 256;
@@ -527,6 +530,8 @@ int backward_chunk_chain(const Ctx& c, Workspace& w, int64_t row0, int64_t rows,
                           w.d_rgb_raw, w.dcolor, c.st));
   {  // view net: rgb head, V7..V0
     ChainArgs a;
+    a.impl = c.chain_impl;
+  a.impl = c.chain_impl;
     a.m = rows;
     a.in = w.d_rgb_raw;
     a.in_cols = 64;
@@ -566,6 +571,8 @@ int backward_chunk_chain(const Ctx& c, Workspace& w, int64_t row0, int64_t rows,
                                    off(g.tint, 3), w.d_scal, c.st));
   {  // spatial net: heads, S7..S1 (no gradient w.r.t. x0 is needed: sdist is detached)
     ChainArgs a;
+    a.impl = c.chain_impl;
+  a.impl = c.chain_impl;
     a.m = rows;
     a.in = w.dheads;
     a.in_cols = 192;
@@ -658,7 +665,8 @@ int make_ctx(Ctx& c, const RnMlpConfig* cfg, const void* packed, const float* td
   c.sc = {cfg->srgb_mapping, cfg->srgb_normalization, cfg->density_bias, cfg->roughness_bias,
           cfg->rgb_premultiplier, cfg->rgb_bias, cfg->rgb_padding};
   c.impl = cfg->gemm_impl == 1 ? 1 : 0;
-  c.chain = cfg->prec == RN_PREC_BF16 && cfg->gemm_impl == 0;
+  c.chain = cfg->prec == RN_PREC_BF16 && (cfg->gemm_impl == 0 || cfg->gemm_impl == 3);
+  c.chain_impl = cfg->gemm_impl == 3 ? 1 : 0;
   return RN_OK;
 }
 

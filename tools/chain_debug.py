@@ -11,7 +11,8 @@ modes = sys.argv[2].split(',') if len(sys.argv) > 2 else ['eval', 'train']
 p = O.init_params(seed=4, bias_std=0.1, weight_scale=1.3)
 rays = synthetic.blender_rays(n, seed=9)
 outs = {}
-for impl in (2, 0):
+IMPL = int(__import__('os').environ.get('IMPL', '0'))
+for impl in (2, IMPL):
     model, _ = build_model('bf16', mlp_kwargs=dict(gemm_impl=impl, chunk_rows=65536))
     load_params(model, p)
     for mode in modes:
@@ -22,7 +23,7 @@ for impl in (2, 0):
         outs[(impl, mode)] = hist
         print('ran', impl, mode, flush=True)
 for mode in modes:
-    ha, hb = outs[(0, mode)], outs[(2, mode)]
+    ha, hb = outs[(IMPL, mode)], outs[(2, mode)]
     for lvl in range(2):
         for k in ('density', 'rgb', 'roughness', 'normals_pred') + (('normals',) if mode == 'train' else ()):
             d = (ha[lvl][k] - hb[lvl][k]).abs()

@@ -12,7 +12,8 @@ p = O.init_params(seed=5, bias_std=0.1, weight_scale=1.2)
 rays = synthetic.blender_rays(n, seed=10)
 gt = torch.tensor(synthetic.gt_rgb(n, 10), device=DEV)
 grads = {}
-for impl in (0, 2):
+IMPL = int(__import__('os').environ.get('IMPL', '0'))
+for impl in (IMPL, 2):
     model, cfg = build_model('bf16', mlp_kwargs=dict(gemm_impl=impl, chunk_rows=chunk))
     load_params(model, p)
     model.train(True)
@@ -21,6 +22,6 @@ for impl in (0, 2):
     loss, _ = train_utils.total_loss(model, r.viewdirs, r.lossmult, gt, rend, hist, cfg)
     loss.backward()
     grads[impl] = {k: v.grad.clone() for k, v in model.nerf_mlp.named_parameters()}
-for k in grads[0]:
-    a, b = grads[0][k].double(), grads[2][k].double()
+for k in grads[IMPL]:
+    a, b = grads[IMPL][k].double(), grads[2][k].double()
     print(f'{k:28s} rel {float((a - b).norm() / b.norm()):.3e}   |b| {float(b.norm()):.3e}')
