@@ -12,11 +12,13 @@
 //
 // Persistent warp-specialised layout (256 threads): warp 0 TMA producer, warp 1 MMA issuer,
 // warp 2 TMEM allocator, warps 4-7 epilogue (warp%4 = TMEM lane quadrant).
-#include "tc_common.cuh"
+#include "chain_common.cuh"
 
 namespace rn {
 namespace {
 using namespace tc;
+using chain::elect_one_sync;
+using chain::uniform_warp_idx;
 
 // mask bits for 16 columns: bit i set iff mask[row, col+i] > 0 (bf16 hi plane: sign/zero test on the raw bits)
 __device__ __forceinline__ uint32_t mask_bits16(const uint32_t* m) {
@@ -383,7 +385,7 @@ wgrad2_tc_kernel(const __grid_constant__ WgMaps maps, int64_t m, int64_t rows_pe
   uint64_t* tfull = bars + 16;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 17);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
   const int64_t r_begin = (int64_t)blockIdx.x * rows_per_cta;
   const int64_t r_end = min(m, r_begin + rows_per_cta);
   const int nblk = r_end > r_begin ? (int)((r_end - r_begin + kRowBlk - 1) / kRowBlk) : 0;
@@ -405,20 +407,24 @@ wgrad2_tc_kernel(const __grid_constant__ WgMaps maps, int64_t m, int64_t rows_pe
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   if (nblk > 0) {
-    if (warp == 0 && lane == 0) {
+    if (warp == 0) {
+      // whole warp runs the loop, one elected lane issues (uniform registers for the TMA operands)
       const uint32_t stage_tx = (uint32_t)stage_bytes;
       int stage = 0;
       uint32_t phase = 0;
       for (int b = 0; b < nblk; ++b) {
         mbar_wait(&empty[stage], phase ^ 1);
         uint8_t* sbase = smem + stage * stage_bytes;
-        mbar_arrive_expect_tx(&full[stage], stage_tx);
         const int r0 = (int)(r_begin + (int64_t)b * kRowBlk);
-        for (int i = 0; i < 2 * NSLAB; ++i) tma_load_2d(sbase + i * kBoxBytes, &maps.dy_hi, &full[stage], i * 64, r0);
-        for (int i = 0; i < xboxes; ++i) tma_load_2d(sbase + kDyBytes + i * kBoxBytes, &maps.x_hi, &full[stage], i * 64, r0);
+        if (elect_one_sync()) {
+          mbar_arrive_expect_tx(&full[stage], stage_tx);
+          for (int i = 0; i < 2 * NSLAB; ++i) tma_load_2d(sbase + i * kBoxBytes, &maps.dy_hi, &full[stage], i * 64, r0);
+          for (int i = 0; i < xboxes; ++i) tma_load_2d(sbase + kDyBytes + i * kBoxBytes, &maps.x_hi, &full[stage], i * 64, r0);
+        }
+        __syncwarp();
         if (++stage == stages) { stage = 0; phase ^= 1; }
       }
-    } else if (warp == 1 && lane == 0) {
+    } else if (warp == 1) {
       const uint32_t idesc = make_idesc(kx, 1, 1);
       int stage = 0;
       uint32_t phase = 0;
@@ -427,19 +433,22 @@ wgrad2_tc_kernel(const __grid_constant__ WgMaps maps, int64_t m, int64_t rows_pe
         tc_fence_after();
         const uint32_t sa = smem_u32(smem + stage * stage_bytes);
         const uint32_t sb = sa + kDyBytes;
+        if (elect_one_sync()) {
 #pragma unroll
-        for (int kk = 0; kk < kRowBlk / kUmmaK; ++kk) {
-          const uint32_t koff = kk * kUmmaK * 128;
-          const uint64_t db = make_desc(sb + koff, kBoxBytes, 1024);
+          for (int kk = 0; kk < kRowBlk / kUmmaK; ++kk) {
+            const uint32_t koff = kk * kUmmaK * 128;
+            const uint64_t db = make_desc(sb + koff, kBoxBytes, 1024);
 #pragma unroll
-          for (int sl = 0; sl < NSLAB; ++sl)
-            umma_bf16(tmem_base + sl * 256, make_desc(sa + sl * 2 * kBoxBytes + koff, kBoxBytes, 1024), db, idesc,
-                      (b | kk) ? 1u : 0u);
+            for (int sl = 0; sl < NSLAB; ++sl)
+              umma_bf16(tmem_base + sl * 256, make_desc(sa + sl * 2 * kBoxBytes + koff, kBoxBytes, 1024), db, idesc,
+                        (b | kk) ? 1u : 0u);
+          }
+          umma_commit(&empty[stage]);
+          if (b == nblk - 1) umma_commit(&tfull[0]);
         }
-        umma_commit(&empty[stage]);
+        __syncwarp();
         if (++stage == stages) { stage = 0; phase ^= 1; }
       }
-      umma_commit(&tfull[0]);
     } else if (warp >= 4) {
       const int q = warp - 4;
       if (do_bias) {
