@@ -179,6 +179,7 @@ struct PairOp {
   int n;           // MMA N = output columns (multiple of 16)
   int kb_act;      // K blocks read from the resident activation tile (0 or 4)
   int kb_in;       // K blocks read from the chain input tile (streamed through the ring)
+  int in2;         // the input K blocks of this op come from the SECOND input tensor (maps.in2)
   int kind;        // 0: hidden (result -> activation tile [+ TMA save]); 1: global epilogue
   int gepi;        // kind 1: which global epilogue
   int save;        // hidden: TMA-store the result through maps.save[op]
@@ -189,6 +190,7 @@ struct PairOp {
 struct PairParams {
   int num_ops;
   int in_kb;
+  int in2_sync_op;   // -1, or: the second input is a save of this launch; the op before its reader orders store -> load
   int64_t m;
   long long* trace;   // debug timeline (RN_CHAIN_TRACE=<launches>): written by CTA 0 only
   PairOp op[kMaxOps];

@@ -41,6 +41,7 @@ static_assert(kSmemTotal <= 232448, "shared memory budget");
 
 struct PairMaps {
   CUtensorMap in;
+  CUtensorMap in2;
   CUtensorMap w[kMaxOps];
   CUtensorMap save[kMaxOps];
 };
@@ -55,7 +56,8 @@ chain_pair_kernel(const __grid_constant__ PairMaps maps, const __grid_constant__
   uint64_t* ring_empty = bars + 8;     // [8]  per CTA, signalled by the multicast MMA commit
   uint64_t* acc_full = bars + 16;      // [2]  per CTA, multicast MMA commit
   uint64_t* acc_free = bars + 18;      // [2]  leader's: 16 arrivals (8 epilogue warps x 2 CTAs)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
+  uint64_t* in2_ready = bars + 20;     // per CTA: 8 arrivals (epilogue warps: their saves of this super tile are complete)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 22);
 
   const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
@@ -75,6 +77,7 @@ chain_pair_kernel(const __grid_constant__ PairMaps maps, const __grid_constant__
       mbar_init(&acc_full[i], 1);
       mbar_init(&acc_free[i], 16);
     }
+    mbar_init(in2_ready, 8);
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc2(tmem_slot, kTmemCols);
@@ -102,7 +105,8 @@ chain_pair_kernel(const __grid_constant__ PairMaps maps, const __grid_constant__
       }
       __syncwarp();
     };
-    for (int64_t st = cluster_id; st < num_super; st += num_clusters) {
+    uint32_t st_iter = 0;
+    for (int64_t st = cluster_id; st < num_super; st += num_clusters, ++st_iter) {
       for (int l = 0; l < p.num_ops; ++l) {
         const PairOp& L = p.op[l];
         const int nh = L.n >> 1;
@@ -110,11 +114,13 @@ chain_pair_kernel(const __grid_constant__ PairMaps maps, const __grid_constant__
           const uint32_t s = acquire(0);
           load(s, (uint32_t)L.n * 128u, &maps.w[l], kb * kBK, (int)rank * nh);
         }
+        // a second input that is a save of this launch: its TMA stores must have completed (see the epilogue)
+        if (L.kb_in && L.in2 && p.in2_sync_op >= 0) mbar_wait(in2_ready, st_iter & 1u);
         for (int kb = 0; kb < L.kb_in; ++kb) {
           for (int t = 0; t < 2; ++t) {
             const uint32_t s = acquire(0);
             const int64_t row0 = st * 512 + t * 256 + (int64_t)rank * 128;
-            load(s, 2u * kStageBytes, &maps.in, kb * kBK, (int)row0);
+            load(s, 2u * kStageBytes, L.in2 ? &maps.in2 : &maps.in, kb * kBK, (int)row0);
             if (t == 0) {
               const uint32_t sw = acquire(0);
               load(sw, (uint32_t)L.n * 128u, &maps.w[l], (L.kb_act + kb) * kBK, (int)rank * nh);
@@ -312,6 +318,14 @@ chain_pair_kernel(const __grid_constant__ PairMaps maps, const __grid_constant__
               if (has_group >> (t ^ 1) & 1u) newer |= 1u << (t ^ 1);
               any_store = true;
             }
+            if (l == p.in2_sync_op && t == 1) {
+              // every store group older than this op's two has fully completed -> the producer may re-load that save
+              if (lane == 0) {
+                if (L.save) asm volatile("cp.async.bulk.wait_group 2;" ::: "memory");
+                else asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+                mbar_arrive(in2_ready);
+              }
+            }
             if (MODE == 0 && L.save_bits && row_ok)
               *(reinterpret_cast<uint4*>(L.save_bits + (size_t)row * 8) + h) = make_uint4(bits_out[0], bits_out[1], bits_out[2], bits_out[3]);
           } else {
@@ -370,6 +384,8 @@ int launch_chain(const ChainArgs& a, cudaStream_t st) {
   int rc;
   int mode = -1;
   if ((rc = tc::make_map(&maps.in, a.in.hi, a.m, a.in_valid, a.in.ld, kBM))) return rc;
+  if ((rc = tc::make_map(&maps.in2, a.in2.hi, a.m, a.in2_valid, a.in2.ld, kBM))) return rc;
+  p.in2_sync_op = -1;
   p.num_ops = a.num_ops;
   p.in_kb = a.in_cols / kBK;
   p.m = a.m;
@@ -379,13 +395,23 @@ int launch_chain(const ChainArgs& a, cudaStream_t st) {
     if (l >= a.num_ops) continue;
     const ChainOpArgs& L = a.op[l];
     if (L.n % 16 || L.n < 16 || L.n > 256 || (L.kind == 0 && L.n != 256)) return rn_set_error(RN_ERR_ARG, "chain: bad op width");
-    if ((L.kb_act != 0 && L.kb_act != 4) || (L.kb_in != 0 && L.kb_in != p.in_kb) || L.kb_act + L.kb_in == 0 ||
-        (l == 0 && L.kb_act != 0))
+    const int in_kb_expected = L.in2 ? a.in2_cols / kBK : p.in_kb;
+    if ((L.kb_act != 0 && L.kb_act != 4) || (L.kb_in != 0 && L.kb_in != in_kb_expected) || L.kb_act + L.kb_in == 0 ||
+        (l == 0 && L.kb_act != 0) || (L.in2 && (!a.in2.hi || a.in2_cols % 64)))
       return rn_set_error(RN_ERR_ARG, "chain: bad K structure");
+    if (L.in2 && L.kb_in) {
+      // if the second input is a save of an earlier op of this launch, op l-1's epilogue orders store -> load
+      for (int j = 0; j < l; ++j)
+        if (a.op[j].kind == 0 && a.op[j].save_hi == a.in2.hi) {
+          if (j > l - 3) return rn_set_error(RN_ERR_ARG, "chain: a re-loaded save must be produced at least 3 ops earlier");
+          if (a.op[l - 1].kind != 0) return rn_set_error(RN_ERR_ARG, "chain: the op before a re-loaded save's reader must be hidden");
+          p.in2_sync_op = l - 1;
+        }
+    }
     const int ktot = (L.kb_act + L.kb_in) * kBK;
     if ((rc = tc::make_map(&maps.w[l], L.w, L.n, ktot, L.w_ld, L.n / 2))) return rc;
     PairOp& o = p.op[l];
-    o.n = L.n; o.kb_act = L.kb_act; o.kb_in = L.kb_in;
+    o.n = L.n; o.kb_act = L.kb_act; o.kb_in = L.kb_in; o.in2 = L.in2;
     o.kind = L.kind; o.gepi = L.gepi; o.bias = L.bias;
     o.mask_bits = L.mask_bits; o.save_bits = L.save_bits;
     o.save = (L.kind == 0 && L.save_hi) ? 1 : 0;

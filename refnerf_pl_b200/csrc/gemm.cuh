@@ -61,6 +61,7 @@ struct ChainOpArgs {
   int n = 0;                 // output columns; 256 for hidden ops
   int kb_act = 0;            // 64-wide K blocks from the running activation (0 or 4)
   int kb_in = 0;             // K blocks from the chain input tile (0 or all of them)
+  int in2 = 0;               // take the input K blocks from ChainArgs::in2 instead (chain_pair.cu only)
   int kind = 0;              // 0 hidden, 1 global epilogue
   int mode = 0;              // hidden: 0 bias + ReLU, 1 ReLU mask
   int gepi = 0;              // global: epilogue index (0/1)
@@ -76,6 +77,8 @@ struct ChainArgs {
   ActBuf in = {nullptr, nullptr, 0};
   int in_cols = 0;           // K extent of the input tile: multiple of 64, <= 256
   int in_valid = 0;          // valid columns of the input buffer (beyond: zero)
+  ActBuf in2 = {nullptr, nullptr, 0};   // optional second input tensor [m, 64*k] (may be a save_hi buffer of an earlier op
+  int in2_cols = 0, in2_valid = 0;      // of the same launch: the kernel orders the TMA store before the TMA load)
   int impl = 0;              // 0: chain_pair.cu (SS operands, two row tiles), 1: chain_ts.cu (A operand in TMEM)
   int num_ops = 0;
   ChainOpArgs op[12];

@@ -51,11 +51,12 @@ inline int planes(int prec) { return prec == RN_PREC_BF16X3 ? 2 : 1; }
 inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
 // Offsets into the packed blob.  Per layer: Wf [n_pad, k_tot] (planes), Wt [k_tot, nt_pad] (planes),
-// bias f32 [n_pad].  After all layers: wd f32 [256] (raw_density weight row, for the normals pass).
+// bias f32 [n_pad].  After all layers: wd f32 [256] (raw_density weight row, for the normals pass), wcat (below).
 struct PackedLayout {
   size_t wf[kNumLayers], wt[kNumLayers], bias[kNumLayers];
   size_t wf_plane[kNumLayers], wt_plane[kNumLayers];  // byte stride between hi and lo planes
   size_t wd;
+  size_t wcat;   // bf16 [256, 512]: [Wt(V0) | Wt(V5)[256:512, :]] -- d v0 = [dY0 | dY5] * wcat^T in ONE dgrad op (fused chains)
   size_t total;
 };
 
@@ -76,6 +77,8 @@ inline PackedLayout packed_layout(int prec) {
   }
   p.wd = off;
   off += align256(256 * 4);
+  p.wcat = off;
+  off += align256((size_t)256 * 512 * 2);
   p.total = off;
   return p;
 }

@@ -266,6 +266,7 @@ struct Packed {
   }
   const float* bias(int l) const { return reinterpret_cast<const float*>(base + lay.bias[l]); }
   const float* wd() const { return reinterpret_cast<const float*>(base + lay.wd); }
+  const void* wcat() const { return base + lay.wcat; }
 };
 
 struct Ctx {
@@ -528,10 +529,10 @@ int backward_chunk_chain(const Ctx& c, Workspace& w, int64_t row0, int64_t rows,
   auto off = [&](const float* p, int per) -> const float* { return p ? p + row0 * per : nullptr; };
   RN_TRY(launch_color_bwd(prec, w.rgb_raw, w.heads_raw, rows, c.sc, off(g.rgb, 3), off(g.diffuse, 3), off(g.specular, 3),
                           w.d_rgb_raw, w.dcolor, c.st));
+  const bool fuse_dv0 = c.chain_impl == 0;   // SS chain: d v0 = [dY0 | dY5] * wcat^T as ONE op, dY5 re-read from its save
   {  // view net: rgb head, V7..V0
     ChainArgs a;
     a.impl = c.chain_impl;
-  a.impl = c.chain_impl;
     a.m = rows;
     a.in = w.d_rgb_raw;
     a.in_cols = 64;
@@ -542,21 +543,38 @@ int backward_chunk_chain(const Ctx& c, Workspace& w, int64_t row0, int64_t rows,
     for (int l = 7; l >= 1; --l) {
       const int L = kLayerV0 + l;
       if (l == 5) {
-        a.op[n] = bwd_op(c, L, 256, 256, 4, 0, nullptr, nullptr);
-        a.op[n].gepi = 0;
         flops += op_flops(rows, L, true, false);
-        ++n;
+        if (!fuse_dv0) {
+          a.op[n] = bwd_op(c, L, 256, 256, 4, 0, nullptr, nullptr);
+          a.op[n].gepi = 0;
+          ++n;
+        }
       }
       a.op[n++] = bwd_op(c, L, 0, 256, 4, 0, w.mb(l), w.gs[l - 1].hi);
       flops += op_flops(rows, L, false, false);
     }
-    a.op[n] = bwd_op(c, kLayerV0, 0, 256, 4, 0, nullptr, nullptr);
-    a.op[n].gepi = 1;
     flops += op_flops(rows, kLayerV0, false, false);
-    ++n;
+    if (fuse_dv0) {
+      ChainOpArgs& F = a.op[n];
+      F.n = 256; F.kb_act = 4; F.kb_in = 4; F.in2 = 1; F.kind = 1; F.mode = 1; F.gepi = 0;
+      F.w = c.pk.wcat(); F.w_ld = 512;
+      ++n;
+      a.in2 = w.gs[5];
+      a.in2_cols = 256;
+      a.in2_valid = 256;
+      // columns 0..127 (bottleneck gradient) leave as the bf16 operand of the heads dgrad / wgrad, 128..255 as f32
+      GemmEpilogue e;
+      e.out = w.d_bott; e.out_cols = 128;
+      e.f32 = w.dv0f + 128; e.f32_ld = 256; e.f32_col0 = 128; e.f32_cols = 128; e.f32_accum = 0;
+      a.gepi[0] = e;
+    } else {
+      a.op[n] = bwd_op(c, kLayerV0, 0, 256, 4, 0, nullptr, nullptr);
+      a.op[n].gepi = 1;
+      ++n;
+      a.gepi[0] = epi_f32(w.dv0f, 256, 256, 0);
+      a.gepi[1] = epi_f32(w.dv0f, 256, 256, 1);
+    }
     a.num_ops = n;
-    a.gepi[0] = epi_f32(w.dv0f, 256, 256, 0);
-    a.gepi[1] = epi_f32(w.dv0f, 256, 256, 1);
     a.algo_flops = flops;
     RN_TRY(launch_chain(a, c.st));
   }
@@ -565,7 +583,7 @@ int backward_chunk_chain(const Ctx& c, Workspace& w, int64_t row0, int64_t rows,
     const int L = kLayerV0 + l;
     RN_TRY(wgrad_layer(c, w, L, rows, w.gs[l], 256, 256, l == 0 ? w.v0 : w.b(l), l == 5 ? w.v0 : none));
   }
-  RN_TRY(launch_f32_to_act(prec, w.dv0f, 256, 0, rows, 128, w.d_bott, c.st));
+  if (!fuse_dv0) RN_TRY(launch_f32_to_act(prec, w.dv0f, 256, 0, rows, 128, w.d_bott, c.st));
   RN_TRY(launch_heads_prologue_bwd(prec, w.heads_raw, c.viewdirs, c.s, row0, rows, c.sc, w.dv0f, w.dcolor,
                                    off(g.density, 1), off(g.normals_pred, 3), off(g.grad_pred, 3), off(g.roughness, 1),
                                    off(g.tint, 3), w.d_scal, c.st));
@@ -738,6 +756,13 @@ extern "C" int rn_mlp_pack(const float* const* params, void* packed, int prec, v
   }
   e = cudaMemcpyAsync(base + lay.wd, params[kParamDensity], 256 * 4, cudaMemcpyDeviceToDevice, st);
   if (e != cudaSuccess) return rn_set_cuda_error(e, __FILE__, __LINE__);
+  if (prec == RN_PREC_BF16) {
+    // wcat[j, 0:256] = W_V0[:, j], wcat[j, 256:512] = W_V5[:, 256 + j]  (j = view-net input feature, 201 real)
+    void* wc = base + lay.wcat;
+    const int p0 = layer_param(kLayerV0), p5 = layer_param(kLayerV0 + 5);
+    RN_TRY(launch_pack_segment(prec, params[p0], kViewReal, 256, kViewReal, 1, wc, nullptr, 512, 0, 0, st));
+    RN_TRY(launch_pack_segment(prec, params[p5] + 256, 256 + kViewReal, 256, kViewReal, 1, wc, nullptr, 512, 0, 256, st));
+  }
   return RN_OK;
 }
 
