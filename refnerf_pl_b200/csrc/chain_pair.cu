@@ -57,7 +57,10 @@ chain_pair_kernel(const __grid_constant__ PairMaps maps, const __grid_constant__
   uint64_t* acc_full = bars + 16;      // [2]  per CTA, multicast MMA commit
   uint64_t* acc_free = bars + 18;      // [2]  leader's: 16 arrivals (8 epilogue warps x 2 CTAs)
   uint64_t* in2_ready = bars + 20;     // per CTA: 8 arrivals (epilogue warps: their saves of this super tile are complete)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 22);
+  uint64_t* seed_done = bars + 22;     // [2]  leader's: 16 arrivals (seed op: activation tile generated).  A separate
+                                       //      barrier: a warp's seed arrival must not be able to land in the acc_free
+                                       //      phase of the op before it (no wait separates the two arrivals)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 24);
 
   const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
@@ -78,6 +81,8 @@ chain_pair_kernel(const __grid_constant__ PairMaps maps, const __grid_constant__
       mbar_init(&acc_free[i], 16);
     }
     mbar_init(in2_ready, 8);
+    mbar_init(&seed_done[0], 16);
+    mbar_init(&seed_done[1], 16);
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc2(tmem_slot, kTmemCols);
@@ -132,7 +137,10 @@ chain_pair_kernel(const __grid_constant__ PairMaps maps, const __grid_constant__
   } else if (warp == 1 && rank == 0) {
     // ===== MMA issuer (leader CTA; whole warp, one elected lane issues) =====
     uint32_t pos = 0;       // ring position, mirrors the producer's item order
-    uint32_t opcount = 0;   // ops issued so far on each tile
+    uint32_t opcount = 0;   // ops walked so far (trace index)
+    uint32_t nreal = 0;     // GEMM ops issued so far on each tile (acc_free phases)
+    uint32_t nseed = 0;     // seed ops passed so far (seed_done phases)
+    bool seed_pending = false;
     auto wait_full = [&](uint32_t q) {
       mbar_wait(&ring_full[q % kRingStages], (q / kRingStages) & 1u);
     };
@@ -155,13 +163,20 @@ chain_pair_kernel(const __grid_constant__ PairMaps maps, const __grid_constant__
     for (int64_t st = cluster_id; st < num_super; st += num_clusters) {
       for (int l = 0; l < p.num_ops; ++l, ++opcount) {
         const PairOp& L = p.op[l];
+        if (L.kind == 2) {           // seed op: the epilogue warps generate the activation tile, no MMA
+          ++nseed;
+          seed_pending = true;
+          continue;
+        }
         const uint32_t idesc = make_idesc2(L.n);
-        const uint32_t free_parity = (opcount & 1u) ^ 1u;
+        const uint32_t free_parity = (nreal & 1u) ^ 1u;   // epilogue of the previous GEMM op on this tile done
+        ++nreal;
         // --- K blocks from the resident activation tiles: tile 0 then tile 1 over the same weight stages
         const uint32_t pos_w = pos;
         for (int t = 0; t < 2; ++t) {
           if (L.kb_act) {
             mbar_wait_cluster(&acc_free[t], free_parity);
+            if (seed_pending) mbar_wait_cluster(&seed_done[t], (nseed - 1u) & 1u);
             tc_fence_after();
           }
           if (p.trace && blockIdx.x == 0 && opcount < 64 && lane == 0) p.trace[(opcount * 2 + t) * 8 + 0] = clock64();
@@ -178,6 +193,7 @@ chain_pair_kernel(const __grid_constant__ PairMaps maps, const __grid_constant__
           if (p.trace && blockIdx.x == 0 && opcount < 64 && lane == 0) p.trace[(opcount * 2 + t) * 8 + 1] = clock64();
         }
         pos += L.kb_act;
+        if (L.kb_act) seed_pending = false;
         // --- K blocks from the chain input: x(tile 0), W, x(tile 1) per K block
         for (int kb = 0; kb < L.kb_in; ++kb) {
           const uint32_t px0 = pos, pw = pos + 1, px1 = pos + 2;
@@ -207,14 +223,16 @@ chain_pair_kernel(const __grid_constant__ PairMaps maps, const __grid_constant__
     // write identical values, so no cross-warp barrier is needed: every warp only relies on its own stores.
     const uint32_t bias_half = smem_base + kSmemBias + (uint32_t)h * 512u;
     const uint32_t free_addr0 = map_to_cta(smem_u32(&acc_free[0]), 0);   // leader's acc_free[0]; [1] is 8 bytes on
+    const uint32_t seed_addr0 = map_to_cta(smem_u32(&seed_done[0]), 0);
     uint32_t opcount = 0;
+    uint32_t nfull = 0;                  // accumulator commits consumed so far (seed ops have none)
     uint32_t has_group = 0, newer = 0;   // TMA-store bookkeeping, bit t (see below)
     bool any_store = false;
     uint4 bits_next = make_uint4(0, 0, 0, 0);
     auto load_bits = [&](int64_t st, int l, int t) -> uint4 {
       // ReLU bits of this thread's row for op l (this warp's 128 columns = words 4h .. 4h+3)
       uint4 b = make_uint4(0, 0, 0, 0);
-      if (l < p.num_ops && st < num_super && p.op[l].kind == 0) {
+      if (l < p.num_ops && st < num_super && p.op[l].kind != 1) {
         const int64_t row = st * 512 + t * 256 + (int64_t)rank * 128 + r_in_tile;
         if (row < p.m) b = __ldg(reinterpret_cast<const uint4*>(p.op[l].mask_bits + (size_t)row * 8) + h);
       }
@@ -224,8 +242,9 @@ chain_pair_kernel(const __grid_constant__ PairMaps maps, const __grid_constant__
     for (int64_t st = cluster_id; st < num_super; st += num_clusters) {
       for (int l = 0; l < p.num_ops; ++l, ++opcount) {
         const PairOp& L = p.op[l];
-        const bool hidden = L.kind == 0;
-        const float* bias_ptr = hidden ? (MODE == 0 ? L.bias : nullptr) : p.gepi[L.gepi].bias;
+        const bool seed = MODE == 1 && L.kind == 2;   // act tile = bits ? vec : 0 (vec staged like a bias), no accumulator
+        const bool hidden = L.kind == 0 || seed;
+        const float* bias_ptr = (L.kind == 0) ? (MODE == 0 ? L.bias : nullptr) : (seed ? L.bias : p.gepi[L.gepi].bias);
         const uint32_t bias_buf = bias_half + (opcount & 1u) * 1024u;
         float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
         if (bias_ptr && h * 128 + 4 * lane < L.n) bv = __ldg(reinterpret_cast<const float4*>(bias_ptr + h * 128) + lane);
@@ -241,8 +260,10 @@ chain_pair_kernel(const __grid_constant__ PairMaps maps, const __grid_constant__
           }
           const bool tr = p.trace && blockIdx.x == 0 && warp == 4 && lane == 0 && opcount < 64;
           if (tr) p.trace[(opcount * 2 + t) * 8 + 2] = clock64();
-          mbar_wait(&acc_full[t], opcount & 1u);
-          tc_fence_after();
+          if (!seed) {
+            mbar_wait(&acc_full[t], nfull & 1u);
+            tc_fence_after();
+          }
           if (tr) p.trace[(opcount * 2 + t) * 8 + 3] = clock64();
           if (t == 0 && bias_ptr) {
             asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(bias_buf + 16u * lane), "f"(bv.x), "f"(bv.y), "f"(bv.z),
@@ -264,13 +285,15 @@ chain_pair_kernel(const __grid_constant__ PairMaps maps, const __grid_constant__
             const uint32_t bits_arr[4] = {bits_cur.x, bits_cur.y, bits_cur.z, bits_cur.w};
             uint32_t bits_out[4];
             uint32_t ra[32], rb[32];
-            tmem_ld32(taddr, ra);
+            if (!seed) tmem_ld32(taddr, ra);
 #pragma unroll
             for (int g = 0; g < 4; ++g) {   // 32-column groups of this warp's 128 columns; TMEM loads run one group ahead
               uint32_t* cur = (g & 1) ? rb : ra;
               uint32_t* nxt = (g & 1) ? ra : rb;
-              tmem_ld_wait();
-              if (g < 3) tmem_ld32(taddr + (uint32_t)((g + 1) * 32), nxt);
+              if (!seed) {
+                tmem_ld_wait();
+                if (g < 3) tmem_ld32(taddr + (uint32_t)((g + 1) * 32), nxt);
+              }
               uint32_t packed[16];
               if (MODE == 0) {
                 const uint32_t baddr = bias_buf + (uint32_t)g * 128u;
@@ -281,6 +304,15 @@ chain_pair_kernel(const __grid_constant__ PairMaps maps, const __grid_constant__
                   packed[2 * i + 1] = pack_relu_bf16x2(__uint_as_float(cur[4 * i + 2]) + b.z, __uint_as_float(cur[4 * i + 3]) + b.w);
                 }
                 if (L.save_bits) bits_out[g] = relu_bits_of(packed);
+              } else if (seed) {
+                // seed tile of a dgrad chain: vec[col] where the ReLU bit is set (vec staged in the bias buffer)
+                const uint32_t baddr = bias_buf + (uint32_t)g * 128u;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                  const float4 b = lds128f(baddr + 16u * i);
+                  packed[2 * i] = apply_relu_bits(bits_arr[g], 2 * i, pack_bf16x2(b.x, b.y));
+                  packed[2 * i + 1] = apply_relu_bits(bits_arr[g], 2 * i + 1, pack_bf16x2(b.z, b.w));
+                }
               } else {
 #pragma unroll
                 for (int i = 0; i < 16; ++i)
@@ -299,7 +331,7 @@ chain_pair_kernel(const __grid_constant__ PairMaps maps, const __grid_constant__
             __syncwarp();
             if (tr) p.trace[(opcount * 2 + t) * 8 + 4] = clock64();
             if (lane == 0) {
-              mbar_arrive_cluster_addr(free_addr0 + 8u * t);
+              mbar_arrive_cluster_addr((seed ? seed_addr0 : free_addr0) + 8u * t);
               if (L.save) {
                 const int64_t row_w = st * 512 + t * 256 + (int64_t)rank * 128 + q * 32;
                 if (row_w < p.m) {
@@ -360,6 +392,7 @@ chain_pair_kernel(const __grid_constant__ PairMaps maps, const __grid_constant__
             if (lane == 0) mbar_arrive_cluster_addr(free_addr0 + 8u * t);
           }
         }
+        if (!seed) ++nfull;
       }
     }
     if (any_store && lane == 0) tma_store_wait_all();
@@ -376,7 +409,7 @@ int launch_chain(const ChainArgs& a, cudaStream_t st) {
   if (a.impl == 1) return launch_chain_ts(a, st);
   if (a.m <= 0) return RN_OK;
   if (a.num_ops < 1 || a.num_ops > kMaxOps) return rn_set_error(RN_ERR_ARG, "chain: 1..12 ops");
-  if (a.in_cols % 64 || a.in_cols < 64 || a.in_cols > 256) return rn_set_error(RN_ERR_ARG, "chain: input tile must be 64..256 columns");
+  if (a.in.hi && (a.in_cols % 64 || a.in_cols < 64 || a.in_cols > 256)) return rn_set_error(RN_ERR_ARG, "chain: input tile must be 64..256 columns");
   if (a.m + 512 > 0x7fffffffLL) return rn_set_error(RN_ERR_ARG, "chain: too many rows for one launch");
   PairMaps maps;
   PairParams p;
@@ -387,17 +420,27 @@ int launch_chain(const ChainArgs& a, cudaStream_t st) {
   if ((rc = tc::make_map(&maps.in2, a.in2.hi, a.m, a.in2_valid, a.in2.ld, kBM))) return rc;
   p.in2_sync_op = -1;
   p.num_ops = a.num_ops;
-  p.in_kb = a.in_cols / kBK;
+  p.in_kb = a.in.hi ? a.in_cols / kBK : 0;
   p.m = a.m;
   for (int l = 0; l < kMaxOps; ++l) {
     memset(&maps.w[l], 0, sizeof(CUtensorMap));
     memset(&maps.save[l], 0, sizeof(CUtensorMap));
     if (l >= a.num_ops) continue;
     const ChainOpArgs& L = a.op[l];
+    if (L.kind == 2) {
+      // seed op of a dgrad chain: activation tile = ReLU bit ? vec[col] : 0 (no GEMM)
+      if (!L.bias || !L.mask_bits || L.kb_act || L.kb_in || L.save_hi || l + 1 >= a.num_ops || a.op[l + 1].kb_act != 4)
+        return rn_set_error(RN_ERR_ARG, "chain: bad seed op (needs vec + bits and a following op that reads the activation tile)");
+      if (mode < 0) mode = 1;
+      if (mode != 1) return rn_set_error(RN_ERR_ARG, "chain: seed ops belong to backward chains");
+      PairOp& o = p.op[l];
+      o.n = 256; o.kind = 2; o.bias = L.bias; o.mask_bits = L.mask_bits;
+      continue;
+    }
     if (L.n % 16 || L.n < 16 || L.n > 256 || (L.kind == 0 && L.n != 256)) return rn_set_error(RN_ERR_ARG, "chain: bad op width");
     const int in_kb_expected = L.in2 ? a.in2_cols / kBK : p.in_kb;
     if ((L.kb_act != 0 && L.kb_act != 4) || (L.kb_in != 0 && L.kb_in != in_kb_expected) || L.kb_act + L.kb_in == 0 ||
-        (l == 0 && L.kb_act != 0) || (L.in2 && (!a.in2.hi || a.in2_cols % 64)))
+        (l == 0 && L.kb_act != 0) || (L.in2 && (!a.in2.hi || a.in2_cols % 64)) || (L.kb_in && !L.in2 && !a.in.hi))
       return rn_set_error(RN_ERR_ARG, "chain: bad K structure");
     if (L.in2 && L.kb_in) {
       // if the second input is a save of an earlier op of this launch, op l-1's epilogue orders store -> load

@@ -62,7 +62,8 @@ struct ChainOpArgs {
   int kb_act = 0;            // 64-wide K blocks from the running activation (0 or 4)
   int kb_in = 0;             // K blocks from the chain input tile (0 or all of them)
   int in2 = 0;               // take the input K blocks from ChainArgs::in2 instead (chain_pair.cu only)
-  int kind = 0;              // 0 hidden, 1 global epilogue
+  int kind = 0;              // 0 hidden, 1 global epilogue, 2 seed (backward chains, chain_pair.cu): the activation tile is
+                             // generated as mask_bits ? bias[col] : 0 -- no GEMM, no input tensor
   int mode = 0;              // hidden: 0 bias + ReLU, 1 ReLU mask
   int gepi = 0;              // global: epilogue index (0/1)
   const void* w = nullptr;   // bf16 weights [n, (kb_act + kb_in) * 64] K-major

@@ -389,15 +389,22 @@ ChainOpArgs bwd_op(const Ctx& c, int l, int in_row0, int n, int kb_act, int kb_i
   return L;
 }
 
-// d raw_density / d x0 through the 8 spatial layers, fused (seed tile = w.g[0])
+// d raw_density / d x0 through the 8 spatial layers, fused.  SS chain: the seed gradient (raw_density weight row where
+// a8 > 0) is generated inside the kernel from the ReLU bits; TS chain: it is read from w.g[0].
 int normals_chain(const Ctx& c, Workspace& w, int64_t rows) {
   ChainArgs a;
   a.impl = c.chain_impl;
   a.m = rows;
-  a.in = w.g[0];
-  a.in_cols = 256;
-  a.in_valid = 256;
+  const bool gen_seed = c.chain_impl == 0;
   int n = 0;
+  if (gen_seed) {
+    ChainOpArgs& S = a.op[n++];
+    S.n = 256; S.kind = 2; S.mode = 1; S.bias = c.pk.wd(); S.mask_bits = w.ma(8);
+  } else {
+    a.in = w.g[0];
+    a.in_cols = 256;
+    a.in_valid = 256;
+  }
   double flops = 0.0;
   for (int l = 7; l >= 1; --l) {
     if (l == 5) {
@@ -406,7 +413,8 @@ int normals_chain(const Ctx& c, Workspace& w, int64_t rows) {
       flops += op_flops(rows, 5, true, false);
       ++n;
     }
-    a.op[n] = bwd_op(c, l, 0, 256, l == 7 ? 0 : 4, l == 7 ? 4 : 0, w.ma(l), nullptr);
+    const bool from_in = l == 7 && !gen_seed;
+    a.op[n] = bwd_op(c, l, 0, 256, from_in ? 0 : 4, from_in ? 4 : 0, w.ma(l), nullptr);
     flops += op_flops(rows, l, false, false);
     ++n;
   }
@@ -440,9 +448,9 @@ int forward_chunk(const Ctx& c, Workspace& w, int64_t row0, int64_t rows, const 
   }
   if (want_normals) {
     // d raw_density / d x0 through the spatial net (models.py:603-609); result is a constant
-    if (c.chain)
+    if (c.chain && c.chain_impl == 1)
       RN_TRY(launch_density_grad_seed_bits(w.ma(8), c.pk.wd(), w.g[0], rows, c.st));
-    else
+    else if (!c.chain)
       RN_TRY(launch_density_grad_seed(prec, w.a(8), c.pk.wd(), w.g[0], rows, c.st));
     if (c.chain) {
       RN_TRY(normals_chain(c, w, rows));
