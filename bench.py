@@ -203,6 +203,18 @@ def time_hbm_kernels(dev, peaks):
     out['composite_fwd_extras'] = entry(11384, n, sec)
     sec = timeit(lambda: ops.composite_fwd(dens, t, dirs, far, c3[0], c3[1], c3[2], c3[3], c3[4], rough, c3[5], 1.0, False))
     out['composite_fwd'] = entry(6208, n, sec)
+    w_, comp_, _, _ = ops.composite_fwd(dens, t, dirs, far, c3[0], c3[1], c3[2], c3[3], c3[4], rough, c3[5], 1.0, False)
+    gwt, gcomp, empty = rnd(n, s), rnd(n, 16), torch.empty(0, device=dev)
+    sec = timeit(lambda: ops.composite_bwd(dens, t, dirs, c3[0], c3[1], c3[2], c3[3], c3[4], rough, c3[5], w_, comp_, gwt, gcomp,
+                                           empty, 1.0, False))
+    # reads density, tdist, weights, g_weights, 3 colour arrays; writes d_density + 3 colour gradients
+    out['composite_bwd'] = entry(512 * 3 + 516 + 128 + 3 * 1536 + 512 + 3 * 1536, n, sec)
+    te = torch.sort(rnd(n, s + 1), dim=-1).values
+    we = rnd(n, s)
+    sec = timeit(lambda: ops.lossfun_outer(te, dens, te, we))
+    out['lossfun_outer'] = entry(2 * 516 + 2 * 512 + 512, n, sec)
+    sec = timeit(lambda: ops.distortion(te, we))
+    out['distortion'] = entry(516 + 512 + 4, n, sec)
     n2 = 131072              # 270 MB per launch
     sd = torch.sort(rnd(n2, s + 1), dim=-1).values
     w = rnd(n2, s)

@@ -430,6 +430,116 @@ __device__ __forceinline__ void bwd_vec3(const float* __restrict__ v, float* __r
   }
 }
 
+// ---- S = 128 fast path of the backward: lane l owns samples 4l..4l+3 (see composite_fwd128_kernel) -------------
+// gw[k] += sum_c g[c] * v[k][c];  dv[k][c] = w[k] * g[c]   for one [128,3] array (v / dv may be null)
+__device__ __forceinline__ void bwd_samples4(const float* __restrict__ v, float* __restrict__ dv, int lane, const float w[4],
+                                             const float g[3], float gw[4]) {
+  if (v) {
+    const float4* p = reinterpret_cast<const float4*>(v) + 3 * lane;
+    const float4 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2);
+    gw[0] += g[0] * a.x + g[1] * a.y + g[2] * a.z;
+    gw[1] += g[0] * a.w + g[1] * b.x + g[2] * b.y;
+    gw[2] += g[0] * b.z + g[1] * b.w + g[2] * c.x;
+    gw[3] += g[0] * c.y + g[1] * c.z + g[2] * c.w;
+  }
+  if (dv) {
+    float4* q = reinterpret_cast<float4*>(dv) + 3 * lane;
+    q[0] = make_float4(w[0] * g[0], w[0] * g[1], w[0] * g[2], w[1] * g[0]);
+    q[1] = make_float4(w[1] * g[1], w[1] * g[2], w[2] * g[0], w[2] * g[1]);
+    q[2] = make_float4(w[2] * g[2], w[3] * g[0], w[3] * g[1], w[3] * g[2]);
+  }
+}
+
+__global__ void __launch_bounds__(kWarps * 32)
+composite_bwd128_kernel(const float* __restrict__ density, const float* __restrict__ tdist, const float* __restrict__ dirs,
+                        const float* __restrict__ rgb, const float* __restrict__ diffuse, const float* __restrict__ specular,
+                        const float* __restrict__ normals, const float* __restrict__ normals_pred,
+                        const float* __restrict__ roughness, const float* __restrict__ tint,
+                        const float* __restrict__ weights, const float* __restrict__ comp,
+                        const float* __restrict__ g_weights, const float* __restrict__ g_comp,
+                        const float* __restrict__ g_extras, int64_t n_rays, float bg, float* __restrict__ d_density,
+                        float* __restrict__ d_rgb, float* __restrict__ d_diffuse, float* __restrict__ d_specular,
+                        float* __restrict__ d_normals_pred, float* __restrict__ d_roughness, float* __restrict__ d_tint) {
+  constexpr int s = 128;
+  __shared__ float sm_t[kWarps][s + 4];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t ray = (int64_t)blockIdx.x * kWarps + warp;
+  if (ray >= n_rays) return;
+  float* ts = sm_t[warp];
+  const float4 w4 = __ldg(reinterpret_cast<const float4*>(weights + ray * s) + lane);
+  const float4 d4 = __ldg(reinterpret_cast<const float4*>(density + ray * s) + lane);
+  float4 gw4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (g_weights) gw4 = __ldg(reinterpret_cast<const float4*>(g_weights + ray * s) + lane);
+  for (int i = lane; i <= s; i += 32) ts[i] = __ldg(tdist + ray * (s + 1) + i);
+  const float dx = dirs[ray * 3 + 0], dy = dirs[ray * 3 + 1], dz = dirs[ray * 3 + 2];
+  const float dnorm = sqrtf(dx * dx + dy * dy + dz * dz);
+  const float acc = comp[ray * 16 + 10];
+  const float bgmask = (1.f - acc > 0.f) ? bg : 0.f;  // d max(0, 1-acc)/d acc
+  float g0[3], g1[3], g2[3];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    g0[c] = g_comp[ray * 16 + c];
+    g1[c] = g_comp[ray * 16 + 3 + c];
+    g2[c] = g_comp[ray * 16 + 6 + c];
+  }
+  const float g_dist = g_comp[ray * 16 + 9], g_acc = g_comp[ray * 16 + 10];
+  const float gbg = -bgmask * (g0[0] + g0[1] + g0[2] + g1[0] + g1[1] + g1[2] + g2[0] + g2[1] + g2[2]);
+  __syncwarp();
+  float t[5];
+#pragma unroll
+  for (int k = 0; k < 5; ++k) t[k] = ts[4 * lane + k];
+  const float w[4] = {w4.x, w4.y, w4.z, w4.w};
+  const float dens[4] = {d4.x, d4.y, d4.z, d4.w};
+  float gw[4] = {gw4.x, gw4.y, gw4.z, gw4.w};
+#pragma unroll
+  for (int k = 0; k < 4; ++k) gw[k] += g_acc + gbg + g_dist * 0.5f * (t[k] + t[k + 1]);
+  bwd_samples4(rgb + ray * 384, d_rgb + ray * 384, lane, w, g0, gw);
+  bwd_samples4(diffuse + ray * 384, d_diffuse + ray * 384, lane, w, g1, gw);
+  bwd_samples4(specular + ray * 384, d_specular + ray * 384, lane, w, g2, gw);
+  if (g_extras) {
+    float e0[3], e1[3], e2[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      e0[c] = g_extras[ray * 12 + c];
+      e1[c] = g_extras[ray * 12 + 3 + c];
+      e2[c] = g_extras[ray * 12 + 6 + c];
+    }
+    const float er = g_extras[ray * 12 + 9];
+    if (normals) bwd_samples4(normals + ray * 384, nullptr, lane, w, e0, gw);
+    if (normals_pred) bwd_samples4(normals_pred + ray * 384, d_normals_pred ? d_normals_pred + ray * 384 : nullptr, lane, w, e1, gw);
+    if (tint) bwd_samples4(tint + ray * 384, d_tint ? d_tint + ray * 384 : nullptr, lane, w, e2, gw);
+    if (roughness) {
+      const float4 r4 = __ldg(reinterpret_cast<const float4*>(roughness + ray * s) + lane);
+      gw[0] += er * r4.x; gw[1] += er * r4.y; gw[2] += er * r4.z; gw[3] += er * r4.w;
+      if (d_roughness) *(reinterpret_cast<float4*>(d_roughness + ray * s) + lane) = make_float4(w[0] * er, w[1] * er, w[2] * er, w[3] * er);
+    }
+  } else {
+    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (d_normals_pred) for (int j = 0; j < 3; ++j) *(reinterpret_cast<float4*>(d_normals_pred + ray * 384) + 3 * lane + j) = z;
+    if (d_tint) for (int j = 0; j < 3; ++j) *(reinterpret_cast<float4*>(d_tint + ray * 384) + 3 * lane + j) = z;
+    if (d_roughness) *(reinterpret_cast<float4*>(d_roughness + ray * s) + lane) = z;
+  }
+  // w_i = (1-e^{-dd_i}) T_i,  T_i = exp(-sum_{j<i} dd_j);  dL/ddd_i = gw_i T_i e^{-dd_i} - sum_{j>i} gw_j w_j
+  float delta[4], incl_dd[4], incl_p[4];
+  float run_dd = 0.f, run_p = 0.f;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    delta[k] = (t[k + 1] - t[k]) * dnorm;
+    run_dd += dens[k] * delta[k];
+    run_p += gw[k] * w[k];
+    incl_dd[k] = run_dd;
+    incl_p[k] = run_p;
+  }
+  const float scan_dd = warp_scan_incl(run_dd, lane), scan_p = warp_scan_incl(run_p, lane);
+  const float off_dd = scan_dd - run_dd, off_p = scan_p - run_p;
+  const float total = __shfl_sync(RN_FULL, scan_p, 31);
+  float o[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+    o[k] = (gw[k] * expf(-(off_dd + incl_dd[k])) - (total - (off_p + incl_p[k]))) * delta[k];
+  *(reinterpret_cast<float4*>(d_density + ray * s) + lane) = make_float4(o[0], o[1], o[2], o[3]);
+}
+
 __global__ void __launch_bounds__(kWarps * 32)
 composite_bwd_kernel(const float* __restrict__ density, const float* __restrict__ tdist, const float* __restrict__ dirs,
                      const float* __restrict__ rgb, const float* __restrict__ diffuse, const float* __restrict__ specular,
@@ -693,6 +803,13 @@ extern "C" int rn_composite_bwd(const float* density, const float* tdist, const 
                                 float* d_tint, void* stream) {
   if (n_rays < 0 || s < 1) return rn_set_error(RN_ERR_ARG, "rn_composite_bwd: bad sizes");
   if (n_rays == 0) return RN_OK;
+  if (s == 128) {
+    composite_bwd128_kernel<<<blocks_for(n_rays), kWarps * 32, 0, (cudaStream_t)stream>>>(
+        density, tdist, dirs, rgb, diffuse, specular, normals, normals_pred, roughness, tint, weights, comp, g_weights, g_comp,
+        g_extras, n_rays, bg, d_density, d_rgb, d_diffuse, d_specular, d_normals_pred, d_roughness, d_tint);
+    RN_CUDA_CHECK_LAUNCH();
+    return RN_OK;
+  }
   size_t smem = (size_t)kWarps * 3 * (s + 2) * sizeof(float);
   if (int rc = ensure_smem(composite_bwd_kernel, smem)) return rc;
   composite_bwd_kernel<<<blocks_for(n_rays), kWarps * 32, smem, (cudaStream_t)stream>>>(
