@@ -114,6 +114,120 @@ resample_kernel(const float* __restrict__ sdist_in, const float* __restrict__ w_
   }
 }
 
+// ---- 128 -> 128 fast path of the resampler: lane l owns input bins 4l..4l+3 and output samples 4l..4l+3 ------------
+// Same arithmetic as resample_kernel (no-FMA interpolation, running-max monotone CDF, idx = #{cw <= u} - 1); the
+// prefix sums are 3 local adds + one warp scan instead of four 32-wide scans, loads / stores are vectorised or
+// staged, and the four binary searches of a lane run interleaved.
+__global__ void __launch_bounds__(kWarps * 32)
+resample128_kernel(const float* __restrict__ sdist_in, const float* __restrict__ w_in, const float* __restrict__ u,
+                   const float* __restrict__ near_, const float* __restrict__ far_, int64_t n_rays, float padding,
+                   float anneal, float dom_lo, float dom_hi, float* __restrict__ sdist_out, float* __restrict__ tdist_out,
+                   float* __restrict__ cw_out, int32_t* __restrict__ idx_out) {
+  constexpr int s = 128;
+  __shared__ float sm_t[kWarps][s + 4];
+  __shared__ float sm_cw[kWarps][s + 4];
+  __shared__ float sm_c[kWarps][s + 4];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t ray = (int64_t)blockIdx.x * kWarps + warp;
+  if (ray >= n_rays) return;
+  float* ts = sm_t[warp];
+  float* cw = sm_cw[warp];
+  float* cs = sm_c[warp];
+  const float4 w4 = __ldg(reinterpret_cast<const float4*>(w_in + ray * s) + lane);
+  const float4 u4 = __ldg(reinterpret_cast<const float4*>(u) + lane);
+  const float* tin = sdist_in + ray * (s + 1);
+  for (int i = lane; i <= s; i += 32) ts[i] = __ldg(tin + i);
+  __syncwarp();
+  float t[5];
+#pragma unroll
+  for (int k = 0; k < 5; ++k) t[k] = ts[4 * lane + k];
+  const float wv[4] = {w4.x, w4.y, w4.z, w4.w};
+  // logits (models.py:200-203), softmax (stepfun.py:160)
+  float lg[4], m = -INFINITY;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    lg[k] = (t[k + 1] > t[k]) ? __fmul_rn(anneal, logf(__fadd_rn(wv[k], padding))) : -INFINITY;
+    m = fmaxf(m, lg[k]);
+  }
+  m = warp_max(m);
+  float e[4], sum = 0.f;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    e[k] = expf(__fsub_rn(lg[k], m));
+    sum += e[k];
+  }
+  sum = warp_sum(sum);
+  // CDF: cw[j] = min(1, sum_{i<j} p_i) with a running max (monotone to the last ulp), cw[0] = 0, cw[128] = 1
+  float c[4], run = 0.f;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    run += __fdiv_rn(e[k], sum);
+    c[k] = run;
+  }
+  const float scan = warp_scan_incl(run, lane);
+  const float off = scan - run;
+  float prev_max = warp_scan_max(off + c[3], lane);        // inclusive running max of the lanes' last values
+  prev_max = __shfl_up_sync(RN_FULL, prev_max, 1);
+  if (lane == 0) prev_max = 0.f;
+  float cm = prev_max;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    cm = fmaxf(cm, off + c[k]);
+    const int j = 4 * lane + k + 1;          // cw index
+    if (j < s) cw[j] = fminf(cm, 1.f);
+  }
+  if (lane == 0) cw[0] = 0.f;
+  if (lane == 31) cw[s] = 1.f;
+  __syncwarp();
+  if (cw_out) {
+    float* o = cw_out + ray * (s + 1);
+    for (int i = lane; i <= s; i += 32) o[i] = cw[i];
+  }
+  // inverse CDF at u[4l..4l+3]: four interleaved binary searches over cw[0..128]
+  const float uj[4] = {u4.x, u4.y, u4.z, u4.w};
+  int lo[4] = {0, 0, 0, 0}, hi[4] = {s + 1, s + 1, s + 1, s + 1};
+#pragma unroll
+  for (int it = 0; it < 8; ++it) {       // ceil(log2(130)) = 8 halvings of [0, 129)
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (lo[k] < hi[k]) {
+        const int mid = (lo[k] + hi[k]) >> 1;
+        if (cw[mid] <= uj[k]) lo[k] = mid + 1; else hi[k] = mid;
+      }
+    }
+  }
+  float cv[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int idx = lo[k] - 1;
+    const int i0 = min(max(idx, 0), s), i1 = min(max(idx + 1, 0), s);
+    const float x0 = cw[i0], x1 = cw[i1], f0 = ts[i0], f1 = ts[i1];
+    const float offk = nan_to_zero_clip01(__fdiv_rn(__fsub_rn(uj[k], x0), __fsub_rn(x1, x0)));
+    cv[k] = __fadd_rn(f0, __fmul_rn(offk, __fsub_rn(f1, f0)));
+    if (idx_out) idx_out[ray * s + 4 * lane + k] = idx;
+  }
+  *(reinterpret_cast<float4*>(cs) + lane) = make_float4(cv[0], cv[1], cv[2], cv[3]);
+  __syncwarp();
+  // midpoints + reflected end fenceposts (stepfun.py:246-258), then t = s*far + (1-s)*near
+  const float nr = near_[ray], fr = far_[ray];
+  float* so = sdist_out + ray * (s + 1);
+  float* to = tdist_out ? tdist_out + ray * (s + 1) : nullptr;
+  for (int j = lane; j <= s; j += 32) {
+    float v;
+    if (j == 0) {
+      const float mid0 = __fdiv_rn(__fadd_rn(cs[1], cs[0]), 2.f);
+      v = fmaxf(dom_lo, __fsub_rn(__fmul_rn(2.f, cs[0]), mid0));
+    } else if (j == s) {
+      const float midl = __fdiv_rn(__fadd_rn(cs[s - 1], cs[s - 2]), 2.f);
+      v = fminf(dom_hi, __fsub_rn(__fmul_rn(2.f, cs[s - 1]), midl));
+    } else {
+      v = __fdiv_rn(__fadd_rn(cs[j], cs[j - 1]), 2.f);
+    }
+    so[j] = v;
+    if (to) to[j] = __fadd_rn(__fmul_rn(v, fr), __fmul_rn(__fsub_rn(1.f, v), nr));
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // compositing forward: render.py:132-149 + render.py:152-254
 // ---------------------------------------------------------------------------------------------
@@ -762,6 +876,12 @@ extern "C" int rn_resample(const float* sdist_in, const float* weights_in, const
                            int32_t* idx_out, void* stream) {
   if (n_rays < 0 || s_in < 1 || s_out < 2) return rn_set_error(RN_ERR_ARG, "rn_resample: need s_in >= 1 and s_out >= 2");
   if (n_rays == 0) return RN_OK;
+  if (s_in == 128 && s_out == 128) {
+    resample128_kernel<<<blocks_for(n_rays), kWarps * 32, 0, (cudaStream_t)stream>>>(
+        sdist_in, weights_in, u, near_, far_, n_rays, padding, anneal, dom_lo, dom_hi, sdist_out, tdist_out, cw_out, idx_out);
+    RN_CUDA_CHECK_LAUNCH();
+    return RN_OK;
+  }
   size_t smem = (size_t)kWarps * (2 * (s_in + 1) + s_out) * sizeof(float);
   if (int rc = ensure_smem(resample_kernel, smem)) return rc;
   resample_kernel<<<blocks_for(n_rays), kWarps * 32, smem, (cudaStream_t)stream>>>(
