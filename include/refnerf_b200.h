@@ -95,6 +95,17 @@ RN_API int rn_encode(const float* tdist, const float* origins, const float* dirs
 /* rn_ide: ref_utils.generate_ide_fn(5) (ref_utils.py:98-161): dirs [R,3], kappa_inv [R] -> [R,72]. */
 RN_API int rn_ide(const float* dirs, const float* kappa_inv, int64_t n, float* out, void* stream);
 
+/* ---- ray generation (the caller side of the path) ----------------------------
+ * rn_pixels_to_rays: camera_utils.pixels_to_rays (camera_utils.py:502-614) for perspective cameras without lens
+ * distortion: pixel centres through pixtocams[cam] [C,3,3] and camtoworlds[cam] [C,3,4] (fp32, row-major) ->
+ * origins, directions (not normalised), viewdirs [n,3], radii [n] (mip-NeRF cone radii from the +x / +y
+ * neighbour rays), imageplane [n,2].  pixtocam_ndc != NULL additionally applies camera_utils.convert_to_ndc
+ * (camera_utils.py:31-97, near = 1) to origins / directions and takes the radii from the NDC origin offsets.
+ * cam_idx may be NULL (single camera).  Arithmetic in float64 like the reference's numpy path, results fp32. */
+RN_API int rn_pixels_to_rays(const int32_t* pix_x, const int32_t* pix_y, const int32_t* cam_idx, const float* pixtocams,
+                      const float* camtoworlds, const float* pixtocam_ndc, int64_t n, float* origins, float* directions,
+                      float* viewdirs, float* radii, float* imageplane, void* stream);
+
 /* ---- K3: the NerfMLP (models.py:533-750) ---------------------------------------------------
  * Parameter order (RN_MLP_NUM_PARAMS pointers, weights [out,in] row-major as in PyTorch):
  *   spatial_net.{0..7}.{weight,bias}, raw_density, grad_pred, raw_roughness, raw_rgb_diffuse,

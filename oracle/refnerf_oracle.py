@@ -543,3 +543,51 @@ def init_params(seed=0, dtype=torch.float32, bias_std=0.0, weight_scale=1.0):
         p[name + '.weight'] = ((torch.rand(n, k, generator=g) * 2 - 1) * bound * weight_scale).to(dtype)
         p[name + '.bias'] = (torch.randn(n, generator=g) * bias_std).to(dtype)
     return p
+
+
+# ---------------------------------------------------------------------------------------------
+# ray generation: camera_utils.convert_to_ndc (camera_utils.py:31-97) and
+# camera_utils.pixels_to_rays (camera_utils.py:502-614), perspective cameras without distortion, numpy
+# arithmetic exactly as the reference's default xnp=np path (integer pixels + 0.5 promote to float64)
+# ---------------------------------------------------------------------------------------------
+def convert_to_ndc_np(origins, directions, pixtocam, near=1.0):
+    import numpy as np
+    t = -(near + origins[..., 2]) / directions[..., 2]
+    origins = origins + t[..., None] * directions
+    dx, dy, dz = np.moveaxis(directions, -1, 0)
+    ox, oy, oz = np.moveaxis(origins, -1, 0)
+    xmult = 1. / pixtocam[0, 2]
+    ymult = 1. / pixtocam[1, 2]
+    origins_ndc = np.stack([xmult * ox / oz, ymult * oy / oz, -np.ones_like(oz)], axis=-1)
+    infinity_ndc = np.stack([xmult * dx / dz, ymult * dy / dz, np.ones_like(oz)], axis=-1)
+    return origins_ndc, infinity_ndc - origins_ndc
+
+
+def pixels_to_rays_np(pix_x_int, pix_y_int, pixtocams, camtoworlds, pixtocam_ndc=None):
+    """-> origins, directions, viewdirs [.., 3], radii [.., 1], imageplane [.., 2] (float64, as the reference returns)."""
+    import numpy as np
+
+    def pix_to_dir(x, y):
+        return np.stack([x + .5, y + .5, np.ones_like(x)], axis=-1)
+
+    stacked = np.stack([pix_to_dir(pix_x_int, pix_y_int), pix_to_dir(pix_x_int + 1, pix_y_int),
+                        pix_to_dir(pix_x_int, pix_y_int + 1)], axis=0)
+    mat_vec_mul = lambda A, b: np.matmul(A, b[..., None])[..., 0]
+    cam_dirs = mat_vec_mul(pixtocams, stacked)
+    cam_dirs = np.matmul(cam_dirs, np.diag(np.array([1., -1., -1.])))
+    imageplane = cam_dirs[0, ..., :2]
+    dirs_stacked = mat_vec_mul(camtoworlds[..., :3, :3], cam_dirs)
+    directions, dx, dy = dirs_stacked
+    origins = np.broadcast_to(camtoworlds[..., :3, -1], directions.shape)
+    viewdirs = directions / np.linalg.norm(directions, axis=-1, keepdims=True)
+    if pixtocam_ndc is None:
+        dx_norm = np.linalg.norm(dx - directions, axis=-1)
+        dy_norm = np.linalg.norm(dy - directions, axis=-1)
+    else:
+        origins_dx, _ = convert_to_ndc_np(origins, dx, pixtocam_ndc)
+        origins_dy, _ = convert_to_ndc_np(origins, dy, pixtocam_ndc)
+        origins, directions = convert_to_ndc_np(origins, directions, pixtocam_ndc)
+        dx_norm = np.linalg.norm(origins_dx - origins, axis=-1)
+        dy_norm = np.linalg.norm(origins_dy - origins, axis=-1)
+    radii = (0.5 * (dx_norm + dy_norm))[..., None] * 2 / np.sqrt(12)
+    return origins, directions, viewdirs, radii, imageplane

@@ -39,6 +39,7 @@ _SIGNATURES = {
     'rn_distortion_bwd': (c_int, [_P, _P, _P, c_int64, c_int, _P, _P]),
     'rn_encode': (c_int, [_P, _P, _P, _P, c_int64, c_int, _P, _P]),
     'rn_ide': (c_int, [_P, _P, c_int64, _P, _P]),
+    'rn_pixels_to_rays': (c_int, [_P, _P, _P, _P, _P, _P, c_int64, _P, _P, _P, _P, _P, _P]),
     'rn_mlp_param_name': (c_char_p, [c_int]),
     'rn_mlp_param_numel': (c_int64, [c_int]),
     'rn_mlp_packed_bytes': (c_size_t, [c_int]),

@@ -437,3 +437,32 @@ def gemm_bench(m, prec=_lib.PREC_BF16, impl=0, iters=20, device='cuda'):
     ms = ctypes.c_float(0)
     _lib.check(lib.rn_gemm_bench(m, prec, impl, iters, ctypes.byref(ms), _ptr(scratch), nb, _stream()))
     return ms.value
+
+
+# ------------------------------------------------------------------------------------------
+# ray generation (camera_utils.pixels_to_rays); no gradient (pixels and cameras are data)
+# ------------------------------------------------------------------------------------------
+@torch.library.custom_op(f'{NS}::pixels_to_rays', mutates_args=(), device_types='cuda')
+def pixels_to_rays(pix_x: Tensor, pix_y: Tensor, cam_idx: Tensor, pixtocams: Tensor, camtoworlds: Tensor,
+                   pixtocam_ndc: Tensor) -> List[Tensor]:
+    """pix_x, pix_y, cam_idx: int32 [n]; pixtocams [C,3,3], camtoworlds [C,3,4] fp32; pixtocam_ndc [3,3] or empty
+    -> [origins, directions, viewdirs [n,3], radii [n,1], imageplane [n,2]]"""
+    lib = _lib.load()
+    n = pix_x.numel()
+    dev = pix_x.device
+    i32 = lambda t: t.contiguous().to(torch.int32)
+    px, py, ci = i32(pix_x), i32(pix_y), i32(cam_idx)
+    p2c, c2w = _f32c(pixtocams), _f32c(camtoworlds)
+    ndc = _f32c(pixtocam_ndc) if pixtocam_ndc.numel() else pixtocam_ndc
+    f = lambda *shape: torch.empty(shape, device=dev, dtype=torch.float32)
+    o, d, v, r, ip = f(n, 3), f(n, 3), f(n, 3), f(n, 1), f(n, 2)
+    _lib.check(lib.rn_pixels_to_rays(_ptr(px), _ptr(py), _ptr(ci), _ptr(p2c), _ptr(c2w), _ptr(ndc) if ndc.numel() else None,
+                                     n, _ptr(o), _ptr(d), _ptr(v), _ptr(r), _ptr(ip), _stream()))
+    return [o, d, v, r, ip]
+
+
+@pixels_to_rays.register_fake
+def _(pix_x, pix_y, cam_idx, pixtocams, camtoworlds, pixtocam_ndc):
+    n = pix_x.numel()
+    f = lambda *shape: pixtocams.new_empty(shape)
+    return [f(n, 3), f(n, 3), f(n, 3), f(n, 1), f(n, 2)]

@@ -194,3 +194,27 @@ def test_step_losses(ops, gold):
 def test_cpu_tensors_fail_loudly(ops):
     with pytest.raises((NotImplementedError, RuntimeError)):
         ops.distortion(torch.rand(2, 5), torch.rand(2, 4))
+
+
+def test_pixels_to_rays_matches_reference_golden(golden_dir):
+    """rn_pixels_to_rays (float64 arithmetic, fp32 outputs) vs the reference camera_utils.pixels_to_rays golden
+    vectors, Blender-shaped and LLFF-NDC cameras: equal after rounding to fp32 (<= 1 ulp where the FP64 sum order
+    of the 3x3 products differs)."""
+    import os
+    from refnerf_pl_b200 import camera_utils
+    g = np.load(os.path.join(golden_dir, 'raygen.npz'))
+    for name, ndc in (('blender', False), ('llff', True)):
+        px, py, ci = (torch.tensor(g[f'{name}_{k}']).to(DEV) for k in ('px', 'py', 'cam'))
+        p2c, c2w = torch.tensor(g[f'{name}_pixtocams']).to(DEV), torch.tensor(g[f'{name}_camtoworlds']).to(DEV)
+        out = camera_utils.pixels_to_rays(px, py, p2c, c2w, pixtocam_ndc=p2c[0] if ndc else None, cam_idx=ci)
+        for k, v in zip(('origins', 'directions', 'viewdirs', 'radii', 'imageplane'), out):
+            ref = g[f'{name}_{k}'].astype(np.float32)
+            got = v.cpu().numpy()
+            assert got.shape == ref.shape, (name, k, got.shape, ref.shape)
+            # 1 fp32 ulp of the value, or of the field's scale where the NDC projection cancels towards zero
+            tol = 1.2e-7 * np.maximum(np.abs(ref), np.abs(ref).max())
+            assert (np.abs(got - ref) <= tol).all(), (name, k, float((np.abs(got - ref) / tol).max()))
+        # the reference's calling convention (per-pixel matrices) gives the same result as the camera-table form
+        out2 = camera_utils.pixels_to_rays(px, py, p2c[ci.long()], c2w[ci.long()], pixtocam_ndc=p2c[0] if ndc else None)
+        for a, b in zip(out, out2):
+            assert torch.equal(a, b)
