@@ -193,7 +193,7 @@ def time_hbm_kernels(dev, peaks):
         gbs = bytes_per_ray * n / sec / 1e9
         return {'gbs': gbs, 'frac': gbs / peaks['hbm_gbs'], 'bytes_per_ray': bytes_per_ray, 'rays': n, 'us': sec * 1e6}
 
-    n, s = 32768, 128        # 373 MB of inputs per launch (> 126 MB L2)
+    n, s = 131072, 128       # 1.5 GB of inputs per launch (>> 126 MB L2; long enough to amortise the launch path)
     t = torch.sort(rnd(n, s + 1) * 4 + 2, dim=-1).values
     dirs = rnd(n, 3) + 0.5
     far = torch.full((n, 1), 6.0, device=dev)
