@@ -119,6 +119,40 @@ def time_cpu(n_rays, steps, warmup):
     return float(np.median(ts))
 
 
+def time_torch_gpu(n_rays, dev, steps=2):
+    """The stock-PyTorch fp32 path (the oracle port, i.e. the reference's unfused ATen op sequence) on THIS GPU: the
+    "what you get without this work" line of SURVEY 8(d).  Baseline only; returns None if it cannot run."""
+    try:
+        from oracle import refnerf_oracle as O
+        from refnerf_pl_b200 import synthetic
+        rays = {k: torch.tensor(v).to(dev) for k, v in synthetic.blender_rays(n_rays, seed=0).items()}
+        gt = torch.tensor(synthetic.gt_rgb(n_rays, 0)).to(dev)
+        p = {k: v.to(dev).requires_grad_(True) for k, v in O.init_params(seed=0).items()}
+
+        def step():
+            for v in p.values():
+                v.grad = None
+            rend, hist = O.model_forward(p, rays, 1.0, True, True)
+            O.total_loss(rend, hist, rays, gt).backward()
+
+        step()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            step()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        return {'value': n_rays / (ms * 1e-3), 'unit': UNIT, 'rays': n_rays, 'ms_per_step': ms, 'dtype': 'f32',
+                'what': 'oracle port (unfused torch ops, fp32, autograd) on the same B200: fwd incl. normals pass + losses + bwd, '
+                        'no optimizer'}
+    except Exception as e:  # noqa: BLE001 -- a baseline must never take the bench down
+        return {'unavailable': f'{type(e).__name__}: {e}'[:200]}
+    finally:
+        torch.cuda.empty_cache()
+
+
 def cpu_model_name():
     try:
         for ln in open('/proc/cpuinfo'):
@@ -309,6 +343,8 @@ def run_b200(args):
     ms_e2e = timed(e2e_step, args.steps) / args.steps
     e2e_value = world * n / (ms_e2e * 1e-3)
 
+    torch_gpu = time_torch_gpu(2048, dev) if (rank == 0 and world == 1 and not args.no_cpu) else None
+
     # ---- 800x800 frame render (eval path, chunked): every rank renders a contiguous slice of the frame's rays ----
     render = None
     if not args.no_render:
@@ -425,6 +461,7 @@ def run_b200(args):
         'roofline_wgrad': roofline_wgrad,
         'hbm_kernels': hbm_kernels,
         'cpu_baseline': cpu,
+        'torch_gpu_baseline': torch_gpu,
         'parity_mode': parity,
         'mlp_tflops_step': step_tflops,
         'mlp_frac_of_bf16_peak': step_tflops / peaks['bf16_sustained'],
