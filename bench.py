@@ -432,7 +432,7 @@ def run_b200(args):
     roofline_wgrad = {'bound': 'hbm', 'kernel': 'wgrad_tc', 'achieved': wg_gbs, 'peak': peaks['hbm_gbs'], 'unit': 'GB/s',
                       'frac': wg_gbs / peaks['hbm_gbs'], 'traffic': load_traffic().get('wgrad_tc'),
                       'kernel_share_of_step': wg['ms'] / ms_total}
-    hbm_kernels = time_hbm_kernels(dev, peaks)
+    hbm_kernels = time_hbm_kernels(dev, peaks) if not args.no_hbm else None
 
     # ---- CPU baseline on this box's host cores (oracle port, bounded sample) -----------------------
     cpu = None
@@ -485,6 +485,7 @@ def main():
     ap.add_argument('--no-render', action='store_true')
     ap.add_argument('--no-cpu', action='store_true')
     ap.add_argument('--no-parity', action='store_true', help='skip the bf16x3 (parity arithmetic) timing')
+    ap.add_argument('--no-hbm', action='store_true', help='skip the stand-alone GB/s timing of the warp-per-ray kernels')
     args = ap.parse_args()
     if args.impl == 'reference':
         run_reference(args)
