@@ -279,7 +279,7 @@ def default_chunk_rows(n_rows, training=False):
     rows anyway, and the wgrad kernels amortise their fp32 reduction over the rows of one launch); eval only needs
     enough rows to fill the machine."""
     rows = (n_rows + 127) // 128 * 128
-    return max(128, min(rows, 2097152 if training else 262144))
+    return max(128, min(rows, 2097152 if training else 1048576))
 
 
 # Training keeps every activation of the forward for the backward (no recompute) while that fits comfortably in
