@@ -446,7 +446,8 @@ def run_b200(args):
     line = {
         'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
         'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-        'dtype': {'bf16': 'bf16', 'bf16x3': 'bf16x3 (split-bf16, fp32 accumulate)', 'fp32': 'f32'}[args.precision],
+        'dtype': {'bf16': 'bf16', 'bf16x3': 'bf16x3 (split-bf16, fp32 accumulate)', 'fp32': 'f32',
+                  'fp16': 'f16 (fp16 weights/activations, bf16 gradient operands, fp32 accumulate)'}[args.precision],
         'data': 'synthetic',
         'config': {'workload': f'configs/blender_refnerf.gin single training step, {n}-ray batch per GPU, NerfMLP at '
                                'both levels (single_mlp), fwd (incl. density-gradient normals) + losses + bwd + Adam',
@@ -478,7 +479,7 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--precision', default=os.environ.get('REFNERF_B200_PRECISION', 'bf16'),
-                    choices=['bf16', 'bf16x3', 'fp32'])
+                    choices=['bf16', 'fp16', 'bf16x3', 'fp32'])
     ap.add_argument('--rays', type=int, default=16384)
     ap.add_argument('--cpu-rays', type=int, default=512)
     ap.add_argument('--render-chunk', type=int, default=65536)

@@ -10,8 +10,8 @@ from ctypes import POINTER, Structure, c_char_p, c_double, c_float, c_int, c_int
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, 'librefnerf_b200.so')
 
-PREC_FP32, PREC_BF16, PREC_BF16X3 = 0, 1, 2
-PREC_BY_NAME = {'fp32': PREC_FP32, 'bf16': PREC_BF16, 'bf16x3': PREC_BF16X3}
+PREC_FP32, PREC_BF16, PREC_BF16X3, PREC_FP16 = 0, 1, 2, 3
+PREC_BY_NAME = {'fp32': PREC_FP32, 'bf16': PREC_BF16, 'bf16x3': PREC_BF16X3, 'fp16': PREC_FP16}
 NUM_PARAMS = 46
 
 

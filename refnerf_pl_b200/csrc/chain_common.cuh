@@ -96,11 +96,13 @@ __device__ __forceinline__ void umma2_commit(uint64_t* bar) {
                "h"((uint16_t)3)
                : "memory");
 }
-__device__ __forceinline__ uint32_t make_idesc2(int n) {
+// a_f16 / b_f16: the operand is FP16 (format code 0) instead of BF16 (1); the two may differ (fp16 mode: bf16
+// gradients times fp16 weights)
+__device__ __forceinline__ uint32_t make_idesc2(int n, int a_f16 = 0, int b_f16 = 0) {
   uint32_t d = 0;
   d |= 1u << 4;                       // c_format = F32
-  d |= 1u << 7;                       // a_format = BF16
-  d |= 1u << 10;                      // b_format = BF16
+  d |= (a_f16 ? 0u : 1u) << 7;        // a_format
+  d |= (b_f16 ? 0u : 1u) << 10;       // b_format
   d |= (uint32_t)(n >> 3) << 17;
   d |= (uint32_t)(256 >> 4) << 24;    // M = 256 across the pair
   return d;
@@ -116,6 +118,20 @@ __device__ __forceinline__ uint32_t pack_relu_bf16x2(float lo, float hi) {
   uint32_t r;
   asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
   return r;
+}
+__device__ __forceinline__ uint32_t pack_relu_f16x2(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.relu.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+// activation-format packers of the chain epilogues: F16 = 0 bf16, 1 fp16
+template <int F16>
+__device__ __forceinline__ uint32_t pack_relu_act(float lo, float hi) {
+  return F16 ? pack_relu_f16x2(lo, hi) : pack_relu_bf16x2(lo, hi);
+}
+template <int F16>
+__device__ __forceinline__ uint32_t pack_act(float lo, float hi) {
+  return F16 ? pack_f16x2(lo, hi) : pack_bf16x2(lo, hi);
 }
 __device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t* r) { tmem_ld32(taddr, r); }
 
@@ -137,6 +153,7 @@ __device__ __forceinline__ uint32_t apply_relu_bits(uint32_t bits, int i, uint32
 
 // epilogue for 16 consecutive columns of one row of a global (non-hidden) op; v holds the fp32 accumulators
 // (bias already added by the caller)
+template <int F16 = 0>
 __device__ __forceinline__ void epi_global16(const GemmEpilogue& e, size_t row, int col, float* v) {
   if (e.relu) {
 #pragma unroll
@@ -145,7 +162,7 @@ __device__ __forceinline__ void epi_global16(const GemmEpilogue& e, size_t row, 
   if (e.out.hi && col < e.out_cols) {
     uint32_t h[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) h[i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);
+    for (int i = 0; i < 8; ++i) h[i] = pack_act<F16>(v[2 * i], v[2 * i + 1]);
     stg256(reinterpret_cast<uint16_t*>(e.out.hi) + row * e.out.ld + col, h);
   }
   if (e.f32 && col + 16 > e.f32_col0 && col < e.f32_col0 + e.f32_cols) {
@@ -191,6 +208,8 @@ struct PairParams {
   int num_ops;
   int in_kb;
   int in2_sync_op;   // -1, or: the second input is a save of this launch; the op before its reader orders store -> load
+  int a_f16, b_f16;  // operand formats of the MMAs (0 bf16, 1 fp16); the activation tile / outputs use a's
+  float seed_scale;  // seed ops: vec * seed_scale
   int64_t m;
   long long* trace;   // debug timeline (RN_CHAIN_TRACE=<launches>): written by CTA 0 only
   PairOp op[kMaxOps];

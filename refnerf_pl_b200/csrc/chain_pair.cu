@@ -47,7 +47,8 @@ struct PairMaps {
 };
 
 // MODE 0: forward chain (hidden ops: bias + ReLU); MODE 1: backward / dgrad chain (hidden ops: ReLU bit mask)
-template <int MODE>
+// F16: format of the activation tile and of the activation-format outputs (0 bf16, 1 fp16)
+template <int MODE, int F16>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
 chain_pair_kernel(const __grid_constant__ PairMaps maps, const __grid_constant__ PairParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -168,7 +169,7 @@ chain_pair_kernel(const __grid_constant__ PairMaps maps, const __grid_constant__
           seed_pending = true;
           continue;
         }
-        const uint32_t idesc = make_idesc2(L.n);
+        const uint32_t idesc = make_idesc2(L.n, p.a_f16, p.b_f16);
         const uint32_t free_parity = (nreal & 1u) ^ 1u;   // epilogue of the previous GEMM op on this tile done
         ++nreal;
         // --- K blocks from the resident activation tiles: tile 0 then tile 1 over the same weight stages
@@ -300,8 +301,8 @@ chain_pair_kernel(const __grid_constant__ PairMaps maps, const __grid_constant__
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
                   const float4 b = lds128f(baddr + 16u * i);
-                  packed[2 * i] = pack_relu_bf16x2(__uint_as_float(cur[4 * i]) + b.x, __uint_as_float(cur[4 * i + 1]) + b.y);
-                  packed[2 * i + 1] = pack_relu_bf16x2(__uint_as_float(cur[4 * i + 2]) + b.z, __uint_as_float(cur[4 * i + 3]) + b.w);
+                  packed[2 * i] = pack_relu_act<F16>(__uint_as_float(cur[4 * i]) + b.x, __uint_as_float(cur[4 * i + 1]) + b.y);
+                  packed[2 * i + 1] = pack_relu_act<F16>(__uint_as_float(cur[4 * i + 2]) + b.z, __uint_as_float(cur[4 * i + 3]) + b.w);
                 }
                 if (L.save_bits) bits_out[g] = relu_bits_of(packed);
               } else if (seed) {
@@ -310,13 +311,13 @@ chain_pair_kernel(const __grid_constant__ PairMaps maps, const __grid_constant__
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
                   const float4 b = lds128f(baddr + 16u * i);
-                  packed[2 * i] = apply_relu_bits(bits_arr[g], 2 * i, pack_bf16x2(b.x, b.y));
-                  packed[2 * i + 1] = apply_relu_bits(bits_arr[g], 2 * i + 1, pack_bf16x2(b.z, b.w));
+                  packed[2 * i] = apply_relu_bits(bits_arr[g], 2 * i, pack_act<F16>(b.x * p.seed_scale, b.y * p.seed_scale));
+                  packed[2 * i + 1] = apply_relu_bits(bits_arr[g], 2 * i + 1, pack_act<F16>(b.z * p.seed_scale, b.w * p.seed_scale));
                 }
               } else {
 #pragma unroll
                 for (int i = 0; i < 16; ++i)
-                  packed[i] = apply_relu_bits(bits_arr[g], i, pack_bf16x2(__uint_as_float(cur[2 * i]), __uint_as_float(cur[2 * i + 1])));
+                  packed[i] = apply_relu_bits(bits_arr[g], i, pack_act<F16>(__uint_as_float(cur[2 * i]), __uint_as_float(cur[2 * i + 1])));
               }
               const int c = 2 * h + (g >> 1);   // activation K block
               const uint32_t blk = act_row + (uint32_t)(c * kBlkBytes);
@@ -382,7 +383,7 @@ chain_pair_kernel(const __grid_constant__ PairMaps maps, const __grid_constant__
                         v[4 * i] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w;
                       }
                     }
-                    epi_global16(ge, (size_t)row, c0 + 16 * hh, v);
+                    epi_global16<F16>(ge, (size_t)row, c0 + 16 * hh, v);
                   }
                 }
               }
@@ -406,8 +407,12 @@ chain_pair_kernel(const __grid_constant__ PairMaps maps, const __grid_constant__
 }  // namespace
 
 int launch_chain(const ChainArgs& a, cudaStream_t st) {
-  if (a.impl == 1) return launch_chain_ts(a, st);
+  if (a.impl == 1) {
+    if (a.act_f16 || a.w_f16) return rn_set_error(RN_ERR_UNSUPPORTED, "chain_ts: bf16 operands only");
+    return launch_chain_ts(a, st);
+  }
   if (a.m <= 0) return RN_OK;
+  if (a.act_f16 != a.w_f16) return rn_set_error(RN_ERR_UNSUPPORTED, "chain: activations and weights must share one 16-bit format");
   if (a.num_ops < 1 || a.num_ops > kMaxOps) return rn_set_error(RN_ERR_ARG, "chain: 1..12 ops");
   if (a.in.hi && (a.in_cols % 64 || a.in_cols < 64 || a.in_cols > 256)) return rn_set_error(RN_ERR_ARG, "chain: input tile must be 64..256 columns");
   if (a.m + 512 > 0x7fffffffLL) return rn_set_error(RN_ERR_ARG, "chain: too many rows for one launch");
@@ -419,6 +424,9 @@ int launch_chain(const ChainArgs& a, cudaStream_t st) {
   if ((rc = tc::make_map(&maps.in, a.in.hi, a.m, a.in_valid, a.in.ld, kBM))) return rc;
   if ((rc = tc::make_map(&maps.in2, a.in2.hi, a.m, a.in2_valid, a.in2.ld, kBM))) return rc;
   p.in2_sync_op = -1;
+  p.a_f16 = a.act_f16;
+  p.b_f16 = a.w_f16;
+  p.seed_scale = a.seed_scale;
   p.num_ops = a.num_ops;
   p.in_kb = a.in.hi ? a.in_cols / kBK : 0;
   p.m = a.m;
@@ -471,8 +479,10 @@ int launch_chain(const ChainArgs& a, cudaStream_t st) {
   p.gepi[1] = a.gepi[1];
   static bool smem_set = false;
   if (!smem_set) {
-    if ((rc = tc::set_smem(chain_pair_kernel<0>, kSmemTotal))) return rc;
-    if ((rc = tc::set_smem(chain_pair_kernel<1>, kSmemTotal))) return rc;
+    if ((rc = tc::set_smem(chain_pair_kernel<0, 0>, kSmemTotal))) return rc;
+    if ((rc = tc::set_smem(chain_pair_kernel<1, 0>, kSmemTotal))) return rc;
+    if ((rc = tc::set_smem(chain_pair_kernel<0, 1>, kSmemTotal))) return rc;
+    if ((rc = tc::set_smem(chain_pair_kernel<1, 1>, kSmemTotal))) return rc;
     smem_set = true;
   }
   const int64_t supers = (a.m + 511) / 512;
@@ -488,10 +498,14 @@ int launch_chain(const ChainArgs& a, cudaStream_t st) {
     p.trace = trace_buf;
   }
   rn_prof_begin(RN_PROF_CHAIN_TC, st, a.algo_flops);
-  if (mode == 0)
-    chain_pair_kernel<0><<<grid, 384, kSmemTotal, st>>>(maps, p);
+  if (mode == 0 && !a.act_f16)
+    chain_pair_kernel<0, 0><<<grid, 384, kSmemTotal, st>>>(maps, p);
+  else if (mode == 0)
+    chain_pair_kernel<0, 1><<<grid, 384, kSmemTotal, st>>>(maps, p);
+  else if (!a.act_f16)
+    chain_pair_kernel<1, 0><<<grid, 384, kSmemTotal, st>>>(maps, p);
   else
-    chain_pair_kernel<1><<<grid, 384, kSmemTotal, st>>>(maps, p);
+    chain_pair_kernel<1, 1><<<grid, 384, kSmemTotal, st>>>(maps, p);
   rn_prof_end(RN_PROF_CHAIN_TC, st);
   RN_CUDA_CHECK_LAUNCH();
   if (p.trace) {

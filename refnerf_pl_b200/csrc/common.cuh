@@ -1,6 +1,7 @@
 // Shared device helpers for the refnerf_pl_b200 CUDA kernels (sm_100a).
 #pragma once
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -29,6 +30,8 @@ void rn_prof_end(int cls, cudaStream_t st);
 //   RN_PREC_FP32   : hi = float*            (exact-parity SIMT path)
 //   RN_PREC_BF16   : hi = bf16*             (throughput tensor path)
 //   RN_PREC_BF16X3 : hi, lo = bf16*         (split-bf16 tensor path: x ~= hi + lo, 16-bit mantissa)
+//   RN_PREC_FP16   : hi = fp16*             (weights / activations of the fp16 mode; its gradient buffers are bf16
+//                                            and are written / read with PREC = RN_PREC_BF16)
 // ------------------------------------------------------------------------------------------
 struct ActBuf {
   void* hi;
@@ -48,6 +51,17 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
+// two floats -> packed fp16x2 (saturating: a finite activation never becomes inf)
+__device__ __forceinline__ uint32_t pack_f16x2(float a, float b) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+  return r;
+}
+__device__ __forceinline__ float2 unpack_f16x2(uint32_t v) {
+  return __half22float2(*reinterpret_cast<const __half2*>(&v));
+}
+__device__ __forceinline__ uint16_t float_to_f16_bits(float x) { return (uint16_t)(pack_f16x2(x, 0.f) & 0xffffu); }
+
 // pack two floats into hi (and lo residual) bf16 pairs
 __device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t& lo) {
   hi = pack_bf16x2(a, b);
@@ -62,6 +76,11 @@ __device__ __forceinline__ void act_store8(const ActBuf& b, size_t row, int col,
     float4* p = reinterpret_cast<float4*>(reinterpret_cast<float*>(b.hi) + row * b.ld + col);
     p[0] = make_float4(v[0], v[1], v[2], v[3]);
     p[1] = make_float4(v[4], v[5], v[6], v[7]);
+  } else if (PREC == RN_PREC_FP16) {
+    uint32_t h[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) h[i] = pack_f16x2(v[2 * i], v[2 * i + 1]);
+    *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(b.hi) + row * b.ld + col) = make_uint4(h[0], h[1], h[2], h[3]);
   } else {
     uint32_t h[4], l[4];
 #pragma unroll
@@ -79,6 +98,15 @@ __device__ __forceinline__ void act_load8(const ActBuf& b, size_t row, int col, 
     const float4* p = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(b.hi) + row * b.ld + col);
     float4 a = p[0], c = p[1];
     v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = c.x; v[5] = c.y; v[6] = c.z; v[7] = c.w;
+  } else if (PREC == RN_PREC_FP16) {
+    uint4 h = *reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(b.hi) + row * b.ld + col);
+    uint32_t hh[4] = {h.x, h.y, h.z, h.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 f = unpack_f16x2(hh[i]);
+      v[2 * i] = f.x;
+      v[2 * i + 1] = f.y;
+    }
   } else {
     uint4 h = *reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(b.hi) + row * b.ld + col);
     uint32_t hh[4] = {h.x, h.y, h.z, h.w};
@@ -104,6 +132,8 @@ template <int PREC>
 __device__ __forceinline__ void act_load8_hi(const ActBuf& b, size_t row, int col, float* v) {
   if (PREC == RN_PREC_FP32) {
     act_load8<RN_PREC_FP32>(b, row, col, v);
+  } else if (PREC == RN_PREC_FP16) {
+    act_load8<RN_PREC_FP16>(b, row, col, v);
   } else {
     act_load8<RN_PREC_BF16>(b, row, col, v);
   }

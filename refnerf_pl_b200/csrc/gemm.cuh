@@ -50,6 +50,8 @@ struct WgradArgs {
   int out_ld = 0;
   int all_slabs = 0;          // bf16 tcgen05 only: cover every 128-wide slab of dY (n_real <= 256) in one launch
   float* bias_out = nullptr;  // with all_slabs: also accumulate the bias gradient (column sums of dY) here
+  int x_f16 = 0, dy_f16 = 0;  // with all_slabs: the operands are fp16 instead of bf16 (both or neither: the MMA
+                              // rejects mixed a/b formats with an illegal-instruction fault)
   double algo_flops = 0.0;
 };
 
@@ -81,6 +83,9 @@ struct ChainArgs {
   ActBuf in2 = {nullptr, nullptr, 0};   // optional second input tensor [m, 64*k] (may be a save_hi buffer of an earlier op
   int in2_cols = 0, in2_valid = 0;      // of the same launch: the kernel orders the TMA store before the TMA load)
   int impl = 0;              // 0: chain_pair.cu (SS operands, two row tiles), 1: chain_ts.cu (A operand in TMEM)
+  int act_f16 = 0;           // chain_pair.cu: inputs, activation tile and activation-format outputs are fp16 (else bf16)
+  int w_f16 = 0;             // chain_pair.cu: weights are fp16 (else bf16); must equal act_f16 (mixed a/b formats fault)
+  float seed_scale = 1.f;    // chain_pair.cu: factor applied to the vector of a seed op
   int num_ops = 0;
   ChainOpArgs op[12];
   GemmEpilogue gepi[2];

@@ -371,7 +371,7 @@ wgrad_tc_kernel(const __grid_constant__ WgMaps maps, int64_t m, int64_t rows_per
 template <int NSLAB>
 __global__ void __launch_bounds__(256, 1)
 wgrad2_tc_kernel(const __grid_constant__ WgMaps maps, int64_t m, int64_t rows_per_cta, int n_real, int kx, int k_real,
-                 int stages, float* __restrict__ out, int out_ld, float* __restrict__ bias_out) {
+                 int stages, float* __restrict__ out, int out_ld, float* __restrict__ bias_out, int f16) {
   constexpr int kRowBlk = 64;
   constexpr int kBoxBytes = kRowBlk * 128;
   constexpr int kDyBytes = 2 * NSLAB * kBoxBytes;
@@ -425,7 +425,7 @@ wgrad2_tc_kernel(const __grid_constant__ WgMaps maps, int64_t m, int64_t rows_pe
         if (++stage == stages) { stage = 0; phase ^= 1; }
       }
     } else if (warp == 1) {
-      const uint32_t idesc = make_idesc(kx, 1, 1);
+      const uint32_t idesc = make_idesc(kx, 1, 1, f16, f16);   // A = dY^T, B = X: both bf16 or both fp16
       int stage = 0;
       uint32_t phase = 0;
       for (int b = 0; b < nblk; ++b) {
@@ -467,8 +467,14 @@ wgrad2_tc_kernel(const __grid_constant__ WgMaps maps, int64_t m, int64_t rows_pe
 #pragma unroll 8
             for (int r = 0; r < kRowBlk; ++r) {
               const uint32_t v = *reinterpret_cast<const uint32_t*>(base + r * 128 + ((((fi >> 3) ^ (r & 7))) << 4));
-              s0 += __uint_as_float(v << 16);
-              s1 += __uint_as_float(v & 0xffff0000u);
+              if (f16) {
+                const float2 f2 = unpack_f16x2(v);
+                s0 += f2.x;
+                s1 += f2.y;
+              } else {
+                s0 += __uint_as_float(v << 16);
+                s1 += __uint_as_float(v & 0xffff0000u);
+              }
             }
           }
           __syncwarp();
@@ -538,6 +544,7 @@ int launch_gemm_tc(const GemmArgs& g, cudaStream_t st) {
 }
 
 int launch_wgrad2_tc(const WgradArgs& g, cudaStream_t st) {
+  if (g.x_f16 != g.dy_f16) return rn_set_error(RN_ERR_UNSUPPORTED, "wgrad2: dY and X must share one 16-bit format");
   WgMaps maps;
   int rc;
   if ((rc = make_map(&maps.dy_hi, g.dy.hi, g.m, g.dy_valid, g.dy.ld, 64))) return rc;
@@ -562,9 +569,9 @@ int launch_wgrad2_tc(const WgradArgs& g, cudaStream_t st) {
   }
   rn_prof_begin(RN_PROF_WGRAD_TC, st, g.algo_flops);
   if (nslab == 2)
-    wgrad2_tc_kernel<2><<<grid, 256, smem, st>>>(maps, g.m, rows_per, g.n_real, g.kx, g.k_real, stages, g.out, g.out_ld, g.bias_out);
+    wgrad2_tc_kernel<2><<<grid, 256, smem, st>>>(maps, g.m, rows_per, g.n_real, g.kx, g.k_real, stages, g.out, g.out_ld, g.bias_out, (g.x_f16 && g.dy_f16) ? 1 : 0);
   else
-    wgrad2_tc_kernel<1><<<grid, 256, smem, st>>>(maps, g.m, rows_per, g.n_real, g.kx, g.k_real, stages, g.out, g.out_ld, g.bias_out);
+    wgrad2_tc_kernel<1><<<grid, 256, smem, st>>>(maps, g.m, rows_per, g.n_real, g.kx, g.k_real, stages, g.out, g.out_ld, g.bias_out, (g.x_f16 && g.dy_f16) ? 1 : 0);
   rn_prof_end(RN_PROF_WGRAD_TC, st);
   RN_CUDA_CHECK_LAUNCH();
   return RN_OK;
@@ -572,9 +579,10 @@ int launch_wgrad2_tc(const WgradArgs& g, cudaStream_t st) {
 
 int launch_wgrad_tc(const WgradArgs& g, cudaStream_t st) {
   if (g.m <= 0) return RN_OK;
-  if (g.prec != RN_PREC_BF16 && g.prec != RN_PREC_BF16X3) return rn_set_error(RN_ERR_ARG, "wgrad_tc: bf16 modes only");
+  if (g.prec == RN_PREC_FP16 && !g.all_slabs) return rn_set_error(RN_ERR_UNSUPPORTED, "wgrad_tc: the fp16 mode needs all_slabs");
+  if (g.prec != RN_PREC_BF16 && g.prec != RN_PREC_BF16X3 && g.prec != RN_PREC_FP16) return rn_set_error(RN_ERR_ARG, "wgrad_tc: bf16 modes only");
   if (g.all_slabs) {
-    if (g.prec != RN_PREC_BF16 || g.n0 != 0 || g.n_real > 256) return rn_set_error(RN_ERR_ARG, "wgrad_tc: all_slabs needs bf16, n0 = 0, n_real <= 256");
+    if ((g.prec != RN_PREC_BF16 && g.prec != RN_PREC_FP16) || g.n0 != 0 || g.n_real > 256) return rn_set_error(RN_ERR_ARG, "wgrad_tc: all_slabs needs bf16, n0 = 0, n_real <= 256");
     return launch_wgrad2_tc(g, st);
   }
   const bool x3 = g.prec == RN_PREC_BF16X3;

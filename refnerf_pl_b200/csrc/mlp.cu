@@ -154,6 +154,7 @@ struct Workspace {
   ActBuf x0, v0, sp[8], vw[8], g[2], gs[8], dheads, d_bott, d_scal, d_rgb_raw;
   uint32_t *msp[8], *mvw[8];   // ReLU bits of the hidden activations (fused chains), valid when nsp / nvw == 8
   float *heads_raw, *rgb_raw, *gx0, *dv0f, *dcolor;
+  float *stage16, *scal;   // fp16 mode: f32 staging of the 16-wide chain seeds; amax / scale scalars (pointwise.cu)
   float* gW[kNumLayers];
   float* gB[kNumLayers];
   int nsp, nvw;
@@ -228,6 +229,8 @@ Workspace carve(void* base, int prec, int64_t rc, int mode, bool external = fals
     w.d_scal.hi = reinterpret_cast<uint8_t*>(w.dheads.hi) + 128 * elem_bytes(prec);
     if (w.dheads.lo) w.d_scal.lo = reinterpret_cast<uint8_t*>(w.dheads.lo) + 128 * 2;
     w.d_rgb_raw = c.act(prec, rc, 16);
+    w.stage16 = (float*)c.take((size_t)rc * 16 * 4);
+    w.scal = (float*)c.take(256);
     for (int l = 0; l < kNumLayers; ++l) {
       LayerDef d = layer_def(l);
       w.gW[l] = (float*)c.take((size_t)d.n_pad * d.k_tot() * 4);
@@ -277,7 +280,8 @@ struct Ctx {
   cudaStream_t st;
   MlpScalars sc;
   int impl;
-  bool chain = false;  // bf16: fused forward chains
+  bool chain = false;  // bf16 / fp16: fused chains
+  bool f16 = false;    // fp16 mode: weights, activations and (dynamically scaled) gradient tiles are fp16
   int chain_impl = 0;  // ChainArgs::impl
   bool algo = true;  // launches carry algorithmic FLOPs (false while recomputing activations in backward)
 };
@@ -349,6 +353,7 @@ int chain_layers(const Ctx& c, int l0, int lh, int64_t rows, ActBuf in, int in_c
   a.in = in;
   a.in_cols = in_cols;
   a.in_valid = in_cols;
+  a.act_f16 = a.w_f16 = c.f16;
   a.num_ops = 9;
   double flops = 0.0;
   for (int i = 0; i < 9; ++i) {
@@ -389,12 +394,19 @@ ChainOpArgs bwd_op(const Ctx& c, int l, int in_row0, int n, int kb_act, int kb_i
   return L;
 }
 
+// fp16 mode: the seed of the density-gradient chain (|raw_density weights| ~ 1/16, shrinking ~2.4x per layer at
+// init) is scaled by an exact power of two so that the fp16 gradient tiles stay in the normal range; the
+// normalisation kernel divides it out again.
+constexpr float kNormalsSeedScale = 64.f;
+
 // d raw_density / d x0 through the 8 spatial layers, fused.  SS chain: the seed gradient (raw_density weight row where
 // a8 > 0) is generated inside the kernel from the ReLU bits; TS chain: it is read from w.g[0].
 int normals_chain(const Ctx& c, Workspace& w, int64_t rows) {
   ChainArgs a;
   a.impl = c.chain_impl;
   a.m = rows;
+  a.act_f16 = a.w_f16 = c.f16;
+  a.seed_scale = c.f16 ? kNormalsSeedScale : 1.f;
   const bool gen_seed = c.chain_impl == 0;
   int n = 0;
   if (gen_seed) {
@@ -465,7 +477,7 @@ int forward_chunk(const Ctx& c, Workspace& w, int64_t row0, int64_t rows, const 
       RN_TRY(dgrad_layer(c, 0, rows, w.g[cur], 256, 256, none, 0, 0, 0, kEncPad, epi_f32(w.gx0, 128, 128, 1)));
     }
     RN_TRY(launch_ipe_grad_normals(w.gx0, 128, c.tdist, c.origins, c.dirs, c.radii, c.s, row0, rows,
-                                   o.normals + row0 * 3, c.st));
+                                   o.normals + row0 * 3, (c.chain && c.f16) ? 1.f / kNormalsSeedScale : 1.f, c.st));
   }
   // outputs of the heads are written even in the recompute pass (cheap); callers pass scratch or real outputs
   RN_TRY(launch_heads_prologue_fwd(prec, w.heads_raw, c.viewdirs, c.s, row0, rows, c.sc, w.v0, o.density + row0,
@@ -495,6 +507,7 @@ int wgrad_layer(const Ctx& c, Workspace& w, int l, int64_t rows, ActBuf dy, int 
     g.m = rows;
     g.dy = dy; g.dy_valid = dy_valid; g.n0 = 0; g.n_real = n_real_total;
     g.all_slabs = 1;
+    g.x_f16 = g.dy_f16 = c.f16;
     g.bias_out = w.gB[l];
     g.x = x1; g.x_valid = d.k1_pad; g.kx = d.k1_pad; g.k_real = d.k1_real;
     g.out = w.gW[l]; g.out_ld = d.k_tot();
@@ -535,12 +548,28 @@ int backward_chunk_chain(const Ctx& c, Workspace& w, int64_t row0, int64_t rows,
   const int prec = c.cfg->prec;
   const ActBuf none = {nullptr, nullptr, 0};
   auto off = [&](const float* p, int per) -> const float* { return p ? p + row0 * per : nullptr; };
-  RN_TRY(launch_color_bwd(prec, w.rgb_raw, w.heads_raw, rows, c.sc, off(g.rgb, 3), off(g.diffuse, 3), off(g.specular, 3),
-                          w.d_rgb_raw, w.dcolor, c.st));
+  // fp16 mode: the gradient tiles entering the two dgrad chains are scaled by a power of two chosen from their
+  // max |x| (S1: view chain, S2: spatial chain), so that the fp16 tiles of all 8 layers stay in the normal range;
+  // the scales are divided out when the packed weight gradients are unpacked.
+  const ActBuf stage = {w.stage16, nullptr, 16};
+  uint32_t* amax = reinterpret_cast<uint32_t*>(w.scal);
+  if (c.f16) {
+    cudaError_t e = cudaMemsetAsync(w.scal, 0, 256, c.st);
+    if (e != cudaSuccess) return rn_set_cuda_error(e, __FILE__, __LINE__);
+    RN_TRY(launch_color_bwd(RN_PREC_FP32, w.rgb_raw, w.heads_raw, rows, c.sc, off(g.rgb, 3), off(g.diffuse, 3),
+                            off(g.specular, 3), stage, w.dcolor, c.st));
+    RN_TRY(launch_amax_f32(w.stage16, rows * 16, amax + 0, c.st));
+    RN_TRY(launch_grad_scale(w.scal, 0, c.st));
+    RN_TRY(launch_scale_to_f16(w.stage16, 16, rows, 16, w.d_rgb_raw.hi, w.d_rgb_raw.ld, w.scal + 4, c.st));
+  } else {
+    RN_TRY(launch_color_bwd(prec, w.rgb_raw, w.heads_raw, rows, c.sc, off(g.rgb, 3), off(g.diffuse, 3), off(g.specular, 3),
+                            w.d_rgb_raw, w.dcolor, c.st));
+  }
   const bool fuse_dv0 = c.chain_impl == 0;   // SS chain: d v0 = [dY0 | dY5] * wcat^T as ONE op, dY5 re-read from its save
   {  // view net: rgb head, V7..V0
     ChainArgs a;
     a.impl = c.chain_impl;
+    a.act_f16 = a.w_f16 = c.f16;
     a.m = rows;
     a.in = w.d_rgb_raw;
     a.in_cols = 64;
@@ -592,13 +621,25 @@ int backward_chunk_chain(const Ctx& c, Workspace& w, int64_t row0, int64_t rows,
     RN_TRY(wgrad_layer(c, w, L, rows, w.gs[l], 256, 256, l == 0 ? w.v0 : w.b(l), l == 5 ? w.v0 : none));
   }
   if (!fuse_dv0) RN_TRY(launch_f32_to_act(prec, w.dv0f, 256, 0, rows, 128, w.d_bott, c.st));
-  RN_TRY(launch_heads_prologue_bwd(prec, w.heads_raw, c.viewdirs, c.s, row0, rows, c.sc, w.dv0f, w.dcolor,
-                                   off(g.density, 1), off(g.normals_pred, 3), off(g.grad_pred, 3), off(g.roughness, 1),
-                                   off(g.tint, 3), w.d_scal, c.st));
+  if (c.f16) {
+    // scalar-head gradients in true scale (f32 staging); the bottleneck gradient is already fp16 in the view chain's scale
+    RN_TRY(launch_heads_prologue_bwd(RN_PREC_FP32, w.heads_raw, c.viewdirs, c.s, row0, rows, c.sc, w.dv0f, w.dcolor,
+                                     off(g.density, 1), off(g.normals_pred, 3), off(g.grad_pred, 3), off(g.roughness, 1),
+                                     off(g.tint, 3), stage, w.scal + 5, c.st));
+    RN_TRY(launch_amax_f32(w.stage16, rows * 16, amax + 1, c.st));
+    RN_TRY(launch_amax_f16(w.d_bott.hi, w.d_bott.ld, 128, rows, amax + 2, c.st));
+    RN_TRY(launch_grad_scale(w.scal, 1, c.st));
+    RN_TRY(launch_rescale_f16(w.d_bott.hi, w.d_bott.ld, 128, rows, w.scal + 8, c.st));
+    RN_TRY(launch_scale_to_f16(w.stage16, 16, rows, 16, w.d_scal.hi, w.d_scal.ld, w.scal + 6, c.st));
+  } else {
+    RN_TRY(launch_heads_prologue_bwd(prec, w.heads_raw, c.viewdirs, c.s, row0, rows, c.sc, w.dv0f, w.dcolor,
+                                     off(g.density, 1), off(g.normals_pred, 3), off(g.grad_pred, 3), off(g.roughness, 1),
+                                     off(g.tint, 3), w.d_scal, nullptr, c.st));
+  }
   {  // spatial net: heads, S7..S1 (no gradient w.r.t. x0 is needed: sdist is detached)
     ChainArgs a;
     a.impl = c.chain_impl;
-  a.impl = c.chain_impl;
+    a.act_f16 = a.w_f16 = c.f16;
     a.m = rows;
     a.in = w.dheads;
     a.in_cols = 192;
@@ -646,7 +687,7 @@ int backward_chunk(const Ctx& c, Workspace& w, int64_t row0, int64_t rows, const
   RN_TRY(launch_f32_to_act(prec, w.dv0f, 256, 0, rows, 128, w.d_bott, c.st));
   RN_TRY(launch_heads_prologue_bwd(prec, w.heads_raw, c.viewdirs, c.s, row0, rows, c.sc, w.dv0f, w.dcolor,
                                    off(g.density, 1), off(g.normals_pred, 3), off(g.grad_pred, 3), off(g.roughness, 1),
-                                   off(g.tint, 3), w.d_scal, c.st));
+                                   off(g.tint, 3), w.d_scal, nullptr, c.st));
   // heads
   {
     LayerDef d = layer_def(kLayerH);
@@ -678,7 +719,8 @@ int backward_chunk(const Ctx& c, Workspace& w, int64_t row0, int64_t rows, const
 int make_ctx(Ctx& c, const RnMlpConfig* cfg, const void* packed, const float* tdist, const float* origins,
              const float* dirs, const float* viewdirs, const float* radii, int s, void* stream) {
   if (!cfg || !packed) return rn_set_error(RN_ERR_ARG, "rn_mlp: null config / packed weights");
-  if (cfg->prec < 0 || cfg->prec > 2) return rn_set_error(RN_ERR_ARG, "rn_mlp: bad precision");
+  if (cfg->prec < 0 || cfg->prec > 3) return rn_set_error(RN_ERR_ARG, "rn_mlp: bad precision");
+  if (cfg->prec == RN_PREC_FP16 && cfg->gemm_impl != 0) return rn_set_error(RN_ERR_UNSUPPORTED, "rn_mlp: the fp16 mode runs on the fused SS chains only (gemm_impl = 0)");
   if (cfg->chunk_rows <= 0 || cfg->chunk_rows % 128) return rn_set_error(RN_ERR_ARG, "rn_mlp: chunk_rows must be a positive multiple of 128");
   if (s < 1) return rn_set_error(RN_ERR_ARG, "rn_mlp: bad sample count");
   c.cfg = cfg;
@@ -691,7 +733,8 @@ int make_ctx(Ctx& c, const RnMlpConfig* cfg, const void* packed, const float* td
   c.sc = {cfg->srgb_mapping, cfg->srgb_normalization, cfg->density_bias, cfg->roughness_bias,
           cfg->rgb_premultiplier, cfg->rgb_bias, cfg->rgb_padding};
   c.impl = cfg->gemm_impl == 1 ? 1 : 0;
-  c.chain = cfg->prec == RN_PREC_BF16 && (cfg->gemm_impl == 0 || cfg->gemm_impl == 3);
+  c.chain = (cfg->prec == RN_PREC_BF16 || cfg->prec == RN_PREC_FP16) && (cfg->gemm_impl == 0 || cfg->gemm_impl == 3);
+  c.f16 = cfg->prec == RN_PREC_FP16;
   c.chain_impl = cfg->gemm_impl == 3 ? 1 : 0;
   return RN_OK;
 }
@@ -707,7 +750,7 @@ extern "C" const char* rn_mlp_param_name(int i) { return (i >= 0 && i < RN_MLP_N
 extern "C" int64_t rn_mlp_param_numel(int i) { return (i >= 0 && i < RN_MLP_NUM_PARAMS) ? param_numel(i) : -1; }
 
 extern "C" size_t rn_mlp_packed_bytes(int prec) {
-  if (prec < 0 || prec > 2) return 0;
+  if (prec < 0 || prec > 3) return 0;
   return packed_layout(prec).total;
 }
 
@@ -729,7 +772,7 @@ extern "C" size_t rn_mlp_saved_bytes(const RnMlpConfig* cfg, int64_t n_rows) {
 }
 
 extern "C" int rn_mlp_pack(const float* const* params, void* packed, int prec, void* stream) {
-  if (!params || !packed || prec < 0 || prec > 2) return rn_set_error(RN_ERR_ARG, "rn_mlp_pack: bad arguments");
+  if (!params || !packed || prec < 0 || prec > 3) return rn_set_error(RN_ERR_ARG, "rn_mlp_pack: bad arguments");
   cudaStream_t st = (cudaStream_t)stream;
   PackedLayout lay = packed_layout(prec);
   uint8_t* base = reinterpret_cast<uint8_t*>(packed);
@@ -764,7 +807,7 @@ extern "C" int rn_mlp_pack(const float* const* params, void* packed, int prec, v
   }
   e = cudaMemcpyAsync(base + lay.wd, params[kParamDensity], 256 * 4, cudaMemcpyDeviceToDevice, st);
   if (e != cudaSuccess) return rn_set_cuda_error(e, __FILE__, __LINE__);
-  if (prec == RN_PREC_BF16) {
+  if (prec == RN_PREC_BF16 || prec == RN_PREC_FP16) {
     // wcat[j, 0:256] = W_V0[:, j], wcat[j, 256:512] = W_V5[:, 256 + j]  (j = view-net input feature, 201 real)
     void* wc = base + lay.wcat;
     const int p0 = layer_param(kLayerV0), p5 = layer_param(kLayerV0 + 5);
@@ -822,12 +865,37 @@ extern "C" int rn_mlp_backward(const RnMlpConfig* cfg, const void* packed, const
   // grad_pred 3, roughness 1, tint 3 = 11 floats per row, packed as separate arrays)
   float* scratch = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(workspace) + scratch_off);
   cudaStream_t st = c.st;
-  for (int l = 0; l < kNumLayers; ++l) {
-    LayerDef d = layer_def(l);
-    cudaError_t e = cudaMemsetAsync(w.gW[l], 0, (size_t)d.n_pad * d.k_tot() * 4, st);
-    if (e == cudaSuccess) e = cudaMemsetAsync(w.gB[l], 0, (size_t)d.n_pad * 4, st);
-    if (e != cudaSuccess) return rn_set_cuda_error(e, __FILE__, __LINE__);
-  }
+  auto zero_packed = [&]() -> int {
+    for (int l = 0; l < kNumLayers; ++l) {
+      LayerDef d = layer_def(l);
+      cudaError_t e = cudaMemsetAsync(w.gW[l], 0, (size_t)d.n_pad * d.k_tot() * 4, st);
+      if (e == cudaSuccess) e = cudaMemsetAsync(w.gB[l], 0, (size_t)d.n_pad * 4, st);
+      if (e != cudaSuccess) return rn_set_cuda_error(e, __FILE__, __LINE__);
+    }
+    return RN_OK;
+  };
+  // packed-layout gradients -> parameter gradients (+=); fp16 mode: times 1/S1 (view net, rgb head) or 1/S2 (the rest)
+  auto unpack_packed = [&](bool scaled) -> int {
+    for (int l = 0; l < kNumLayers; ++l) {
+      LayerDef d = layer_def(l);
+      const float* sc = scaled ? (l >= kLayerV0 ? w.scal + 5 : w.scal + 7) : nullptr;
+      if (l == kLayerH) {
+        for (const HeadSeg& hs : kHeadSegs) {
+          RN_TRY(launch_unpack_add(w.gW[l], d.k_tot(), hs.row0, 0, hs.rows, 256, grads[hs.param], 256, sc, st));
+          RN_TRY(launch_unpack_add(w.gB[l], d.n_pad, 0, hs.row0, 1, hs.rows, grads[hs.param + 1], hs.rows, sc, st));
+        }
+        continue;
+      }
+      const int pi = layer_param(l);
+      const int kr = d.k1_real + d.k2_real;
+      RN_TRY(launch_unpack_add(w.gW[l], d.k_tot(), 0, 0, d.n_real, d.k1_real, grads[pi], kr, sc, st));
+      if (d.k2_pad) RN_TRY(launch_unpack_add(w.gW[l], d.k_tot(), 0, d.k1_pad, d.n_real, d.k2_real, grads[pi] + d.k1_real, kr, sc, st));
+      RN_TRY(launch_unpack_add(w.gB[l], d.n_pad, 0, 0, 1, d.n_real, grads[pi + 1], d.n_real, sc, st));
+    }
+    return RN_OK;
+  };
+  const bool per_chunk = c.f16;   // the scales are chosen per chunk, so every chunk is unpacked on its own
+  if (!per_chunk) RN_TRY(zero_packed());
   for (int64_t row0 = 0; row0 < rows_total; row0 += rc) {
     const int64_t rows = rows_total - row0 < rc ? rows_total - row0 : rc;
     RnMlpOutputs tmp;
@@ -845,28 +913,15 @@ extern "C" int rn_mlp_backward(const RnMlpConfig* cfg, const void* packed, const
       RN_TRY(forward_chunk(c, w, row0, rows, tmp, false, false));
       c.algo = true;
     }
+    if (per_chunk) RN_TRY(zero_packed());
     if (c.chain) {
       RN_TRY(backward_chunk_chain(c, w, row0, rows, *g));
     } else {
       RN_TRY(backward_chunk(c, w, row0, rows, *g));
     }
+    if (per_chunk) RN_TRY(unpack_packed(true));
   }
-  // packed-layout gradients -> parameter gradients (+=)
-  for (int l = 0; l < kNumLayers; ++l) {
-    LayerDef d = layer_def(l);
-    if (l == kLayerH) {
-      for (const HeadSeg& hs : kHeadSegs) {
-        RN_TRY(launch_unpack_add(w.gW[l], d.k_tot(), hs.row0, 0, hs.rows, 256, grads[hs.param], 256, st));
-        RN_TRY(launch_unpack_add(w.gB[l], d.n_pad, 0, hs.row0, 1, hs.rows, grads[hs.param + 1], hs.rows, st));
-      }
-      continue;
-    }
-    const int pi = layer_param(l);
-    const int kr = d.k1_real + d.k2_real;
-    RN_TRY(launch_unpack_add(w.gW[l], d.k_tot(), 0, 0, d.n_real, d.k1_real, grads[pi], kr, st));
-    if (d.k2_pad) RN_TRY(launch_unpack_add(w.gW[l], d.k_tot(), 0, d.k1_pad, d.n_real, d.k2_real, grads[pi] + d.k1_real, kr, st));
-    RN_TRY(launch_unpack_add(w.gB[l], d.n_pad, 0, 0, 1, d.n_real, grads[pi + 1], d.n_real, st));
-  }
+  if (!per_chunk) RN_TRY(unpack_packed(false));
   return RN_OK;
 }
 

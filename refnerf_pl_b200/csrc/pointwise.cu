@@ -15,6 +15,7 @@ namespace {
     case RN_PREC_FP32: { constexpr int PREC = RN_PREC_FP32; __VA_ARGS__; } break;     \
     case RN_PREC_BF16: { constexpr int PREC = RN_PREC_BF16; __VA_ARGS__; } break;     \
     case RN_PREC_BF16X3: { constexpr int PREC = RN_PREC_BF16X3; __VA_ARGS__; } break; \
+    case RN_PREC_FP16: { constexpr int PREC = RN_PREC_FP16; __VA_ARGS__; } break;     \
     default: return rn_set_error(RN_ERR_ARG, "bad precision");    \
   }
 
@@ -130,7 +131,7 @@ __global__ void __launch_bounds__(256)
 ipe_grad_normals_kernel(const float* __restrict__ gx0, int ld, const float* __restrict__ tdist,
                         const float* __restrict__ origins, const float* __restrict__ dirs,
                         const float* __restrict__ radii, int s, int64_t row0, int64_t rows,
-                        float* __restrict__ normals_out) {
+                        float* __restrict__ normals_out, float gscale) {
   __shared__ float tile[kEncRows * 97];
   const int tid = threadIdx.x;
   for (int g = tid; g < kEncRows * 24; g += 256) {  // 24 float4 per row
@@ -179,7 +180,7 @@ ipe_grad_normals_kernel(const float* __restrict__ gx0, int ld, const float* __re
   }
   if (lrow < rows && q == 0) {
     // d mean = basis * d lifted_mean = (-dl[2], -dl[1], -dl[0]);  normals = -g / sqrt(max(|g|^2, eps))
-    const float gx = -dl[2], gy = -dl[1], gz = -dl[0];
+    const float gx = -dl[2] * gscale, gy = -dl[1] * gscale, gz = -dl[0] * gscale;   // gscale: exact power of two
     const float inv = 1.f / sqrtf(fmaxf(gx * gx + gy * gy + gz * gz, RN_EPS32));
     float* o = normals_out + (size_t)lrow * 3;
     o[0] = -gx * inv;
@@ -349,9 +350,10 @@ heads_prologue_bwd_kernel(const float* __restrict__ heads_raw, const float* __re
                           int64_t rows, MlpScalars sc, const float* __restrict__ dv0f, const float* __restrict__ dcolor,
                           const float* __restrict__ g_density, const float* __restrict__ g_normals_pred,
                           const float* __restrict__ g_grad_pred, const float* __restrict__ g_roughness,
-                          const float* __restrict__ g_tint, ActBuf d_scal) {
+                          const float* __restrict__ g_tint, ActBuf d_scal, const float* __restrict__ dv0_unscale) {
   const int64_t lrow = (int64_t)blockIdx.x * kProRows + threadIdx.x;
   if (lrow >= rows) return;
+  const float us = dv0_unscale ? *dv0_unscale : 1.f;   // fp16 mode: dv0f carries the view chain's power-of-two scale
   const int64_t ray = (row0 + lrow) / s;
   float hr[16];
   const float4* hp = reinterpret_cast<const float4*>(heads_raw + (size_t)lrow * 16);
@@ -367,8 +369,9 @@ heads_prologue_bwd_kernel(const float* __restrict__ heads_raw, const float* __re
   const float* gide = dv0f + (size_t)lrow * 256 + 128;
   double dx = 0, dy = 0, dz = 0, dk = 0;
   ide_core<true>(h.refd[0], h.refd[1], h.refd[2], h.rough, nullptr, 0, gide, 1, dx, dy, dz, dk);
-  const float dref[3] = {(float)dx, (float)dy, (float)dz};
-  const float ddot = gide[72];
+  const float dref[3] = {(float)dx * us, (float)dy * us, (float)dz * us};
+  const float ddot = gide[72] * us;
+  dk *= (double)us;
   // d normals_pred: upstream + n.v feature + reflection (r = 2 (n.v') n - v', v' = -viewdirs)
   const float ndv = -(h.np[0] * vd[0] + h.np[1] * vd[1] + h.np[2] * vd[2]);
   const float dr_dot_n = dref[0] * h.np[0] + dref[1] * h.np[1] + dref[2] * h.np[2];
@@ -601,6 +604,8 @@ __global__ void pack_segment_kernel(const float* __restrict__ src, int src_ld, i
   const size_t d = transpose ? (size_t)(r0 + j) * dst_ld + (c0 + i) : (size_t)(r0 + i) * dst_ld + (c0 + j);
   if (PREC == RN_PREC_FP32) {
     reinterpret_cast<float*>(dst_hi)[d] = v;
+  } else if (PREC == RN_PREC_FP16) {
+    reinterpret_cast<uint16_t*>(dst_hi)[d] = float_to_f16_bits(v);
   } else {
     const uint16_t h = float_to_bf16_bits(v);
     reinterpret_cast<uint16_t*>(dst_hi)[d] = h;
@@ -609,11 +614,109 @@ __global__ void pack_segment_kernel(const float* __restrict__ src, int src_ld, i
 }
 
 __global__ void unpack_add_kernel(const float* __restrict__ src, int src_ld, int r0, int c0, int nr, int nc,
-                                  float* __restrict__ dst, int dst_ld) {
+                                  float* __restrict__ dst, int dst_ld, const float* __restrict__ scale) {
   const int idx = blockIdx.x * 256 + threadIdx.x;
   if (idx >= nr * nc) return;
   const int i = idx / nc, j = idx - i * nc;
-  dst[(size_t)i * dst_ld + j] += src[(size_t)(r0 + i) * src_ld + c0 + j];
+  const float v = src[(size_t)(r0 + i) * src_ld + c0 + j];
+  dst[(size_t)i * dst_ld + j] += scale ? v * *scale : v;
+}
+
+// ------------------------------------------------------------------------------------------
+// fp16 mode: dynamic power-of-two scaling of the gradient tiles entering the dgrad chains.
+// scal layout (floats / uint bit patterns): [0] amax view-chain seed, [1] amax scalar-head seed, [2] amax bottleneck
+// gradient (view-chain scale) | [4] S1, [5] 1/S1, [6] S2, [7] 1/S2, [8] S2/S1
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void block_amax_commit(float m, uint32_t* dst) {
+  m = warp_max(m);
+  if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(dst, __float_as_uint(m));   // non-negative floats order like uints
+}
+__global__ void __launch_bounds__(256)
+amax_f32_kernel(const float* __restrict__ src, int64_t n4, uint32_t* __restrict__ dst) {
+  float m = 0.f;
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n4; i += (int64_t)gridDim.x * 256) {
+    const float4 v = reinterpret_cast<const float4*>(src)[i];
+    m = fmaxf(fmaxf(m, fmaxf(fabsf(v.x), fabsf(v.y))), fmaxf(fabsf(v.z), fabsf(v.w)));
+  }
+  block_amax_commit(m, dst);
+}
+// fp16 [rows, ld] matrix, first ncols columns (ncols % 8 == 0)
+__global__ void __launch_bounds__(256)
+amax_f16_kernel(const uint16_t* __restrict__ src, int ld, int ncols, int64_t rows, uint32_t* __restrict__ dst) {
+  const int ng = ncols >> 3;
+  const int64_t total = rows * ng;
+  float m = 0.f;
+  for (int64_t g = (int64_t)blockIdx.x * 256 + threadIdx.x; g < total; g += (int64_t)gridDim.x * 256) {
+    const int64_t row = g / ng;
+    const int cg = (int)(g - row * ng);
+    const uint4 h = *reinterpret_cast<const uint4*>(src + (size_t)row * ld + cg * 8);
+    const uint32_t hh[4] = {h.x, h.y, h.z, h.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 f = unpack_f16x2(hh[i]);
+      m = fmaxf(m, fmaxf(fabsf(f.x), fabsf(f.y)));
+    }
+  }
+  block_amax_commit(m, dst);
+}
+// S = 2^e such that amax * S lies in [2^11, 2^12): 16x headroom below the fp16 maximum, 2^25 above its smallest normal
+__device__ __forceinline__ float pow2_scale_for(float amax) {
+  if (!(amax > 0.f) || !isfinite(amax)) return 1.f;
+  int e;
+  frexpf(amax, &e);   // amax = m * 2^e, m in [0.5, 1)
+  int k = 12 - e;
+  k = k < -60 ? -60 : (k > 60 ? 60 : k);
+  return ldexpf(1.f, k);
+}
+__global__ void grad_scale_kernel(float* __restrict__ scal, int stage) {
+  const uint32_t* a = reinterpret_cast<const uint32_t*>(scal);
+  if (stage == 0) {
+    const float s1 = pow2_scale_for(__uint_as_float(a[0]));
+    scal[4] = s1;
+    scal[5] = 1.f / s1;
+  } else {
+    const float s1inv = scal[5];
+    const float s2 = pow2_scale_for(fmaxf(__uint_as_float(a[1]), __uint_as_float(a[2]) * s1inv));
+    scal[6] = s2;
+    scal[7] = 1.f / s2;
+    scal[8] = s2 * s1inv;
+  }
+}
+// dst fp16 [rows, ld_dst][:, 0:ncols] = src f32 [rows, ld_src][:, 0:ncols] * *scale
+__global__ void __launch_bounds__(256)
+scale_to_f16_kernel(const float* __restrict__ src, int ld_src, int64_t rows, int ncols, uint16_t* __restrict__ dst, int ld_dst,
+                    const float* __restrict__ scale) {
+  const int ng = ncols >> 3;
+  const int64_t g = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  const int64_t row = g / ng;
+  const int cg = (int)(g - row * ng);
+  if (row >= rows) return;
+  const float sc = *scale;
+  const float4* p = reinterpret_cast<const float4*>(src + (size_t)row * ld_src + cg * 8);
+  const float4 a = p[0], b = p[1];
+  *reinterpret_cast<uint4*>(dst + (size_t)row * ld_dst + cg * 8) =
+      make_uint4(pack_f16x2(a.x * sc, a.y * sc), pack_f16x2(a.z * sc, a.w * sc), pack_f16x2(b.x * sc, b.y * sc),
+                 pack_f16x2(b.z * sc, b.w * sc));
+}
+// in place: fp16 [rows, ld][:, 0:ncols] *= *ratio (a power of two: exact unless the result leaves the normal range)
+__global__ void __launch_bounds__(256)
+rescale_f16_kernel(uint16_t* __restrict__ buf, int ld, int ncols, int64_t rows, const float* __restrict__ ratio) {
+  const int ng = ncols >> 3;
+  const int64_t g = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  const int64_t row = g / ng;
+  const int cg = (int)(g - row * ng);
+  if (row >= rows) return;
+  const float r = *ratio;
+  uint4* p = reinterpret_cast<uint4*>(buf + (size_t)row * ld + cg * 8);
+  const uint4 h = *p;
+  const uint32_t hh[4] = {h.x, h.y, h.z, h.w};
+  uint32_t o[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 f = unpack_f16x2(hh[i]);
+    o[i] = pack_f16x2(f.x * r, f.y * r);
+  }
+  *p = make_uint4(o[0], o[1], o[2], o[3]);
 }
 
 __global__ void __launch_bounds__(128)
@@ -637,9 +740,10 @@ int launch_encode(int prec, const float* tdist, const float* origins, const floa
 }
 
 int launch_ipe_grad_normals(const float* gx0, int ld, const float* tdist, const float* origins, const float* dirs,
-                            const float* radii, int s, int64_t row0, int64_t rows, float* normals_out, cudaStream_t st) {
+                            const float* radii, int s, int64_t row0, int64_t rows, float* normals_out, float gscale,
+                            cudaStream_t st) {
   if (rows <= 0) return RN_OK;
-  ipe_grad_normals_kernel<<<nblk(rows, kEncRows), 256, 0, st>>>(gx0, ld, tdist, origins, dirs, radii, s, row0, rows, normals_out);
+  ipe_grad_normals_kernel<<<nblk(rows, kEncRows), 256, 0, st>>>(gx0, ld, tdist, origins, dirs, radii, s, row0, rows, normals_out, gscale);
   RN_CUDA_CHECK_LAUNCH();
   return RN_OK;
 }
@@ -671,11 +775,11 @@ int launch_heads_prologue_fwd(int prec, const float* heads_raw, const float* vie
 int launch_heads_prologue_bwd(int prec, const float* heads_raw, const float* viewdirs, int s, int64_t row0, int64_t rows,
                               MlpScalars sc, const float* dv0f, const float* dcolor, const float* g_density,
                               const float* g_normals_pred, const float* g_grad_pred, const float* g_roughness,
-                              const float* g_tint, ActBuf d_scal, cudaStream_t st) {
+                              const float* g_tint, ActBuf d_scal, const float* dv0_unscale, cudaStream_t st) {
   if (rows <= 0) return RN_OK;
   DISPATCH_PREC(prec, (heads_prologue_bwd_kernel<PREC><<<nblk(rows, kProRows), kProRows, 0, st>>>(
                           heads_raw, viewdirs, s, row0, rows, sc, dv0f, dcolor, g_density, g_normals_pred, g_grad_pred,
-                          g_roughness, g_tint, d_scal)));
+                          g_roughness, g_tint, d_scal, dv0_unscale)));
   RN_CUDA_CHECK_LAUNCH();
   return RN_OK;
 }
@@ -722,8 +826,45 @@ int launch_pack_segment(int prec, const float* src, int src_ld, int nr, int nc, 
 }
 
 int launch_unpack_add(const float* src, int src_ld, int r0, int c0, int nr, int nc, float* dst, int dst_ld,
-                      cudaStream_t st) {
-  unpack_add_kernel<<<nblk((int64_t)nr * nc, 256), 256, 0, st>>>(src, src_ld, r0, c0, nr, nc, dst, dst_ld);
+                      const float* scale, cudaStream_t st) {
+  unpack_add_kernel<<<nblk((int64_t)nr * nc, 256), 256, 0, st>>>(src, src_ld, r0, c0, nr, nc, dst, dst_ld, scale);
+  RN_CUDA_CHECK_LAUNCH();
+  return RN_OK;
+}
+
+static unsigned reduce_grid(int64_t items) {
+  const int64_t b = (items + 255) / 256;
+  return (unsigned)(b < 1 ? 1 : (b > 1184 ? 1184 : b));   // 8 CTAs per SM
+}
+int launch_amax_f32(const float* src, int64_t n, uint32_t* dst, cudaStream_t st) {
+  if (n <= 0) return RN_OK;
+  if (n & 3) return rn_set_error(RN_ERR_ARG, "amax_f32: element count must be a multiple of 4");
+  amax_f32_kernel<<<reduce_grid(n / 4), 256, 0, st>>>(src, n / 4, dst);
+  RN_CUDA_CHECK_LAUNCH();
+  return RN_OK;
+}
+int launch_amax_f16(const void* src, int ld, int ncols, int64_t rows, uint32_t* dst, cudaStream_t st) {
+  if (rows <= 0) return RN_OK;
+  amax_f16_kernel<<<reduce_grid(rows * (ncols >> 3)), 256, 0, st>>>(reinterpret_cast<const uint16_t*>(src), ld, ncols, rows, dst);
+  RN_CUDA_CHECK_LAUNCH();
+  return RN_OK;
+}
+int launch_grad_scale(float* scal, int stage, cudaStream_t st) {
+  grad_scale_kernel<<<1, 1, 0, st>>>(scal, stage);
+  RN_CUDA_CHECK_LAUNCH();
+  return RN_OK;
+}
+int launch_scale_to_f16(const float* src, int ld_src, int64_t rows, int ncols, void* dst, int ld_dst, const float* scale,
+                        cudaStream_t st) {
+  if (rows <= 0) return RN_OK;
+  scale_to_f16_kernel<<<nblk(rows * (ncols >> 3), 256), 256, 0, st>>>(src, ld_src, rows, ncols, reinterpret_cast<uint16_t*>(dst),
+                                                                     ld_dst, scale);
+  RN_CUDA_CHECK_LAUNCH();
+  return RN_OK;
+}
+int launch_rescale_f16(void* buf, int ld, int ncols, int64_t rows, const float* ratio, cudaStream_t st) {
+  if (rows <= 0) return RN_OK;
+  rescale_f16_kernel<<<nblk(rows * (ncols >> 3), 256), 256, 0, st>>>(reinterpret_cast<uint16_t*>(buf), ld, ncols, rows, ratio);
   RN_CUDA_CHECK_LAUNCH();
   return RN_OK;
 }

@@ -14,7 +14,8 @@ int launch_encode(int prec, const float* tdist, const float* origins, const floa
                   int64_t row0, int64_t rows, ActBuf out, int ncols, cudaStream_t st);
 // normals = -l2_normalize(d raw_density / d means) from gx0 = d raw_density / d ipe features
 int launch_ipe_grad_normals(const float* gx0, int ld, const float* tdist, const float* origins, const float* dirs,
-                            const float* radii, int s, int64_t row0, int64_t rows, float* normals_out, cudaStream_t st);
+                            const float* radii, int s, int64_t row0, int64_t rows, float* normals_out, float gscale,
+                            cudaStream_t st);
 // seed of the normals pass: out[r, j] = wd[j] * (a8[r, j] > 0)
 int launch_density_grad_seed(int prec, ActBuf a8, const float* wd, ActBuf out, int64_t rows, cudaStream_t st);
 // the same from the 1-bit ReLU masks of a8 written by the fused forward chain (bf16 output)
@@ -28,7 +29,7 @@ int launch_heads_prologue_fwd(int prec, const float* heads_raw, const float* vie
 int launch_heads_prologue_bwd(int prec, const float* heads_raw, const float* viewdirs, int s, int64_t row0, int64_t rows,
                               MlpScalars sc, const float* dv0f, const float* dcolor, const float* g_density,
                               const float* g_normals_pred, const float* g_grad_pred, const float* g_roughness,
-                              const float* g_tint, ActBuf d_scal, cudaStream_t st);
+                              const float* g_tint, ActBuf d_scal, const float* dv0_unscale, cudaStream_t st);
 // colour combine (models.py:699-729): rgb_raw [rows,4], heads_raw [rows,16] -> rgb, diffuse, specular [.,3]
 int launch_color_fwd(const float* rgb_raw, const float* heads_raw, int64_t rows, MlpScalars sc, float* rgb,
                      float* diffuse, float* specular, cudaStream_t st);
@@ -45,7 +46,15 @@ int launch_pack_segment(int prec, const float* src, int src_ld, int nr, int nc, 
                         int dst_ld, int r0, int c0, cudaStream_t st);
 // grad unpacking: dst[i*dst_ld + j] += src[(r0+i)*src_ld + c0 + j]
 int launch_unpack_add(const float* src, int src_ld, int r0, int c0, int nr, int nc, float* dst, int dst_ld,
-                      cudaStream_t st);
+                      const float* scale, cudaStream_t st);
+// fp16 mode: dynamic power-of-two scaling of the gradient tiles entering the dgrad chains (layout of `scal` in
+// pointwise.cu).  amax kernels accumulate max|x| as a uint bit pattern (zero the slot first).
+int launch_amax_f32(const float* src, int64_t n, uint32_t* dst, cudaStream_t st);
+int launch_amax_f16(const void* src, int ld, int ncols, int64_t rows, uint32_t* dst, cudaStream_t st);
+int launch_grad_scale(float* scal, int stage, cudaStream_t st);
+int launch_scale_to_f16(const float* src, int ld_src, int64_t rows, int ncols, void* dst, int ld_dst, const float* scale,
+                        cudaStream_t st);
+int launch_rescale_f16(void* buf, int ld, int ncols, int64_t rows, const float* ratio, cudaStream_t st);
 // standalone IDE (unit test surface)
 int launch_ide(const float* dirs, const float* kappa_inv, int64_t n, float* out, cudaStream_t st);
 

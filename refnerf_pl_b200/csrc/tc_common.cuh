@@ -111,11 +111,11 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t lbo_b
   return d;
 }
 // Instruction descriptor (cute::UMMA::InstrDescriptor): c=f32, a=b=bf16, M=128, N=n
-__device__ __forceinline__ uint32_t make_idesc(int n, int a_mn_major, int b_mn_major) {
+__device__ __forceinline__ uint32_t make_idesc(int n, int a_mn_major, int b_mn_major, int a_f16 = 0, int b_f16 = 0) {
   uint32_t d = 0;
   d |= 1u << 4;                       // c_format = F32
-  d |= 1u << 7;                       // a_format = BF16
-  d |= 1u << 10;                      // b_format = BF16
+  d |= (a_f16 ? 0u : 1u) << 7;        // a_format: BF16 (1) or FP16 (0)
+  d |= (b_f16 ? 0u : 1u) << 10;       // b_format
   d |= (uint32_t)a_mn_major << 15;
   d |= (uint32_t)b_mn_major << 16;
   d |= (uint32_t)(n >> 3) << 17;

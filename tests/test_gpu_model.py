@@ -26,7 +26,10 @@ TOL = {
     'fp32':   dict(rel=2e-4, colour=2e-5, npred=2e-4, comp=2e-5, normals_mean=2e-3, normals_p99=5e-2, grad=5e-3),
     'bf16x3': dict(rel=1e-3, colour=1e-4, npred=1e-3, comp=1e-4, normals_mean=5e-3, normals_p99=1e-1, grad=1e-2),
     'bf16':   dict(rel=1e-2, colour=1e-3, npred=2e-2, comp=1e-3, normals_mean=1e-1, normals_p99=2.0, grad=1e-1),
+    # fp16 operands (11-bit): measured <= 1.3e-4 / 2.9e-5 / 2e-3 / 1.2e-5 / 4.3e-3 / 0.10 / 3.5e-2 on the three fixtures
+    'fp16':   dict(rel=1e-3, colour=1e-4, npred=5e-3, comp=1e-4, normals_mean=1e-2, normals_p99=0.3, grad=5e-2),
 }
+ALL = bool(os.environ.get('RN_PARITY_ALL'))   # report-only runs: also try plain bf16 on the trained-scale fixtures
 LEVEL1 = 8.0   # level-1 samples sit on fenceposts resampled from level-0 weights: errors compound
 
 
@@ -48,11 +51,11 @@ def _report(key, rep):
         f.write(json.dumps({'case': key, **rep}) + '\n')
 
 
-@pytest.mark.parametrize('precision', ['fp32', 'bf16x3', 'bf16'])
+@pytest.mark.parametrize('precision', ['fp32', 'bf16x3', 'bf16', 'fp16'])
 @pytest.mark.parametrize('name', ['blender_init', 'blender_pert', 'llff_geom'])
 @pytest.mark.parametrize('mode', ['eval', 'train'])
 def test_model_vs_reference_fixture(name, precision, mode):
-    if precision == 'bf16' and name != 'blender_init':
+    if precision == 'bf16' and name != 'blender_init' and not ALL:
         pytest.skip('plain bf16 is the throughput mode: gated at reference init only (SURVEY 7.4)')
     g, model, cfg, r, rend, hist = _run(name, precision, mode)
     tol = TOL[precision]
@@ -99,10 +102,10 @@ def test_model_vs_reference_fixture(name, precision, mode):
     assert not bad, bad
 
 
-@pytest.mark.parametrize('precision', ['fp32', 'bf16x3', 'bf16'])
+@pytest.mark.parametrize('precision', ['fp32', 'bf16x3', 'bf16', 'fp16'])
 @pytest.mark.parametrize('name', ['blender_init', 'blender_pert', 'llff_geom'])
 def test_gradients_vs_reference_fixture(name, precision):
-    if precision == 'bf16' and name != 'blender_init':
+    if precision == 'bf16' and name != 'blender_init' and not ALL:
         pytest.skip('plain bf16 is gated at reference init only')
     from refnerf_pl_b200 import train_utils
     g, model, cfg, r, rend, hist = _run(name, precision, 'train')
@@ -180,7 +183,7 @@ def test_saved_activation_backward_matches_recompute(monkeypatch):
     rays = synthetic.blender_rays(520, seed=11)
     gt = torch.tensor(synthetic.gt_rgb(520, 11), device=DEV)
     default_cap = ops.SAVED_BYTES_CAP
-    for prec in ('bf16', 'bf16x3'):
+    for prec in ('bf16', 'bf16x3', 'fp16'):
         grads = {}
         for cap in (default_cap, 0):
             monkeypatch.setattr(ops, 'SAVED_BYTES_CAP', cap)

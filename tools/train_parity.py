@@ -2,7 +2,7 @@
 
 There is no dataset in this environment, so the scene is analytic: a Phong-shaded unit sphere with a procedural
 albedo in front of a white background, seen from Blender-shaped cameras (synthetic.blender_rays).  The SAME ray
-stream, ground truth and initial weights train the throughput mode (bf16 tensor-core chains) and the parity mode
+stream, ground truth and initial weights train the throughput modes (fp16 / bf16 tensor-core chains) and the parity mode
 (bf16x3 split-bf16, ~fp32 arithmetic, the mode that meets the per-sample 1e-3 gates against the reference); the
 held-out PSNR of the two must agree within 0.1 dB.   python tools/train_parity.py [steps] [rays_per_step]
 """
@@ -81,12 +81,15 @@ def main():
     n_rays = int(sys.argv[2]) if len(sys.argv) > 2 else 4096
     dev = torch.device('cuda', 0)
     res = {}
-    for prec in ('bf16', 'bf16x3'):
+    modes = tuple(sys.argv[3].split(',')) if len(sys.argv) > 3 else ('fp16', 'bf16', 'bf16x3')
+    for prec in modes:
         torch.manual_seed(0)
         psnr, secs = run(prec, steps, n_rays, dev)
         res[prec] = {'psnr_db': psnr, 'train_seconds': secs}
         print(f'{prec}: held-out PSNR {psnr:.3f} dB after {steps} steps of {n_rays} rays ({secs:.1f} s)', flush=True)
-    res['delta_db'] = res['bf16']['psnr_db'] - res['bf16x3']['psnr_db']
+    for prec in modes:
+        if prec != 'bf16x3' and 'bf16x3' in res:
+            res[f'delta_db_{prec}'] = res[prec]['psnr_db'] - res['bf16x3']['psnr_db']
     res['steps'], res['rays_per_step'] = steps, n_rays
     res['scene'] = 'analytic Phong sphere, white background, Blender-shaped cameras (tools/train_parity.py)'
     print(json.dumps(res))
