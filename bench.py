@@ -374,7 +374,7 @@ def run_b200(args):
 
     # ---- the same step in the parity arithmetic (bf16x3 = split-bf16, ~fp32; the mode that meets the 1e-3 gates) ----
     parity = None
-    if rank == 0 and not args.no_parity and args.precision == 'bf16':
+    if rank == 0 and not args.no_parity and args.precision in ('bf16', 'fp16'):
         del opt, sched
         torch.cuda.empty_cache()
         pm, pcfg = build_everything('bf16x3', dev)
@@ -478,7 +478,7 @@ def main():
     ap.add_argument('--steps', type=int, default=5)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
-    ap.add_argument('--precision', default=os.environ.get('REFNERF_B200_PRECISION', 'bf16'),
+    ap.add_argument('--precision', default=os.environ.get('REFNERF_B200_PRECISION', 'fp16'),
                     choices=['bf16', 'fp16', 'bf16x3', 'fp32'])
     ap.add_argument('--rays', type=int, default=16384)
     ap.add_argument('--cpu-rays', type=int, default=512)

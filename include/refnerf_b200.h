@@ -87,6 +87,17 @@ RN_API int rn_lossfun_outer_bwd(const float* t, const float* w, const float* t_e
 RN_API int rn_distortion_fwd(const float* t, const float* w, int64_t n_rays, int s, float* loss_out, void* stream);
 RN_API int rn_distortion_bwd(const float* t, const float* w, const float* g_loss, int64_t n_rays, int s, float* d_w,
                       void* stream);
+/* train_utils.orientation_loss + predicted_normal_loss (train_utils.py:165-204), per ray, one pass:
+ * ori[r] = sum_s w (min(0, n_t . (-v)))^2 with n_t = normals_pred (ori_target_is_pred) or the density-gradient
+ * normals; pred[r] = sum_s w (1 - normals . normals_pred) (0 when normals == NULL).  The caller takes the means and
+ * applies the loss multipliers.  weights [N,s]; normals, normals_pred [N,s,3]; viewdirs [N,3]; outputs [N].
+ * Backward w.r.t. weights and normals_pred (the density-gradient normals are constants, models.py:603-609);
+ * g_ori / g_pred [N] may be NULL (= 0). */
+RN_API int rn_normal_losses_fwd(const float* weights, const float* normals, const float* normals_pred, const float* viewdirs,
+                         int64_t n_rays, int s, int ori_target_is_pred, float* ori_out, float* pred_out, void* stream);
+RN_API int rn_normal_losses_bwd(const float* weights, const float* normals, const float* normals_pred, const float* viewdirs,
+                         const float* g_ori, const float* g_pred, int64_t n_rays, int s, int ori_target_is_pred,
+                         float* d_weights, float* d_normals_pred, void* stream);
 
 /* ---- K1 / K2 unit-level entry points (the fused MLP uses the same device code) -------------
  * rn_encode: render.cast_rays (render.py:105-129, cone, full cov) + coord.lift_and_diagonalize

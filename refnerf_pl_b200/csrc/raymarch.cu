@@ -856,6 +856,67 @@ distortion_kernel(const float* __restrict__ t, const float* __restrict__ w, cons
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// orientation + predicted-normal losses (train_utils.py:165-204), per ray, in one pass over the per-sample
+// normals:  ori[r] = sum_s w (min(0, n_t . (-v)))^2   (n_t = normals_pred or the density-gradient normals),
+//           pred[r] = sum_s w (1 - n . n_pred).
+// One warp per ray; the [s,3] rows are staged through shared memory with coalesced accesses, each lane then
+// owns samples lane, lane+32, ...  Backward: d w and d normals_pred (the density-gradient normals are constants).
+// ---------------------------------------------------------------------------------------------
+template <bool BWD>
+__global__ void __launch_bounds__(kWarps * 32)
+normal_losses_kernel(const float* __restrict__ w, const float* __restrict__ normals, const float* __restrict__ npred,
+                     const float* __restrict__ viewdirs, const float* __restrict__ g_ori, const float* __restrict__ g_pred,
+                     int64_t n_rays, int s, int ori_is_pred, float* __restrict__ ori_out, float* __restrict__ pred_out,
+                     float* __restrict__ d_w, float* __restrict__ d_npred) {
+  extern __shared__ float smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* sn = smem + warp * 6 * s;   // density-gradient normals [s,3] (zeros when absent)
+  float* sp = sn + 3 * s;            // predicted normals [s,3]; backward: overwritten by d normals_pred
+  const int64_t ray = (int64_t)blockIdx.x * kWarps + warp;
+  if (ray >= n_rays) return;
+  const size_t base3 = (size_t)ray * s * 3;
+  for (int i = lane; i < 3 * s; i += 32) {
+    sn[i] = normals ? normals[base3 + i] : 0.f;
+    sp[i] = npred[base3 + i];
+  }
+  __syncwarp();
+  const float vx = -viewdirs[ray * 3], vy = -viewdirs[ray * 3 + 1], vz = -viewdirs[ray * 3 + 2];
+  const float go = BWD ? (g_ori ? g_ori[ray] : 0.f) : 0.f;
+  const float gp = BWD ? ((g_pred && normals) ? g_pred[ray] : 0.f) : 0.f;
+  float ori = 0.f, pred = 0.f;
+  for (int i = lane; i < s; i += 32) {
+    const float wi = w[(size_t)ray * s + i];
+    const float nx = sn[3 * i], ny = sn[3 * i + 1], nz = sn[3 * i + 2];
+    const float px = sp[3 * i], py = sp[3 * i + 1], pz = sp[3 * i + 2];
+    const float tx = ori_is_pred ? px : nx, ty = ori_is_pred ? py : ny, tz = ori_is_pred ? pz : nz;
+    const float ndv = fminf(tx * vx + ty * vy + tz * vz, 0.f);
+    const float one_m = 1.f - (nx * px + ny * py + nz * pz);
+    if (!BWD) {
+      ori += wi * ndv * ndv;
+      pred += wi * one_m;
+    } else {
+      d_w[(size_t)ray * s + i] = go * ndv * ndv + gp * one_m;
+      const float c = ori_is_pred ? go * wi * 2.f * ndv : 0.f;
+      const float d = -gp * wi;
+      sp[3 * i] = c * vx + d * nx;
+      sp[3 * i + 1] = c * vy + d * ny;
+      sp[3 * i + 2] = c * vz + d * nz;
+    }
+  }
+  if (!BWD) {
+    ori = warp_sum(ori);
+    pred = warp_sum(pred);
+    if (lane == 0) {
+      ori_out[ray] = ori;
+      pred_out[ray] = normals ? pred : 0.f;
+    }
+  } else {
+    __syncwarp();
+    for (int i = lane; i < 3 * s; i += 32) d_npred[base3 + i] = sp[i];
+  }
+}
+
 inline unsigned blocks_for(int64_t n_rays) { return (unsigned)((n_rays + kWarps - 1) / kWarps); }
 
 template <typename K>
@@ -976,6 +1037,34 @@ extern "C" int rn_distortion_bwd(const float* t, const float* w, const float* g_
   size_t smem = (size_t)kWarps * 2 * s * sizeof(float);
   if (int rc = ensure_smem(distortion_kernel<true>, smem)) return rc;
   distortion_kernel<true><<<blocks_for(n_rays), kWarps * 32, smem, (cudaStream_t)stream>>>(t, w, g_loss, n_rays, s, d_w);
+  RN_CUDA_CHECK_LAUNCH();
+  return RN_OK;
+}
+
+extern "C" int rn_normal_losses_fwd(const float* weights, const float* normals, const float* normals_pred,
+                                    const float* viewdirs, int64_t n_rays, int s, int ori_target_is_pred, float* ori_out,
+                                    float* pred_out, void* stream) {
+  if (n_rays == 0) return RN_OK;
+  if (!weights || !normals_pred || !viewdirs || !ori_out || !pred_out || s < 1) return rn_set_error(RN_ERR_ARG, "rn_normal_losses_fwd: bad arguments");
+  if (!ori_target_is_pred && !normals) return rn_set_error(RN_ERR_ARG, "rn_normal_losses_fwd: orientation target 'normals' needs the density-gradient normals");
+  size_t smem = (size_t)kWarps * 6 * s * sizeof(float);
+  if (int rc = ensure_smem(normal_losses_kernel<false>, smem)) return rc;
+  normal_losses_kernel<false><<<blocks_for(n_rays), kWarps * 32, smem, (cudaStream_t)stream>>>(
+      weights, normals, normals_pred, viewdirs, nullptr, nullptr, n_rays, s, ori_target_is_pred, ori_out, pred_out, nullptr, nullptr);
+  RN_CUDA_CHECK_LAUNCH();
+  return RN_OK;
+}
+
+extern "C" int rn_normal_losses_bwd(const float* weights, const float* normals, const float* normals_pred,
+                                    const float* viewdirs, const float* g_ori, const float* g_pred, int64_t n_rays, int s,
+                                    int ori_target_is_pred, float* d_weights, float* d_normals_pred, void* stream) {
+  if (n_rays == 0) return RN_OK;
+  if (!weights || !normals_pred || !viewdirs || !d_weights || !d_normals_pred || s < 1) return rn_set_error(RN_ERR_ARG, "rn_normal_losses_bwd: bad arguments");
+  if (!ori_target_is_pred && !normals) return rn_set_error(RN_ERR_ARG, "rn_normal_losses_bwd: orientation target 'normals' needs the density-gradient normals");
+  size_t smem = (size_t)kWarps * 6 * s * sizeof(float);
+  if (int rc = ensure_smem(normal_losses_kernel<true>, smem)) return rc;
+  normal_losses_kernel<true><<<blocks_for(n_rays), kWarps * 32, smem, (cudaStream_t)stream>>>(
+      weights, normals, normals_pred, viewdirs, g_ori, g_pred, n_rays, s, ori_target_is_pred, nullptr, nullptr, d_weights, d_normals_pred);
   RN_CUDA_CHECK_LAUNCH();
   return RN_OK;
 }

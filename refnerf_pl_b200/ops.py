@@ -245,6 +245,57 @@ torch.library.register_autograd(f'{NS}::distortion', _dist_backward, setup_conte
 
 
 # ------------------------------------------------------------------------------------------
+# orientation + predicted-normal losses, per ray (train_utils.py:165-204)
+# ------------------------------------------------------------------------------------------
+@torch.library.custom_op(f'{NS}::normal_losses', mutates_args=(), device_types='cuda')
+def normal_losses(weights: Tensor, normals: Tensor, normals_pred: Tensor, viewdirs: Tensor, ori_is_pred: bool) -> Tensor:
+    """weights [N,S]; normals [N,S,3] (empty = absent) and normals_pred [N,S,3]; viewdirs [N,3] ->
+    [2,N]: row 0 = sum_s w min(0, n_t.(-v))^2, row 1 = sum_s w (1 - n.n_pred)."""
+    lib = _lib.load()
+    n, s = weights.shape
+    out = torch.empty((2, n), device=weights.device, dtype=torch.float32)
+    _lib.check(lib.rn_normal_losses_fwd(_ptr(weights), _ptr(normals), _ptr(normals_pred), _ptr(viewdirs), n, s,
+                                        int(ori_is_pred), _ptr(out[0]), _ptr(out[1]), _stream()))
+    return out
+
+
+@normal_losses.register_fake
+def _(weights, normals, normals_pred, viewdirs, ori_is_pred):
+    return weights.new_empty((2, weights.shape[0]))
+
+
+@torch.library.custom_op(f'{NS}::normal_losses_bwd', mutates_args=(), device_types='cuda')
+def normal_losses_bwd(weights: Tensor, normals: Tensor, normals_pred: Tensor, viewdirs: Tensor, g: Tensor,
+                      ori_is_pred: bool) -> List[Tensor]:
+    lib = _lib.load()
+    n, s = weights.shape
+    d_w, d_np = torch.empty_like(weights), torch.empty_like(normals_pred)
+    _lib.check(lib.rn_normal_losses_bwd(_ptr(weights), _ptr(normals), _ptr(normals_pred), _ptr(viewdirs), _ptr(g[0]),
+                                        _ptr(g[1]), n, s, int(ori_is_pred), _ptr(d_w), _ptr(d_np), _stream()))
+    return [d_w, d_np]
+
+
+@normal_losses_bwd.register_fake
+def _(weights, normals, normals_pred, viewdirs, g, ori_is_pred):
+    return [torch.empty_like(weights), torch.empty_like(normals_pred)]
+
+
+def _nl_setup(ctx, inputs, output):
+    weights, normals, normals_pred, viewdirs, ori_is_pred = inputs
+    ctx.save_for_backward(weights, normals, normals_pred, viewdirs)
+    ctx.ori_is_pred = ori_is_pred
+
+
+def _nl_backward(ctx, g):
+    weights, normals, normals_pred, viewdirs = ctx.saved_tensors
+    d_w, d_np = normal_losses_bwd(weights, normals, normals_pred, viewdirs, _f32c(g), ctx.ori_is_pred)
+    return d_w, None, d_np, None, None
+
+
+torch.library.register_autograd(f'{NS}::normal_losses', _nl_backward, setup_context=_nl_setup)
+
+
+# ------------------------------------------------------------------------------------------
 # unit-level encoders
 # ------------------------------------------------------------------------------------------
 @torch.library.custom_op(f'{NS}::encode', mutates_args=(), device_types='cuda')

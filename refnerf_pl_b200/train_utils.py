@@ -6,7 +6,7 @@ import functools
 import numpy as np
 import torch
 
-from . import stepfun
+from . import ops, stepfun
 
 
 def compute_data_loss(batch_rgb, renderings, lossmult, config):
@@ -68,14 +68,48 @@ def predicted_normal_loss(num_levels, ray_history, config):
     return total
 
 
-def total_loss(model, rays_viewdirs, lossmult, gt_rgb, renderings, ray_history, config):
+def normal_losses(viewdirs, num_levels, ray_history, config):
+    """orientation_loss + predicted_normal_loss (train_utils.py:165-204) from ONE pass over the per-sample normals
+    per level (`rn_normal_losses_*`) instead of ~20 elementwise / reduction launches over
+    [N,S,3] tensors.  Same value as `orientation_loss(...) + predicted_normal_loss(...)`."""
+    want_ori = config.orientation_coarse_loss_mult > 0 or config.orientation_loss_mult > 0
+    want_pred = config.predicted_normal_coarse_loss_mult > 0 or config.predicted_normal_loss_mult > 0
+    target = config.orientation_loss_target
+    if target not in ('normals', 'normals_pred'):
+        raise ValueError(f'unsupported orientation_loss_target {target!r}')
+    total = 0.
+    for i, res in enumerate(ray_history):
+        n, n_pred, w = res['normals'], res['normals_pred'], res['weights']
+        if want_ori and res[target] is None:
+            raise ValueError('Normals cannot be None if orientation loss is on.')
+        if want_pred and (n is None or n_pred is None):
+            raise ValueError('Predicted normals and gradient normals cannot be None if predicted normal loss is on.')
+        s = w.shape[-1]
+        flat3 = lambda t: t.reshape(-1, s, 3) if t is not None else w.new_empty((0,))
+        per_ray = ops.normal_losses(w.reshape(-1, s).contiguous(), flat3(n).detach().contiguous(),
+                                    flat3(n_pred).contiguous(), viewdirs.reshape(-1, 3).contiguous().float(),
+                                    target == 'normals_pred')
+        means = per_ray.mean(dim=1)
+        fine = i == num_levels - 1
+        if want_ori:
+            total = total + (config.orientation_loss_mult if fine else config.orientation_coarse_loss_mult) * means[0]
+        if want_pred:
+            total = total + (config.predicted_normal_loss_mult if fine else config.predicted_normal_coarse_loss_mult) * means[1]
+    return total
+
+
+def total_loss(model, rays_viewdirs, lossmult, gt_rgb, renderings, ray_history, config, fused_normal_losses=True):
     """The loss sum of nerf_system.py:138-191 restricted to the terms of the Ref-NeRF configs."""
     loss, stats = compute_data_loss(gt_rgb, renderings, lossmult, config)
     if config.interlevel_loss_mult > 0:
         loss = loss + interlevel_loss(ray_history, config)
-    if config.orientation_coarse_loss_mult > 0 or config.orientation_loss_mult > 0:
+    want_ori = config.orientation_coarse_loss_mult > 0 or config.orientation_loss_mult > 0
+    want_pred = config.predicted_normal_coarse_loss_mult > 0 or config.predicted_normal_loss_mult > 0
+    if fused_normal_losses and (want_ori or want_pred) and ray_history[0]['weights'].is_cuda:
+        return loss + normal_losses(rays_viewdirs, model.num_levels, ray_history, config), stats
+    if want_ori:
         loss = loss + orientation_loss(rays_viewdirs, model.num_levels, ray_history, config)
-    if config.predicted_normal_coarse_loss_mult > 0 or config.predicted_normal_loss_mult > 0:
+    if want_pred:
         loss = loss + predicted_normal_loss(model.num_levels, ray_history, config)
     return loss, stats
 

@@ -1,0 +1,116 @@
+"""-m gpu: size-independent properties of the hot path at BASELINE.json's full configuration-2 size
+(16 384 rays x 128 samples x 2 levels = 2 097 152 MLP rows per level), where the CPU oracle is too slow to be the
+checker.  Every property below follows from the reference's definition of the path (rays are independent,
+models.py:129-321; the backward is linear in the loss, the weight gradient is a sum over rays):
+
+  * ray-permutation equivariance and chunk independence: a ray's outputs do not depend on where it sits in the
+    batch, on its tile / CTA, or on the chunk size -- bit for bit;
+  * compositing identities on the returned per-sample tensors (render.py:132-254);
+  * linearity of the backward in the loss scale and additivity of the weight gradient over a ray partition
+    (the check behind ray-sharded data parallelism), within the atomics' re-ordering noise.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import refnerf_oracle as O
+from refnerf_pl_b200 import synthetic, train_utils
+from tests._gpu import DEV, build_model, load_params, rays_obj
+
+pytestmark = pytest.mark.gpu
+
+N = 16384
+PRECISIONS = ['fp16', 'bf16']
+
+
+def _model(precision, **mlp_kwargs):
+    model, cfg = build_model(precision, mlp_kwargs=mlp_kwargs or None)
+    load_params(model, O.init_params(seed=3, bias_std=0.1, weight_scale=1.3))
+    return model, cfg
+
+
+def _take(rays, idx):
+    return {k: v[idx] for k, v in rays.items()}
+
+
+@pytest.mark.parametrize('precision', PRECISIONS)
+def test_permutation_and_chunk_independence(precision):
+    rays = synthetic.blender_rays(N, seed=31)
+    perm = np.random.default_rng(0).permutation(N)
+    outs = []
+    for chunk_rows, r in ((0, rays), (0, _take(rays, perm)), (393216, rays)):
+        model, _ = _model(precision, chunk_rows=chunk_rows)
+        model.train(True)   # training forward: includes the density-gradient normals chain
+        with torch.no_grad():
+            rend, hist = model(rays_obj(r), 1.0, True)
+        outs.append((rend, hist))
+    (ra, ha), (rp, hp), (rc, hc) = outs
+    p = torch.as_tensor(perm, device=DEV)
+    for lvl in range(2):
+        for k in ('density', 'rgb', 'normals', 'normals_pred', 'roughness', 'tint', 'weights', 'sdist'):
+            assert torch.equal(ha[lvl][k][p], hp[lvl][k]), (precision, 'permutation', lvl, k)
+            assert torch.equal(ha[lvl][k], hc[lvl][k]), (precision, 'chunking', lvl, k)
+        for k in ('rgb', 'acc', 'distance', 'distance_median', 'normals_pred'):
+            assert torch.equal(ra[lvl][k][p], rp[lvl][k]), (precision, 'permutation', lvl, k)
+            assert torch.equal(ra[lvl][k], rc[lvl][k]), (precision, 'chunking', lvl, k)
+
+
+@pytest.mark.parametrize('precision', PRECISIONS)
+def test_compositing_identities(precision):
+    rays = synthetic.blender_rays(N, seed=32)
+    model, _ = _model(precision)
+    model.eval()
+    with torch.no_grad():
+        rend, hist = model(rays_obj(rays), 1.0, True)
+    for lvl in range(2):
+        h, r = hist[lvl], rend[lvl]
+        sd, w = h['sdist'], h['weights']
+        assert sd.shape == (N, 129) and w.shape == (N, 128)
+        assert bool((sd[:, 1:] >= sd[:, :-1]).all()), 'fenceposts must be sorted'
+        assert float(sd.min()) >= 0.0 and float(sd.max()) <= 1.0
+        assert bool(torch.isfinite(h['density']).all()) and float(h['density'].min()) >= 0.0
+        assert float(w.min()) >= 0.0
+        acc = w.double().sum(-1)
+        assert float(acc.max()) <= 1.0 + 1e-5
+        assert float((r['acc'].double() - acc).abs().max()) <= 2e-6
+        # rgb = sum w c + (1 - acc) * bg, bg = 1 (render.py:199-216; no render-time tone map in the Blender config)
+        comp = (w.double()[..., None] * h['rgb'].double()).sum(-2) + (1.0 - acc).clamp_min(0.0)[..., None]
+        assert float((r['rgb'].double() - comp).abs().max()) <= 5e-6
+        nrm = h['normals_pred'].double().norm(dim=-1)
+        assert float((nrm - 1.0).abs().max()) <= 1e-5
+        assert bool((r['distance_percentile_5'] <= r['distance_median']).all())
+        assert bool((r['distance_median'] <= r['distance_percentile_95']).all())
+
+
+def _grads(model, cfg, rays, gt, scale=1.0):
+    model.train(True)
+    r = rays_obj(rays)
+    rend, hist = model(r, 1.0, False)
+    loss, _ = train_utils.total_loss(model, r.viewdirs, r.lossmult, gt, rend, hist, cfg)
+    for q in model.nerf_mlp.parameters():
+        q.grad = None
+    (loss * scale).backward()
+    return torch.cat([q.grad.reshape(-1) for q in model.nerf_mlp.parameters()]).double()
+
+
+@pytest.mark.parametrize('precision', PRECISIONS)
+def test_backward_linearity_and_ray_additivity(precision):
+    rays = synthetic.blender_rays(N, seed=33)
+    gt_np = synthetic.gt_rgb(N, 33)
+    gt = torch.tensor(gt_np, device=DEV)
+    model, cfg = _model(precision)
+    g1 = _grads(model, cfg, rays, gt)
+    assert bool(torch.isfinite(g1).all()) and float(g1.norm()) > 0
+    rel = lambda a, b: float((a - b).norm() / b.norm())
+    noise = rel(_grads(model, cfg, rays, gt), g1)          # same call twice: only the atomics re-order
+    assert noise <= 1e-4, noise
+    # the loss scale is a power of two: the fp16 mode's dynamic gradient scales absorb it exactly
+    g8 = _grads(model, cfg, rays, gt, scale=8.0)
+    assert rel(g8 / 8.0, g1) <= 1e-4 + 2 * noise
+    g3 = _grads(model, cfg, rays, gt, scale=3.0)
+    assert rel(g3 / 3.0, g1) <= (5e-3 if precision == 'fp16' else 3e-2)   # operands round differently
+    # mean losses over N rays: grad(all) = (grad(first half) + grad(second half)) / 2 -- what ray sharding relies on
+    half = N // 2
+    ga = _grads(model, cfg, _take(rays, slice(0, half)), gt[:half])
+    gb = _grads(model, cfg, _take(rays, slice(half, N)), gt[half:])
+    assert rel((ga + gb) / 2.0, g1) <= (5e-3 if precision == 'fp16' else 3e-2)

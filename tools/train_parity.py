@@ -79,19 +79,26 @@ def run(precision, steps, n_rays, dev):
 def main():
     steps = int(sys.argv[1]) if len(sys.argv) > 1 else 2000
     n_rays = int(sys.argv[2]) if len(sys.argv) > 2 else 4096
-    dev = torch.device('cuda', 0)
-    res = {}
     modes = tuple(sys.argv[3].split(',')) if len(sys.argv) > 3 else ('fp16', 'bf16', 'bf16x3')
+    repeats = int(sys.argv[4]) if len(sys.argv) > 4 else 1
+    dev = torch.device('cuda', 0)
+    # identical initial weights and ray stream every run: repeats differ only through the order of the wgrad atomics,
+    # i.e. they measure the run-to-run spread a precision mode has against ITSELF
+    runs = []
+    for rep in range(repeats):
+        for prec in modes:
+            torch.manual_seed(0)
+            psnr, secs = run(prec, steps, n_rays, dev)
+            runs.append({'precision': prec, 'repeat': rep, 'psnr_db': psnr, 'train_seconds': secs})
+            print(f'{prec}[{rep}]: held-out PSNR {psnr:.3f} dB after {steps} steps of {n_rays} rays ({secs:.1f} s)', flush=True)
+    res = {'runs': runs, 'steps': steps, 'rays_per_step': n_rays,
+           'scene': 'analytic Phong sphere, white background, Blender-shaped cameras (tools/train_parity.py)'}
     for prec in modes:
-        torch.manual_seed(0)
-        psnr, secs = run(prec, steps, n_rays, dev)
-        res[prec] = {'psnr_db': psnr, 'train_seconds': secs}
-        print(f'{prec}: held-out PSNR {psnr:.3f} dB after {steps} steps of {n_rays} rays ({secs:.1f} s)', flush=True)
+        v = [r['psnr_db'] for r in runs if r['precision'] == prec]
+        res[prec] = {'mean_psnr_db': float(np.mean(v)), 'min': float(np.min(v)), 'max': float(np.max(v)), 'n': len(v)}
     for prec in modes:
         if prec != 'bf16x3' and 'bf16x3' in res:
-            res[f'delta_db_{prec}'] = res[prec]['psnr_db'] - res['bf16x3']['psnr_db']
-    res['steps'], res['rays_per_step'] = steps, n_rays
-    res['scene'] = 'analytic Phong sphere, white background, Blender-shaped cameras (tools/train_parity.py)'
+            res[f'delta_db_{prec}'] = res[prec]['mean_psnr_db'] - res['bf16x3']['mean_psnr_db']
     print(json.dumps(res))
 
 
