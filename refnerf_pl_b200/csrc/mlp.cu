@@ -778,6 +778,23 @@ extern "C" int rn_mlp_pack(const float* const* params, void* packed, int prec, v
   uint8_t* base = reinterpret_cast<uint8_t*>(packed);
   cudaError_t e = cudaMemsetAsync(packed, 0, lay.total, st);
   if (e != cudaSuccess) return rn_set_cuda_error(e, __FILE__, __LINE__);
+  // every weight block / bias vector is one segment of a table-driven launch (pointwise.cu)
+  PackTable tw, tb;
+  tw.n = tb.n = 0;
+  int rc_flush = RN_OK;
+  auto flush = [&](PackTable& t) {
+    if (t.n && rc_flush == RN_OK) rc_flush = launch_pack_batch(prec, t, st);
+    t.n = 0;
+  };
+  auto seg = [&](const float* src, int src_ld, int nr, int nc, int transpose, void* dst_hi, void* dst_lo, int dst_ld, int r0,
+                 int c0) {
+    if (tw.n == kMaxBatchSegs) flush(tw);
+    tw.seg[tw.n++] = PackSeg{src, dst_hi, prec == RN_PREC_BF16X3 ? dst_lo : nullptr, src_ld, nr, nc, transpose, dst_ld, r0, c0, 0};
+  };
+  auto copy_f32 = [&](const float* src, float* dst, int n) {
+    if (tb.n == kMaxBatchSegs) flush(tb);
+    tb.seg[tb.n++] = PackSeg{src, dst, nullptr, n, 1, n, 0, n, 0, 0, 1};
+  };
   for (int l = 0; l < kNumLayers; ++l) {
     LayerDef d = layer_def(l);
     void* wf_hi = base + lay.wf[l];
@@ -787,33 +804,33 @@ extern "C" int rn_mlp_pack(const float* const* params, void* packed, int prec, v
     float* bias = reinterpret_cast<float*>(base + lay.bias[l]);
     if (l == kLayerH) {
       for (const HeadSeg& hs : kHeadSegs) {
-        RN_TRY(launch_pack_segment(prec, params[hs.param], 256, hs.rows, 256, 0, wf_hi, wf_lo, d.k_tot(), hs.row0, 0, st));
-        RN_TRY(launch_pack_segment(prec, params[hs.param], 256, hs.rows, 256, 1, wt_hi, wt_lo, d.nt_pad, 0, hs.row0, st));
-        e = cudaMemcpyAsync(bias + hs.row0, params[hs.param + 1], hs.rows * 4, cudaMemcpyDeviceToDevice, st);
-        if (e != cudaSuccess) return rn_set_cuda_error(e, __FILE__, __LINE__);
+        seg(params[hs.param], 256, hs.rows, 256, 0, wf_hi, wf_lo, d.k_tot(), hs.row0, 0);
+        seg(params[hs.param], 256, hs.rows, 256, 1, wt_hi, wt_lo, d.nt_pad, 0, hs.row0);
+        copy_f32(params[hs.param + 1], bias + hs.row0, hs.rows);
       }
       continue;
     }
     const int pi = layer_param(l);
     const int kr = d.k1_real + d.k2_real;
-    RN_TRY(launch_pack_segment(prec, params[pi], kr, d.n_real, d.k1_real, 0, wf_hi, wf_lo, d.k_tot(), 0, 0, st));
-    RN_TRY(launch_pack_segment(prec, params[pi], kr, d.n_real, d.k1_real, 1, wt_hi, wt_lo, d.nt_pad, 0, 0, st));
+    seg(params[pi], kr, d.n_real, d.k1_real, 0, wf_hi, wf_lo, d.k_tot(), 0, 0);
+    seg(params[pi], kr, d.n_real, d.k1_real, 1, wt_hi, wt_lo, d.nt_pad, 0, 0);
     if (d.k2_pad) {
-      RN_TRY(launch_pack_segment(prec, params[pi] + d.k1_real, kr, d.n_real, d.k2_real, 0, wf_hi, wf_lo, d.k_tot(), 0, d.k1_pad, st));
-      RN_TRY(launch_pack_segment(prec, params[pi] + d.k1_real, kr, d.n_real, d.k2_real, 1, wt_hi, wt_lo, d.nt_pad, d.k1_pad, 0, st));
+      seg(params[pi] + d.k1_real, kr, d.n_real, d.k2_real, 0, wf_hi, wf_lo, d.k_tot(), 0, d.k1_pad);
+      seg(params[pi] + d.k1_real, kr, d.n_real, d.k2_real, 1, wt_hi, wt_lo, d.nt_pad, d.k1_pad, 0);
     }
-    e = cudaMemcpyAsync(bias, params[pi + 1], d.n_real * 4, cudaMemcpyDeviceToDevice, st);
-    if (e != cudaSuccess) return rn_set_cuda_error(e, __FILE__, __LINE__);
+    copy_f32(params[pi + 1], bias, d.n_real);
   }
-  e = cudaMemcpyAsync(base + lay.wd, params[kParamDensity], 256 * 4, cudaMemcpyDeviceToDevice, st);
-  if (e != cudaSuccess) return rn_set_cuda_error(e, __FILE__, __LINE__);
+  copy_f32(params[kParamDensity], reinterpret_cast<float*>(base + lay.wd), 256);
   if (prec == RN_PREC_BF16 || prec == RN_PREC_FP16) {
     // wcat[j, 0:256] = W_V0[:, j], wcat[j, 256:512] = W_V5[:, 256 + j]  (j = view-net input feature, 201 real)
     void* wc = base + lay.wcat;
     const int p0 = layer_param(kLayerV0), p5 = layer_param(kLayerV0 + 5);
-    RN_TRY(launch_pack_segment(prec, params[p0], kViewReal, 256, kViewReal, 1, wc, nullptr, 512, 0, 0, st));
-    RN_TRY(launch_pack_segment(prec, params[p5] + 256, 256 + kViewReal, 256, kViewReal, 1, wc, nullptr, 512, 0, 256, st));
+    seg(params[p0], kViewReal, 256, kViewReal, 1, wc, nullptr, 512, 0, 0);
+    seg(params[p5] + 256, 256 + kViewReal, 256, kViewReal, 1, wc, nullptr, 512, 0, 256);
   }
+  flush(tw);
+  flush(tb);
+  if (rc_flush != RN_OK) return rc_flush;
   return RN_OK;
 }
 
@@ -866,33 +883,43 @@ extern "C" int rn_mlp_backward(const RnMlpConfig* cfg, const void* packed, const
   float* scratch = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(workspace) + scratch_off);
   cudaStream_t st = c.st;
   auto zero_packed = [&]() -> int {
-    for (int l = 0; l < kNumLayers; ++l) {
-      LayerDef d = layer_def(l);
-      cudaError_t e = cudaMemsetAsync(w.gW[l], 0, (size_t)d.n_pad * d.k_tot() * 4, st);
-      if (e == cudaSuccess) e = cudaMemsetAsync(w.gB[l], 0, (size_t)d.n_pad * 4, st);
-      if (e != cudaSuccess) return rn_set_cuda_error(e, __FILE__, __LINE__);
-    }
+    // gW[0] .. gB[last] are carved back to back: one memset
+    uint8_t* lo = reinterpret_cast<uint8_t*>(w.gW[0]);
+    uint8_t* hi = reinterpret_cast<uint8_t*>(w.gB[kNumLayers - 1]) + align256((size_t)layer_def(kNumLayers - 1).n_pad * 4);
+    cudaError_t e = cudaMemsetAsync(lo, 0, (size_t)(hi - lo), st);
+    if (e != cudaSuccess) return rn_set_cuda_error(e, __FILE__, __LINE__);
     return RN_OK;
   };
   // packed-layout gradients -> parameter gradients (+=); fp16 mode: times 1/S1 (view net, rgb head) or 1/S2 (the rest)
   auto unpack_packed = [&](bool scaled) -> int {
+    UnpackTable t;
+    t.n = 0;
+    int rc = RN_OK;
+    auto add = [&](const float* src, int src_ld, int r0, int c0, int nr, int nc, float* dst, int dst_ld, const float* sc) {
+      if (t.n == kMaxBatchSegs) {
+        if (rc == RN_OK) rc = launch_unpack_add_batch(t, st);
+        t.n = 0;
+      }
+      t.seg[t.n++] = UnpackSeg{src, dst, sc, src_ld, r0, c0, nr, nc, dst_ld};
+    };
     for (int l = 0; l < kNumLayers; ++l) {
       LayerDef d = layer_def(l);
       const float* sc = scaled ? (l >= kLayerV0 ? w.scal + 5 : w.scal + 7) : nullptr;
       if (l == kLayerH) {
         for (const HeadSeg& hs : kHeadSegs) {
-          RN_TRY(launch_unpack_add(w.gW[l], d.k_tot(), hs.row0, 0, hs.rows, 256, grads[hs.param], 256, sc, st));
-          RN_TRY(launch_unpack_add(w.gB[l], d.n_pad, 0, hs.row0, 1, hs.rows, grads[hs.param + 1], hs.rows, sc, st));
+          add(w.gW[l], d.k_tot(), hs.row0, 0, hs.rows, 256, grads[hs.param], 256, sc);
+          add(w.gB[l], d.n_pad, 0, hs.row0, 1, hs.rows, grads[hs.param + 1], hs.rows, sc);
         }
         continue;
       }
       const int pi = layer_param(l);
       const int kr = d.k1_real + d.k2_real;
-      RN_TRY(launch_unpack_add(w.gW[l], d.k_tot(), 0, 0, d.n_real, d.k1_real, grads[pi], kr, sc, st));
-      if (d.k2_pad) RN_TRY(launch_unpack_add(w.gW[l], d.k_tot(), 0, d.k1_pad, d.n_real, d.k2_real, grads[pi] + d.k1_real, kr, sc, st));
-      RN_TRY(launch_unpack_add(w.gB[l], d.n_pad, 0, 0, 1, d.n_real, grads[pi + 1], d.n_real, sc, st));
+      add(w.gW[l], d.k_tot(), 0, 0, d.n_real, d.k1_real, grads[pi], kr, sc);
+      if (d.k2_pad) add(w.gW[l], d.k_tot(), 0, d.k1_pad, d.n_real, d.k2_real, grads[pi] + d.k1_real, kr, sc);
+      add(w.gB[l], d.n_pad, 0, 0, 1, d.n_real, grads[pi + 1], d.n_real, sc);
     }
-    return RN_OK;
+    if (rc == RN_OK) rc = launch_unpack_add_batch(t, st);
+    return rc;
   };
   const bool per_chunk = c.f16;   // the scales are chosen per chunk, so every chunk is unpacked on its own
   if (!per_chunk) RN_TRY(zero_packed());

@@ -622,6 +622,41 @@ __global__ void unpack_add_kernel(const float* __restrict__ src, int src_ld, int
   dst[(size_t)i * dst_ld + j] += scale ? v * *scale : v;
 }
 
+// Table-driven variants: ONE launch packs / unpacks every segment of a NerfMLP (blockIdx.y = segment) instead of one
+// tiny launch per weight block -- ~90 launches per re-pack and ~50 per backward otherwise.
+template <int PREC>
+__global__ void __launch_bounds__(256)
+pack_batch_kernel(const __grid_constant__ PackTable t) {
+  const PackSeg& g = t.seg[blockIdx.y];
+  const int total = g.nr * g.nc;
+  for (int idx = blockIdx.x * 256 + threadIdx.x; idx < total; idx += gridDim.x * 256) {
+    const int i = idx / g.nc, j = idx - i * g.nc;
+    const float v = g.src[(size_t)i * g.src_ld + j];
+    const size_t d = g.transpose ? (size_t)(g.r0 + j) * g.dst_ld + (g.c0 + i) : (size_t)(g.r0 + i) * g.dst_ld + (g.c0 + j);
+    if (PREC == RN_PREC_FP32 || g.f32) {
+      reinterpret_cast<float*>(g.dst_hi)[d] = v;
+    } else if (PREC == RN_PREC_FP16) {
+      reinterpret_cast<uint16_t*>(g.dst_hi)[d] = float_to_f16_bits(v);
+    } else {
+      const uint16_t h = float_to_bf16_bits(v);
+      reinterpret_cast<uint16_t*>(g.dst_hi)[d] = h;
+      if (PREC == RN_PREC_BF16X3 && g.dst_lo) reinterpret_cast<uint16_t*>(g.dst_lo)[d] = float_to_bf16_bits(v - bf16_bits_to_float(h));
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+unpack_add_batch_kernel(const __grid_constant__ UnpackTable t) {
+  const UnpackSeg& g = t.seg[blockIdx.y];
+  const int total = g.nr * g.nc;
+  const float sc = g.scale ? *g.scale : 1.f;
+  for (int idx = blockIdx.x * 256 + threadIdx.x; idx < total; idx += gridDim.x * 256) {
+    const int i = idx / g.nc, j = idx - i * g.nc;
+    const float v = g.src[(size_t)(g.r0 + i) * g.src_ld + g.c0 + j];
+    g.dst[(size_t)i * g.dst_ld + j] += g.scale ? v * sc : v;
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // fp16 mode: dynamic power-of-two scaling of the gradient tiles entering the dgrad chains.
 // scal layout (floats / uint bit patterns): [0] amax view-chain seed, [1] amax scalar-head seed, [2] amax bottleneck
@@ -828,6 +863,23 @@ int launch_pack_segment(int prec, const float* src, int src_ld, int nr, int nc, 
 int launch_unpack_add(const float* src, int src_ld, int r0, int c0, int nr, int nc, float* dst, int dst_ld,
                       const float* scale, cudaStream_t st) {
   unpack_add_kernel<<<nblk((int64_t)nr * nc, 256), 256, 0, st>>>(src, src_ld, r0, c0, nr, nc, dst, dst_ld, scale);
+  RN_CUDA_CHECK_LAUNCH();
+  return RN_OK;
+}
+
+int launch_pack_batch(int prec, const PackTable& t, cudaStream_t st) {
+  if (t.n <= 0) return RN_OK;
+  if (t.n > kMaxBatchSegs) return rn_set_error(RN_ERR_ARG, "pack_batch: too many segments");
+  const dim3 grid(32, (unsigned)t.n);
+  DISPATCH_PREC(prec, (pack_batch_kernel<PREC><<<grid, 256, 0, st>>>(t)));
+  RN_CUDA_CHECK_LAUNCH();
+  return RN_OK;
+}
+int launch_unpack_add_batch(const UnpackTable& t, cudaStream_t st) {
+  if (t.n <= 0) return RN_OK;
+  if (t.n > kMaxBatchSegs) return rn_set_error(RN_ERR_ARG, "unpack_add_batch: too many segments");
+  const dim3 grid(32, (unsigned)t.n);
+  unpack_add_batch_kernel<<<grid, 256, 0, st>>>(t);
   RN_CUDA_CHECK_LAUNCH();
   return RN_OK;
 }

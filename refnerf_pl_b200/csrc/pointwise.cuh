@@ -47,6 +47,25 @@ int launch_pack_segment(int prec, const float* src, int src_ld, int nr, int nc, 
 // grad unpacking: dst[i*dst_ld + j] += src[(r0+i)*src_ld + c0 + j]
 int launch_unpack_add(const float* src, int src_ld, int r0, int c0, int nr, int nc, float* dst, int dst_ld,
                       const float* scale, cudaStream_t st);
+// table-driven pack / unpack: one launch for every weight block of a NerfMLP
+constexpr int kMaxBatchSegs = 64;
+struct PackSeg {      // dst[(r0 + i) * dst_ld + c0 + j] (or transposed) = convert(src[i * src_ld + j]),  i < nr, j < nc
+  const float* src;
+  void* dst_hi;
+  void* dst_lo;       // bf16x3 only
+  int src_ld, nr, nc, transpose, dst_ld, r0, c0;
+  int f32;            // destination is f32 whatever the precision (biases)
+};
+struct PackTable { int n; PackSeg seg[kMaxBatchSegs]; };
+struct UnpackSeg {    // dst[i * dst_ld + j] += src[(r0 + i) * src_ld + c0 + j] * (scale ? *scale : 1)
+  const float* src;
+  float* dst;
+  const float* scale;
+  int src_ld, r0, c0, nr, nc, dst_ld;
+};
+struct UnpackTable { int n; UnpackSeg seg[kMaxBatchSegs]; };
+int launch_pack_batch(int prec, const PackTable& t, cudaStream_t st);
+int launch_unpack_add_batch(const UnpackTable& t, cudaStream_t st);
 // fp16 mode: dynamic power-of-two scaling of the gradient tiles entering the dgrad chains (layout of `scal` in
 // pointwise.cu).  amax kernels accumulate max|x| as a uint bit pattern (zero the slot first).
 int launch_amax_f32(const float* src, int64_t n, uint32_t* dst, cudaStream_t st);

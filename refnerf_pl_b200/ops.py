@@ -396,13 +396,19 @@ def _(tdist, origins, dirs, viewdirs, radii, params, packed, training, prec, srg
             f(n, s, 3), f(n, s, 1), tdist.new_empty((0,), dtype=torch.uint8)]
 
 
+def _param_sizes():
+    lib = _lib.load()
+    return [int(lib.rn_mlp_param_numel(i)) for i in range(_lib.NUM_PARAMS)]
+
+
 @torch.library.custom_op(f'{NS}::mlp_backward', mutates_args=(), device_types='cuda')
 def mlp_backward(tdist: Tensor, origins: Tensor, dirs: Tensor, viewdirs: Tensor, radii: Tensor, packed: Tensor,
                  saved: Tensor, grads: Sequence[Tensor], prec: int, srgb_mapping: bool, srgb_norm: bool, density_bias: float,
                  roughness_bias: float, rgb_premultiplier: float, rgb_bias: float, rgb_padding: float, chunk_rows: int,
-                 gemm_impl: int) -> List[Tensor]:
+                 gemm_impl: int) -> Tensor:
     """grads: [g_density, g_rgb, g_normals_pred, g_grad_pred, g_tint, g_diffuse, g_specular, g_roughness] (empty = 0)
-    -> parameter gradients in rn order."""
+    -> the parameter gradients in rn order, concatenated in one flat fp32 tensor (one zero fill instead of 46; the
+    autograd wrapper hands out per-parameter views)."""
     lib = _lib.load()
     n, s1 = tdist.shape
     s = s1 - 1
@@ -417,19 +423,19 @@ def mlp_backward(tdist: Tensor, origins: Tensor, dirs: Tensor, viewdirs: Tensor,
     g = [_f32c(x) for x in grads]
     pg = lambda t: t.data_ptr() if t.numel() else None
     gs = _lib.RnMlpOutputs(pg(g[0]), pg(g[1]), None, pg(g[2]), pg(g[3]), pg(g[4]), pg(g[5]), pg(g[6]), pg(g[7]))
-    out = [torch.zeros((lib.rn_mlp_param_numel(i),), device=dev, dtype=torch.float32) for i in range(_lib.NUM_PARAMS)]
-    arr = (ctypes.c_void_p * _lib.NUM_PARAMS)(*[t.data_ptr() for t in out])
+    sizes = _param_sizes()
+    flat = torch.zeros((sum(sizes),), device=dev, dtype=torch.float32)
+    arr = (ctypes.c_void_p * _lib.NUM_PARAMS)(*[t.data_ptr() for t in flat.split(sizes)])
     _lib.check(lib.rn_mlp_backward(ctypes.byref(cfg), _ptr(packed), _ptr(tdist), _ptr(origins), _ptr(dirs),
                                    _ptr(viewdirs), _ptr(radii), n, s, ctypes.byref(gs), arr, _ptr(ws), ws_bytes,
                                    _ptr(saved) if saved_bytes else None, saved_bytes, _stream()))
-    return out
+    return flat
 
 
 @mlp_backward.register_fake
 def _(tdist, origins, dirs, viewdirs, radii, packed, saved, grads, prec, srgb_mapping, srgb_norm, density_bias, roughness_bias,
       rgb_premultiplier, rgb_bias, rgb_padding, chunk_rows, gemm_impl):
-    lib = _lib.load()
-    return [tdist.new_empty((lib.rn_mlp_param_numel(i),)) for i in range(_lib.NUM_PARAMS)]
+    return tdist.new_empty((sum(_param_sizes()),))
 
 
 def _mlp_setup(ctx, inputs, output):
@@ -446,8 +452,8 @@ def _mlp_backward(ctx, grads):
     empty = tdist.new_empty((0,))
     order = (0, 1, 3, 4, 5, 6, 7, 8)  # density, rgb, normals_pred, grad_pred, tint, diffuse, specular, roughness
     g = [grads[i] if grads[i] is not None else empty for i in order]
-    pg = mlp_backward(tdist, origins, dirs, viewdirs, radii, packed, saved, g, *ctx.scalars)
-    pg = [t.view(shape) for t, shape in zip(pg, ctx.param_shapes)]
+    flat = mlp_backward(tdist, origins, dirs, viewdirs, radii, packed, saved, g, *ctx.scalars)
+    pg = [t.view(shape) for t, shape in zip(flat.split(_param_sizes()), ctx.param_shapes)]
     return (None, None, None, None, None, pg, None, None) + (None,) * len(ctx.scalars)
 
 

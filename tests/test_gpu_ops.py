@@ -191,6 +191,46 @@ def test_step_losses(ops, gold):
     assert (w_g.grad.cpu() - w_c.grad).abs().max() <= 1e-5
 
 
+@pytest.mark.parametrize('n,s', [(37, 128), (5, 7), (1, 1), (300, 64)])
+@pytest.mark.parametrize('target', ['normals_pred', 'normals'])
+def test_normal_losses_match_oracle(ops, n, s, target):
+    """rn_normal_losses_* vs the oracle's orientation_loss / predicted_normal_loss (train_utils.py:165-204) on the same
+    inputs: per-level loss values and the gradients w.r.t. weights and normals_pred."""
+    from types import SimpleNamespace
+    from refnerf_pl_b200 import train_utils
+    g = torch.Generator().manual_seed(n * 131 + s)
+    unit = lambda x: x / x.norm(dim=-1, keepdim=True)
+    hist_c, hist_g = [], []
+    for lvl in range(2):
+        w = torch.rand(n, s, generator=g) / s
+        nrm = unit(torch.randn(n, s, 3, generator=g))
+        npred = unit(torch.randn(n, s, 3, generator=g))
+        hist_c.append(dict(weights=w.clone().requires_grad_(True), normals=nrm, normals_pred=npred.clone().requires_grad_(True)))
+        hist_g.append(dict(weights=w.to(DEV).requires_grad_(True), normals=nrm.to(DEV),
+                           normals_pred=npred.to(DEV).requires_grad_(True)))
+    vd = unit(torch.randn(n, 3, generator=g))
+    cfg = dict(O.DEFAULT_LOSS_CFG)
+    if target == 'normals_pred':
+        ref = O.orientation_loss(hist_c, vd, cfg) + O.predicted_normal_loss(hist_c, cfg)
+    else:   # the oracle restates the configs' target; the 'normals' target is the same formula on the other tensor
+        ref = O.orientation_loss([dict(h, normals_pred=h['normals']) for h in hist_c], vd, cfg) + O.predicted_normal_loss(hist_c, cfg)
+    ref.backward()
+    c = SimpleNamespace(orientation_loss_target=target, **{k: v for k, v in cfg.items()})
+    out = train_utils.normal_losses(vd.to(DEV), 2, hist_g, c)
+    out.backward()
+    assert abs(float(out) - float(ref)) <= 2e-6 * max(1.0, abs(float(ref)))
+    for hc, hg in zip(hist_c, hist_g):
+        for k in ('weights', 'normals_pred'):
+            a, b = hg[k].grad.cpu(), hc[k].grad
+            assert float((a - b).abs().max()) <= 1e-5 * max(float(b.abs().max()), 1e-12), (k, float((a - b).abs().max()))
+    # and against the unfused torch path of this package on the GPU
+    for h in hist_g:
+        h['weights'].grad = None
+        h['normals_pred'].grad = None
+    unf = train_utils.orientation_loss(vd.to(DEV), 2, hist_g, c) + train_utils.predicted_normal_loss(2, hist_g, c)
+    assert abs(float(unf) - float(out)) <= 2e-6 * max(1.0, abs(float(out)))
+
+
 def test_cpu_tensors_fail_loudly(ops):
     with pytest.raises((NotImplementedError, RuntimeError)):
         ops.distortion(torch.rand(2, 5), torch.rand(2, 4))
