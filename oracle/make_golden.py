@@ -31,11 +31,15 @@ def _load_params(model, p):
     model.nerf_mlp.load_state_dict(sd)
 
 
-def model_case(name, gin_file, rays_np, n_rays, seed, bias_std, weight_scale):
+def model_case(name, gin_file, rays_np, n_rays, seed, bias_std, weight_scale, params_file=None):
     ns, config = ref_import.load(gin_file)
     torch.manual_seed(0)
     model = ns.models.construct_model(ns.utils.dummy_rays(), config)
-    p = O.init_params(seed=seed, bias_std=bias_std, weight_scale=weight_scale)
+    if params_file:   # trained weights (tools/train_parity.py, bf16x3 mode, 2 000 steps on the analytic sphere scene)
+        with np.load(os.path.join(OUT, params_file)) as f:
+            p = {k: torch.tensor(f[k]) for k in f.files}
+    else:
+        p = O.init_params(seed=seed, bias_std=bias_std, weight_scale=weight_scale)
     _load_params(model, p)
     rays_t = {k: torch.tensor(v) for k, v in rays_np.items()}
     rays = ns.utils.Rays(**rays_t)
@@ -43,6 +47,8 @@ def model_case(name, gin_file, rays_np, n_rays, seed, bias_std, weight_scale):
     out = {'meta_seed': np.int64(seed), 'meta_bias_std': np.float64(bias_std),
            'meta_weight_scale': np.float64(weight_scale), 'gt_rgb': _np(gt),
            'param_checksum': np.float64(sum(float(v.double().abs().sum()) for v in p.values()))}
+    if params_file:
+        out['meta_params_file'] = np.array(params_file)
     for k, v in rays_np.items():
         out['rays_' + k] = v
     for mode in ('eval', 'train'):
@@ -143,6 +149,13 @@ def op_cases():
 
 def main():
     os.makedirs(OUT, exist_ok=True)
+    if 'trained' in sys.argv[1:]:
+        # trained-scale case only (needs tests/golden/trained_sphere_params.npz, written on the GPU box by
+        # tools/train_parity.py): rays of one Blender-shaped camera, most of them crossing the learnt sphere
+        n = 32
+        model_case('blender_trained', 'blender_refnerf.gin', synthetic.blender_rays(n, seed=14), n, seed=14,
+                   bias_std=0.0, weight_scale=1.0, params_file='trained_sphere_params.npz')
+        return
     op_cases()
     n = 24
     model_case('blender_init', 'blender_refnerf.gin', synthetic.blender_rays(n, seed=11), n, seed=0,

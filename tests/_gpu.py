@@ -13,6 +13,7 @@ def to_dev(d):
 
 
 GIN_FOR_CASE = {'blender_init': 'blender_refnerf.gin', 'blender_pert': 'blender_refnerf.gin',
+                'blender_trained': 'blender_refnerf.gin',
                 'llff_geom': 'llff_refnerf_geometry_losses.gin'}
 
 

@@ -29,6 +29,23 @@ TOL = {
     # fp16 operands (11-bit): measured <= 1.3e-4 / 2.9e-5 / 2e-3 / 1.2e-5 / 4.3e-3 / 0.10 / 3.5e-2 on the three fixtures
     'fp16':   dict(rel=1e-3, colour=1e-4, npred=5e-3, comp=1e-4, normals_mean=1e-2, normals_p99=0.3, grad=5e-2),
 }
+# Trained-scale weights (fixture blender_trained: 2 000 steps on the sphere scene, sharp density field).  The parity
+# modes keep the north-star gates; 11-bit operands do not at the tail of the distribution (softplus of a raw density
+# that swings over +-50 across the surface amplifies an activation error of 2^-12): measured against bf16x3 on 4 096
+# rays, fp16 per-sample density p99.9 1.2e-2 relative, composited rgb mean 5e-5 / p99 6e-4 / max 8.5e-3.
+TOL_TRAINED = {
+    'fp16':   dict(rel=5e-2, colour=5e-3, npred=2e-2, comp=3e-2, normals_mean=1e-2, normals_p99=0.5, grad=2e-1),
+    'bf16':   dict(rel=5e-1, colour=5e-2, npred=2e-1, comp=2e-1, normals_mean=1e-1, normals_p99=2.0, grad=1.0),
+}
+NAMES = ['blender_init', 'blender_pert', 'llff_geom', 'blender_trained']
+
+
+def _tol(name, precision):
+    if name == 'blender_trained' and precision in TOL_TRAINED:
+        return TOL_TRAINED[precision]
+    return TOL[precision]
+
+
 ALL = bool(os.environ.get('RN_PARITY_ALL'))   # report-only runs: also try plain bf16 on the trained-scale fixtures
 LEVEL1 = 8.0   # level-1 samples sit on fenceposts resampled from level-0 weights: errors compound
 
@@ -52,13 +69,13 @@ def _report(key, rep):
 
 
 @pytest.mark.parametrize('precision', ['fp32', 'bf16x3', 'bf16', 'fp16'])
-@pytest.mark.parametrize('name', ['blender_init', 'blender_pert', 'llff_geom'])
+@pytest.mark.parametrize('name', NAMES)
 @pytest.mark.parametrize('mode', ['eval', 'train'])
 def test_model_vs_reference_fixture(name, precision, mode):
     if precision == 'bf16' and name != 'blender_init' and not ALL:
         pytest.skip('plain bf16 is the throughput mode: gated at reference init only (SURVEY 7.4)')
     g, model, cfg, r, rend, hist = _run(name, precision, mode)
-    tol = TOL[precision]
+    tol = _tol(name, precision)
     rep, bad = {}, []
 
     def gate(key, val, lim):
@@ -73,7 +90,8 @@ def test_model_vs_reference_fixture(name, precision, mode):
         if lvl == 0:
             assert np.array_equal(sd, ref_sd)          # level-0 fenceposts: input independent, bit-exact
         else:
-            gate('sdist1_abs', np.abs(sd - ref_sd).max(), 2e-3 if precision != 'bf16' else 2e-2)
+            loose = precision == 'bf16' or (name == 'blender_trained' and precision == 'fp16')
+            gate('sdist1_abs', np.abs(sd - ref_sd).max(), 2e-2 if loose else 2e-3)
         for k in ('density', 'roughness'):
             e = rel_err(hist[lvl][k].detach().cpu().numpy(), g[f'{mode}_hist{lvl}_{k}'])
             gate(f'{k}{lvl}_rel_p999', np.quantile(e, 0.999), tol['rel'] * f)
@@ -103,7 +121,7 @@ def test_model_vs_reference_fixture(name, precision, mode):
 
 
 @pytest.mark.parametrize('precision', ['fp32', 'bf16x3', 'bf16', 'fp16'])
-@pytest.mark.parametrize('name', ['blender_init', 'blender_pert', 'llff_geom'])
+@pytest.mark.parametrize('name', NAMES)
 def test_gradients_vs_reference_fixture(name, precision):
     if precision == 'bf16' and name != 'blender_init' and not ALL:
         pytest.skip('plain bf16 is gated at reference init only')
@@ -113,7 +131,7 @@ def test_gradients_vs_reference_fixture(name, precision):
     loss, _ = train_utils.total_loss(model, r.viewdirs, r.lossmult, gt, rend, hist, cfg)
     assert abs(float(loss.detach()) - float(g['train_loss'])) <= 1e-3 * abs(float(g['train_loss'])) + 1e-6
     loss.backward()
-    tol = TOL[precision]['grad']
+    tol = _tol(name, precision)['grad']
     rep = {}
     for kname, p in model.nerf_mlp.named_parameters():
         ref_norm = float(g['grad_norm_' + kname])

@@ -73,7 +73,55 @@ def run(precision, steps, n_rays, dev):
             mse += float(((rend[-1]['rgb'] - gt) ** 2).sum())
             cnt += gt.numel()
     psnr = -10 * np.log10(mse / cnt)
+    if precision == 'bf16x3':
+        TRAINED['model'] = model
     return psnr, train_s
+
+
+TRAINED = {}
+
+
+def trained_scale_parity(dev):
+    """Forward parity of the throughput modes at TRAINED weights: the model trained in the parity mode (bf16x3) is
+    evaluated on held-out rays in every mode (NerfMLP.precision is read per call) and compared with its own bf16x3
+    outputs -- per-sample density (relative, 99.9th percentile), per-sample rgb and composited rgb (absolute)."""
+    model = TRAINED.get('model')
+    if model is None:
+        return None
+    r = synthetic.blender_rays(4096, seed=910000)
+    rays = utils.Rays(**{k: torch.from_numpy(v).to(dev) for k, v in r.items()})
+    outs = {}
+    for train_mode in (False, True):
+        model.train(train_mode)
+        for prec in ('bf16x3', 'fp16', 'bf16'):
+            model.nerf_mlp.precision = prec
+            with torch.no_grad():
+                outs[(prec, train_mode)] = model(rays, 1.0, True)
+    model.nerf_mlp.precision = 'bf16x3'
+    res = {}
+    q = lambda x, p: float(torch.quantile(x.flatten()[::3].float(), p))
+    for prec in ('fp16', 'bf16'):
+        (rend, hist), (rend0, hist0) = outs[(prec, False)], outs[('bf16x3', False)]
+        # level 0 samples sit on input-independent fenceposts, so per-sample values are comparable one to one; level 1
+        # samples are re-drawn from the level-0 weights, so there only the composited values are compared
+        d, d0 = hist[0]['density'].double(), hist0[0]['density'].double()
+        rel = (d - d0).abs() / (d0.abs() + 1e-3 * d0.abs().max())
+        nrm, nrm0 = outs[(prec, True)][1][0]['normals'], outs[('bf16x3', True)][1][0]['normals']
+        e = {'level0_density_rel_p999': q(rel, 0.999), 'level0_density_rel_median': q(rel, 0.5),
+             'level0_density_max': float(d0.max()),
+             'level0_sample_rgb_abs_p999': q((hist[0]['rgb'] - hist0[0]['rgb']).abs(), 0.999),
+             'level0_density_normals_mean_abs': float((nrm - nrm0).abs().mean())}
+        for lvl in (0, 1):
+            c = (rend[lvl]['rgb'] - rend0[lvl]['rgb']).abs().max(dim=-1).values
+            e[f'composited_rgb{lvl}_abs'] = {'mean': float(c.mean()), 'p99': q(c, 0.99), 'max': float(c.max())}
+            a_ = (rend[lvl]['acc'] - rend0[lvl]['acc']).abs()
+            e[f'composited_acc{lvl}_abs'] = {'mean': float(a_.mean()), 'p99': q(a_, 0.99), 'max': float(a_.max())}
+        res[prec] = e
+    import os
+    os.makedirs('gpurun_out', exist_ok=True)
+    np.savez_compressed('gpurun_out/trained_bf16x3_params.npz',
+                        **{k: v.detach().cpu().numpy() for k, v in model.nerf_mlp.state_dict().items()})
+    return res
 
 
 def main():
@@ -99,6 +147,7 @@ def main():
     for prec in modes:
         if prec != 'bf16x3' and 'bf16x3' in res:
             res[f'delta_db_{prec}'] = res[prec]['mean_psnr_db'] - res['bf16x3']['mean_psnr_db']
+    res['trained_scale_forward_parity_vs_bf16x3'] = trained_scale_parity(dev)
     print(json.dumps(res))
 
 
