@@ -33,8 +33,11 @@ TOL = {
 # modes keep the north-star gates; 11-bit operands do not at the tail of the distribution (softplus of a raw density
 # that swings over +-50 across the surface amplifies an activation error of 2^-12): measured against bf16x3 on 4 096
 # rays, fp16 per-sample density p99.9 1.2e-2 relative, composited rgb mean 5e-5 / p99 6e-4 / max 8.5e-3.
+# Against the reference fixture (32 rays): composited rgb fp32 3e-7 / bf16x3 2.5e-6 / fp16 1.4e-4 / bf16 8e-4; level-0
+# density p99.9 5e-6 / 1e-4 / 5e-3 / 6e-2; gradients 7e-3 (rgb.bias, a cancellation-dominated sum) / 6e-3 / 6e-2 / 0.65.
 TOL_TRAINED = {
-    'fp16':   dict(rel=5e-2, colour=5e-3, npred=2e-2, comp=3e-2, normals_mean=1e-2, normals_p99=0.5, grad=2e-1),
+    'fp32':   dict(TOL['fp32'], grad=1e-2),
+    'fp16':   dict(rel=2e-2, colour=5e-3, npred=2e-3, comp=1e-3, normals_mean=1e-2, normals_p99=0.5, grad=2e-1),
     'bf16':   dict(rel=5e-1, colour=5e-2, npred=2e-1, comp=2e-1, normals_mean=1e-1, normals_p99=2.0, grad=1.0),
 }
 NAMES = ['blender_init', 'blender_pert', 'llff_geom', 'blender_trained']
@@ -113,7 +116,13 @@ def test_model_vs_reference_fixture(name, precision, mode):
             assert a.shape == b.shape and a.dtype == b.dtype, (k, a.shape, b.shape, a.dtype, b.dtype)
             depthlike = 'distance' in k
             lim = tol['npred'] if k == 'normals_pred' else tol['comp'] * (50 if depthlike else 1)
-            gate(f'rend_{k}{lvl}', np.abs(a - b).max(), lim * f)
+            err = np.abs(a - b)
+            if k == 'distance_mean':
+                # sum(w log t) / max(eps, acc): for rays that hit nothing the weights are rounding noise of
+                # 1 - exp(-sigma delta) (0 or 2^-24 depending on the last bit of exp), so the reference's own value is
+                # noise there (render.py:231-238); compared where the ray has accumulated something
+                err = err[g[f'{mode}_rend{lvl}_acc'] >= 1e-3]
+            gate(f'rend_{k}{lvl}', err.max() if err.size else 0.0, lim * f)
         for k in ('ray_sdist', 'ray_weights', 'ray_rgbs'):
             assert tuple(rend[lvl][k].shape) == g[f'{mode}_rend{lvl}_{k}'].shape
     _report(f'{name}/{precision}/{mode}', rep)
