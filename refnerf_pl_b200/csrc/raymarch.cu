@@ -258,8 +258,22 @@ __device__ __forceinline__ void acc_samples4(const float* __restrict__ v, int la
   acc[1] = w[0] * a.y + w[1] * b.x + w[2] * b.w + w[3] * c.z;
   acc[2] = w[0] * a.z + w[1] * b.y + w[2] * c.x + w[3] * c.w;
 }
+// the same in two steps, so that the forward kernel can put ALL of a ray's loads in flight before the first use
+// (the kernel is bound by load latency: ncu long-scoreboard stalls, profiles/r01_composite_fwd_ncu_full.txt)
+struct Vec12 { float4 a, b, c; };
+__device__ __forceinline__ Vec12 load_samples4(const float* __restrict__ v, int lane) {
+  const float4* p = reinterpret_cast<const float4*>(v) + 3 * lane;
+  Vec12 r;
+  r.a = __ldg(p); r.b = __ldg(p + 1); r.c = __ldg(p + 2);
+  return r;
+}
+__device__ __forceinline__ void acc_loaded4(const Vec12& x, const float w[4], float acc[3]) {
+  acc[0] = w[0] * x.a.x + w[1] * x.a.w + w[2] * x.b.z + w[3] * x.c.y;
+  acc[1] = w[0] * x.a.y + w[1] * x.b.x + w[2] * x.b.w + w[3] * x.c.z;
+  acc[2] = w[0] * x.a.z + w[1] * x.b.y + w[2] * x.c.x + w[3] * x.c.w;
+}
 
-__global__ void __launch_bounds__(kWarps * 32)
+__global__ void __launch_bounds__(kWarps * 32, 5)
 composite_fwd128_kernel(const float* __restrict__ density, const float* __restrict__ tdist, const float* __restrict__ dirs,
                         const float* __restrict__ far_, const float* __restrict__ rgb, const float* __restrict__ diffuse,
                         const float* __restrict__ specular, const float* __restrict__ normals,
@@ -268,19 +282,35 @@ composite_fwd128_kernel(const float* __restrict__ density, const float* __restri
                         float* __restrict__ comp_out, float* __restrict__ extras_out, double* __restrict__ pct_out) {
   constexpr int s = 128;
   __shared__ float sm_t[kWarps][s + 4];
-  __shared__ __align__(16) float sm_w[kWarps][s + 4];   // rows stay 16-byte aligned for the float4 store
   __shared__ float sm_cw[kWarps][s + 4];
   __shared__ float sm_red[kWarps][kFastVals][33];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t ray = (int64_t)blockIdx.x * kWarps + warp;
   if (ray >= n_rays) return;
   float* ts = sm_t[warp];
-  float* ws = sm_w[warp];
   float* cw = sm_cw[warp];
 
   const float4 d4 = __ldg(reinterpret_cast<const float4*>(density + ray * s) + lane);
   const float* tin = tdist + ray * (s + 1);
-  for (int i = lane; i <= s; i += 32) ts[i] = __ldg(tin + i);
+  float tstage[5];
+#pragma unroll
+  for (int i = 0; i < 5; ++i) tstage[i] = (lane + 32 * i <= s) ? __ldg(tin + lane + 32 * i) : 0.f;
+  // every other load of the ray is issued now, before anything waits on the first one
+  const Vec12 c_rgb = load_samples4(rgb + ray * 384, lane);
+  const Vec12 c_dif = load_samples4(diffuse + ray * 384, lane);
+  const Vec12 c_spe = load_samples4(specular + ray * 384, lane);
+  const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  Vec12 c_nrm = {z4, z4, z4}, c_npr = {z4, z4, z4}, c_tin = {z4, z4, z4};
+  float4 r4 = z4;
+  if (extras_out) {
+    if (normals) c_nrm = load_samples4(normals + ray * 384, lane);
+    if (normals_pred) c_npr = load_samples4(normals_pred + ray * 384, lane);
+    if (tint) c_tin = load_samples4(tint + ray * 384, lane);
+    if (roughness) r4 = __ldg(reinterpret_cast<const float4*>(roughness + ray * s) + lane);
+  }
+#pragma unroll
+  for (int i = 0; i < 5; ++i)
+    if (lane + 32 * i <= s) ts[lane + 32 * i] = tstage[i];
   const float dx = dirs[ray * 3 + 0], dy = dirs[ray * 3 + 1], dz = dirs[ray * 3 + 2];
   const float dnorm = sqrtf(dx * dx + dy * dy + dz * dz);
   __syncwarp();
@@ -308,32 +338,24 @@ composite_fwd128_kernel(const float* __restrict__ density, const float* __restri
     logd += w[k] * logf(tmid);
   }
   *(reinterpret_cast<float4*>(weights_out + ray * s) + lane) = make_float4(w[0], w[1], w[2], w[3]);
-  acc_samples4(rgb + ray * 384, lane, w, vals + 0);
-  acc_samples4(diffuse + ray * 384, lane, w, vals + 3);
-  acc_samples4(specular + ray * 384, lane, w, vals + 6);
+  acc_loaded4(c_rgb, w, vals + 0);
+  acc_loaded4(c_dif, w, vals + 3);
+  acc_loaded4(c_spe, w, vals + 6);
   vals[9] = dist;
   vals[10] = acc;
   vals[11] = logd;
   int nvals = 12;
   if (extras_out) {
     nvals = kFastVals;
-    if (normals) acc_samples4(normals + ray * 384, lane, w, vals + 12);
-    else vals[12] = vals[13] = vals[14] = 0.f;
-    if (normals_pred) acc_samples4(normals_pred + ray * 384, lane, w, vals + 15);
-    else vals[15] = vals[16] = vals[17] = 0.f;
-    if (tint) acc_samples4(tint + ray * 384, lane, w, vals + 18);
-    else vals[18] = vals[19] = vals[20] = 0.f;
-    vals[21] = 0.f;
-    if (roughness) {
-      const float4 r4 = __ldg(reinterpret_cast<const float4*>(roughness + ray * s) + lane);
-      vals[21] = w[0] * r4.x + w[1] * r4.y + w[2] * r4.z + w[3] * r4.w;
-    }
+    acc_loaded4(c_nrm, w, vals + 12);      // absent arrays were loaded as zeros
+    acc_loaded4(c_npr, w, vals + 15);
+    acc_loaded4(c_tin, w, vals + 18);
+    vals[21] = w[0] * r4.x + w[1] * r4.y + w[2] * r4.z + w[3] * r4.w;
   }
   // transpose reduction: value v of lane l -> red[v][l]; lane v then sums row v
 #pragma unroll
   for (int v = 0; v < kFastVals; ++v)
     if (v < nvals) sm_red[warp][v][lane] = vals[v];
-  if (pct_out) *(reinterpret_cast<float4*>(ws) + lane) = make_float4(w[0], w[1], w[2], w[3]);
   __syncwarp();
   float total = 0.f;
   if (lane < nvals) {
@@ -357,14 +379,24 @@ composite_fwd128_kernel(const float* __restrict__ density, const float* __restri
   if (extras_out && lane >= 12 && lane < 24) extras_out[ray * 12 + (lane - 12)] = lane < kFastVals ? total : 0.f;
   if (pct_out) {
     // weighted_percentile (stepfun.py:294-307) on t_aug=[tdist, far], w_aug=[weights, bg_w]: see the generic kernel
-    float cr = 0.f, crmax = 0.f;
-    for (int base = 0; base < s; base += 32) {
-      const int i = base + lane;
-      float c = warp_scan_incl(ws[i], lane) + cr;
-      cr = __shfl_sync(RN_FULL, c, 31);
-      c = fmaxf(warp_scan_max(c, lane), crmax);
-      crmax = __shfl_sync(RN_FULL, c, 31);
-      cw[i + 1] = fminf(c, 1.f);
+    // CDF of the weights with a running max (monotone to the last ulp): the lane owns samples 4l..4l+3, so this is
+    // 3 local adds + one warp sum scan + one warp max scan (as in resample128_kernel)
+    {
+      float c[4], r = 0.f;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        r += w[k];
+        c[k] = r;
+      }
+      const float offc = warp_scan_incl(r, lane) - r;
+      float pm = warp_scan_max(offc + c[3], lane);
+      pm = __shfl_up_sync(RN_FULL, pm, 1);
+      if (lane == 0) pm = 0.f;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        pm = fmaxf(pm, offc + c[k]);
+        cw[4 * lane + k + 1] = fminf(pm, 1.f);
+      }
     }
     if (lane == 0) {
       cw[0] = 0.f;
