@@ -447,7 +447,7 @@ def run_b200(args):
         'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
         'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
         'dtype': {'bf16': 'bf16', 'bf16x3': 'bf16x3 (split-bf16, fp32 accumulate)', 'fp32': 'f32',
-                  'fp16': 'f16 (fp16 weights/activations, bf16 gradient operands, fp32 accumulate)'}[args.precision],
+                  'fp16': 'f16 (fp16 weights, activations and dynamically scaled gradient tiles; fp32 accumulate)'}[args.precision],
         'data': 'synthetic',
         'config': {'workload': f'configs/blender_refnerf.gin single training step, {n}-ray batch per GPU, NerfMLP at '
                                'both levels (single_mlp), fwd (incl. density-gradient normals) + losses + bwd + Adam',

@@ -35,8 +35,9 @@ extern "C" {
 #define RN_PREC_FP32 0   /* fp32 FFMA GEMMs (exact-parity anchor)                     */
 #define RN_PREC_BF16 1   /* tcgen05 kind::f16 BF16 operands, fp32 accumulate in TMEM  */
 #define RN_PREC_BF16X3 2 /* split-BF16 (hi/lo, 3 MMAs): ~16-bit mantissa, parity mode */
-#define RN_PREC_FP16 3   /* tcgen05 kind::f16 with FP16 (11-bit) weights and activations, BF16 gradient operands
-                            (mixed a/b formats in the dgrad and wgrad MMAs), fp32 accumulate; fused chains only */
+#define RN_PREC_FP16 3   /* tcgen05 kind::f16 with FP16 (11-bit) weights, activations and gradient tiles (each dgrad
+                            chain runs in its own power-of-two scale chosen on the device), fp32 accumulate;
+                            fused chains only (gemm_impl = 0) */
 
 /* number of parameter tensors of one NerfMLP in rn order (see rn_mlp_param_name) */
 #define RN_MLP_NUM_PARAMS 46

@@ -96,8 +96,8 @@ __device__ __forceinline__ void umma2_commit(uint64_t* bar) {
                "h"((uint16_t)3)
                : "memory");
 }
-// a_f16 / b_f16: the operand is FP16 (format code 0) instead of BF16 (1); the two may differ (fp16 mode: bf16
-// gradients times fp16 weights)
+// a_f16 / b_f16: the operand is FP16 (format code 0) instead of BF16 (1).  Callers keep the two equal: a kind::f16 MMA
+// with a_format != b_format raised an illegal-instruction fault on sm_100a
 __device__ __forceinline__ uint32_t make_idesc2(int n, int a_f16 = 0, int b_f16 = 0) {
   uint32_t d = 0;
   d |= 1u << 4;                       // c_format = F32

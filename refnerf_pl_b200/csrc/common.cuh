@@ -30,8 +30,7 @@ void rn_prof_end(int cls, cudaStream_t st);
 //   RN_PREC_FP32   : hi = float*            (exact-parity SIMT path)
 //   RN_PREC_BF16   : hi = bf16*             (throughput tensor path)
 //   RN_PREC_BF16X3 : hi, lo = bf16*         (split-bf16 tensor path: x ~= hi + lo, 16-bit mantissa)
-//   RN_PREC_FP16   : hi = fp16*             (weights / activations of the fp16 mode; its gradient buffers are bf16
-//                                            and are written / read with PREC = RN_PREC_BF16)
+//   RN_PREC_FP16   : hi = fp16*             (weights, activations and scaled gradient tiles of the fp16 mode)
 // ------------------------------------------------------------------------------------------
 struct ActBuf {
   void* hi;
