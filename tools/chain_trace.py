@@ -5,7 +5,7 @@ import torch
 sys.path.insert(0, '.')
 from bench import build_everything
 from refnerf_pl_b200 import synthetic, utils
-model, cfg = build_everything('bf16', 'cuda')
+model, cfg = build_everything(os.environ.get('PREC', 'fp16'), 'cuda')
 train = len(sys.argv) > 1 and sys.argv[1] == 'train'
 model.train(train)
 r = synthetic.blender_rays(16384, seed=3)
