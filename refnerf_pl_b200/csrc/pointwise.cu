@@ -351,6 +351,19 @@ heads_prologue_bwd_kernel(const float* __restrict__ heads_raw, const float* __re
                           const float* __restrict__ g_density, const float* __restrict__ g_normals_pred,
                           const float* __restrict__ g_grad_pred, const float* __restrict__ g_roughness,
                           const float* __restrict__ g_tint, ActBuf d_scal, const float* __restrict__ dv0_unscale) {
+  // the 73 gradient values of a row (d IDE, d n.v) are staged through shared memory with coalesced reads: one
+  // thread per row reading its own 1 KB-strided row would touch 32 different rows per load instruction
+  __shared__ float tile[kProRows * kProLd];
+  for (int g = threadIdx.x; g < kProRows * 19; g += kProRows) {   // 19 float4 = columns 128..203 of a row
+    const int rr = g / 19, c4 = g - rr * 19;
+    const int64_t lr = (int64_t)blockIdx.x * kProRows + rr;
+    if (lr >= rows) continue;
+    const float4 v = __ldg(reinterpret_cast<const float4*>(dv0f + (size_t)lr * 256 + 128) + c4);
+    float* t = tile + rr * kProLd + c4 * 4;
+    t[0] = v.x;
+    if (c4 < 18) { t[1] = v.y; t[2] = v.z; t[3] = v.w; }          // c4 == 18: only column 200 (= value 72) is used
+  }
+  __syncthreads();
   const int64_t lrow = (int64_t)blockIdx.x * kProRows + threadIdx.x;
   if (lrow >= rows) return;
   const float us = dv0_unscale ? *dv0_unscale : 1.f;   // fp16 mode: dv0f carries the view chain's power-of-two scale
@@ -366,7 +379,7 @@ heads_prologue_bwd_kernel(const float* __restrict__ heads_raw, const float* __re
   HeadsFwd h;
   heads_forward(hr, vd, sc, h);
   // IDE backward
-  const float* gide = dv0f + (size_t)lrow * 256 + 128;
+  const float* gide = tile + threadIdx.x * kProLd;
   double dx = 0, dy = 0, dz = 0, dk = 0;
   ide_core<true>(h.refd[0], h.refd[1], h.refd[2], h.rough, nullptr, 0, gide, 1, dx, dy, dz, dk);
   const float dref[3] = {(float)dx * us, (float)dy * us, (float)dz * us};
