@@ -49,7 +49,8 @@ struct WgradArgs {
   float* out = nullptr;  // dW (fp32), row-major [.., out_ld], element (n, j) at out[n*out_ld + j]
   int out_ld = 0;
   int all_slabs = 0;          // bf16 tcgen05 only: cover every 128-wide slab of dY (n_real <= 256) in one launch
-  float* bias_out = nullptr;  // with all_slabs: also accumulate the bias gradient (column sums of dY) here
+  float* bias_out = nullptr;  // tcgen05 kernels: also accumulate the bias gradient here, bias_out[c] += sum_r dY[r, c] for the
+                              // dY columns this launch covers (all of them with all_slabs, else n0 .. n0+127)
   int x_f16 = 0, dy_f16 = 0;  // with all_slabs: the operands are fp16 instead of bf16 (both or neither: the MMA
                               // rejects mixed a/b formats with an illegal-instruction fault)
   double algo_flops = 0.0;

@@ -252,8 +252,9 @@ struct WgMaps {
 template <int SPLIT>
 __global__ void __launch_bounds__(256, 1)
 wgrad_tc_kernel(const __grid_constant__ WgMaps maps, int64_t m, int64_t rows_per_cta, int n0, int n_real, int kx,
-                int k_real, float* __restrict__ out, int out_ld) {
+                int k_real, float* __restrict__ out, int out_ld, float* __restrict__ bias_out) {
   using C = Cfg<SPLIT>;
+  const bool do_bias = bias_out != nullptr;   // also accumulate bias_out[n0 + f] += sum_r dY[r, n0 + f] (hi + lo planes)
   constexpr int kRowBlk = 64;                       // rows (reduction) per stage
   constexpr int kBoxBytes = kRowBlk * 128;          // one [64 rows x 64 features] TMA box = 8 KB
   extern __shared__ uint8_t smem_raw[];
@@ -275,7 +276,7 @@ wgrad_tc_kernel(const __grid_constant__ WgMaps maps, int64_t m, int64_t rows_per
     tma_prefetch_desc(&maps.x_hi);
     for (int i = 0; i < C::kStages; ++i) {
       mbar_init(&full[i], 1);
-      mbar_init(&empty[i], 1);
+      mbar_init(&empty[i], do_bias ? 5 : 1);   // MMA commit (+ the four epilogue warps that sum the staged dY tile)
     }
     mbar_init(&tfull[0], 1);
     fence_barrier_init();
@@ -338,6 +339,38 @@ wgrad_tc_kernel(const __grid_constant__ WgMaps maps, int64_t m, int64_t rows_per
       umma_commit(&tfull[0]);
     } else if (warp >= 4) {
       const int q = warp - 4;
+      if (do_bias) {
+        // column sums of the dY slab from the staged (128B-swizzled, MN-major) tiles: thread t owns features 2t, 2t+1
+        const int t = threadIdx.x - 128;
+        const bool active = t < 64;
+        const int f = 2 * t;
+        const int box = f >> 6, fi = f & 63;
+        float s0 = 0.f, s1 = 0.f;
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int b = 0; b < nblk; ++b) {
+          mbar_wait(&full[stage], phase);
+          if (active) {
+#pragma unroll
+            for (int pl = 0; pl < C::kPlanes; ++pl) {
+              const uint8_t* base = smem + stage * C::kStageBytes + pl * C::kABytes + box * kBoxBytes + (fi & 7) * 2;
+#pragma unroll 8
+              for (int r = 0; r < kRowBlk; ++r) {
+                const uint32_t v = *reinterpret_cast<const uint32_t*>(base + r * 128 + ((((fi >> 3) ^ (r & 7))) << 4));
+                s0 += __uint_as_float(v << 16);
+                s1 += __uint_as_float(v & 0xffff0000u);
+              }
+            }
+          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&empty[stage]);
+          if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+        }
+        if (active) {
+          if (n0 + f < n_real) atomicAdd(bias_out + n0 + f, s0);
+          if (n0 + f + 1 < n_real) atomicAdd(bias_out + n0 + f + 1, s1);
+        }
+      }
       mbar_wait(&tfull[0], 0);
       tc_fence_after();
       const int nrow = n0 + q * 32 + lane;
@@ -601,11 +634,11 @@ int launch_wgrad_tc(const WgradArgs& g, cudaStream_t st) {
   if (x3) {
     static bool once = false;
     if (!once) { if ((rc = set_smem(wgrad_tc_kernel<3>, Cfg<3>::kSmemBytes))) return rc; once = true; }
-    wgrad_tc_kernel<3><<<grid, 256, Cfg<3>::kSmemBytes, st>>>(maps, g.m, rows_per, g.n0, g.n_real, g.kx, g.k_real, g.out, g.out_ld);
+    wgrad_tc_kernel<3><<<grid, 256, Cfg<3>::kSmemBytes, st>>>(maps, g.m, rows_per, g.n0, g.n_real, g.kx, g.k_real, g.out, g.out_ld, g.bias_out);
   } else {
     static bool once = false;
     if (!once) { if ((rc = set_smem(wgrad_tc_kernel<1>, Cfg<1>::kSmemBytes))) return rc; once = true; }
-    wgrad_tc_kernel<1><<<grid, 256, Cfg<1>::kSmemBytes, st>>>(maps, g.m, rows_per, g.n0, g.n_real, g.kx, g.k_real, g.out, g.out_ld);
+    wgrad_tc_kernel<1><<<grid, 256, Cfg<1>::kSmemBytes, st>>>(maps, g.m, rows_per, g.n0, g.n_real, g.kx, g.k_real, g.out, g.out_ld, g.bias_out);
   }
   rn_prof_end(RN_PROF_WGRAD_TC, st);
   RN_CUDA_CHECK_LAUNCH();

@@ -283,6 +283,8 @@ struct Ctx {
   bool chain = false;  // bf16 / fp16: fused chains
   bool f16 = false;    // fp16 mode: weights, activations and (dynamically scaled) gradient tiles are fp16
   int chain_impl = 0;  // ChainArgs::impl
+  // per-layer tcgen05 wgrad kernels also produce the bias gradient (no separate column-sum pass over dY)
+  bool fused_bias() const { return !chain && impl == 0 && cfg->prec != RN_PREC_FP32; }
   bool algo = true;  // launches carry algorithmic FLOPs (false while recomputing activations in backward)
 };
 
@@ -530,10 +532,12 @@ int wgrad_layer(const Ctx& c, Workspace& w, int l, int64_t rows, ActBuf dy, int 
     g.dy = dy; g.dy_valid = dy_valid; g.n0 = n0; g.n_real = n_real_total;
     g.x = x1; g.x_valid = d.k1_pad; g.kx = d.k1_pad; g.k_real = d.k1_real;
     g.out = w.gW[l]; g.out_ld = d.k_tot();
+    g.bias_out = c.fused_bias() ? w.gB[l] : nullptr;   // per-layer tcgen05 path: the slab's bias gradient rides along
     const int nslab = n_real_total - n0 < 128 ? n_real_total - n0 : 128;
     g.algo_flops = 2.0 * (double)rows * nslab * d.k1_real;
     RN_TRY(launch_wgrad(g, c.st));
     if (d.k2_pad) {
+      g.bias_out = nullptr;
       g.x = x2; g.x_valid = d.k2_pad; g.kx = d.k2_pad; g.k_real = d.k2_real;
       g.out = w.gW[l] + d.k1_pad;
       g.algo_flops = 2.0 * (double)rows * nslab * d.k2_real;
@@ -669,13 +673,13 @@ int backward_chunk(const Ctx& c, Workspace& w, int64_t row0, int64_t rows, const
                           w.d_rgb_raw, w.dcolor, c.st));
   // rgb head
   RN_TRY(wgrad_layer(c, w, kLayerC, rows, w.d_rgb_raw, 16, 3, w.b(8), none));
-  RN_TRY(launch_colsum(prec, w.d_rgb_raw, rows, 16, w.gB[kLayerC], c.st));
+  if (!c.fused_bias()) RN_TRY(launch_colsum(prec, w.d_rgb_raw, rows, 16, w.gB[kLayerC], c.st));
   RN_TRY(dgrad_layer(c, kLayerC, rows, w.d_rgb_raw, 64, 16, none, 0, 0, 0, 256, epi_masked(w.g[0], w.b(8))));
   int cur = 0;
   for (int l = 7; l >= 0; --l) {
     const int L = kLayerV0 + l;
     RN_TRY(wgrad_layer(c, w, L, rows, w.g[cur], 256, 256, l == 0 ? w.v0 : w.b(l), l == 5 ? w.v0 : none));
-    RN_TRY(launch_colsum(prec, w.g[cur], rows, 256, w.gB[L], c.st));
+    if (!c.fused_bias()) RN_TRY(launch_colsum(prec, w.g[cur], rows, 256, w.gB[L], c.st));
     if (l == 5) RN_TRY(dgrad_layer(c, L, rows, w.g[cur], 256, 256, none, 0, 0, 256, 256, epi_f32(w.dv0f, 256, 256, 0)));
     if (l > 0) {
       RN_TRY(dgrad_layer(c, L, rows, w.g[cur], 256, 256, none, 0, 0, 0, 256, epi_masked(w.g[cur ^ 1], w.b(l))));
@@ -695,19 +699,23 @@ int backward_chunk(const Ctx& c, Workspace& w, int64_t row0, int64_t rows, const
     a.prec = prec; a.impl = c.impl; a.m = rows;
     a.x = w.a(8); a.x_valid = 256; a.kx = 256; a.k_real = 256; a.out_ld = d.k_tot();
     a.dy = w.d_bott; a.dy_valid = 128; a.n0 = 0; a.n_real = 128; a.out = w.gW[kLayerH];
+    a.bias_out = c.fused_bias() ? w.gB[kLayerH] : nullptr;
     a.algo_flops = 2.0 * (double)rows * 128 * 256;
     RN_TRY(launch_wgrad(a, c.st));
     a.dy = w.d_scal; a.dy_valid = 16; a.n0 = 0; a.n_real = kHeadScalars; a.out = w.gW[kLayerH] + (size_t)128 * d.k_tot();
+    a.bias_out = c.fused_bias() ? w.gB[kLayerH] + 128 : nullptr;
     a.algo_flops = 2.0 * (double)rows * kHeadScalars * 256;
     RN_TRY(launch_wgrad(a, c.st));
-    RN_TRY(launch_colsum(prec, w.d_bott, rows, 128, w.gB[kLayerH], c.st));
-    RN_TRY(launch_colsum(prec, w.d_scal, rows, 16, w.gB[kLayerH] + 128, c.st));
+    if (!c.fused_bias()) {
+      RN_TRY(launch_colsum(prec, w.d_bott, rows, 128, w.gB[kLayerH], c.st));
+      RN_TRY(launch_colsum(prec, w.d_scal, rows, 16, w.gB[kLayerH] + 128, c.st));
+    }
     RN_TRY(dgrad_layer(c, kLayerH, rows, w.d_bott, 128, 128, w.d_scal, 64, 16, 0, 256, epi_masked(w.g[0], w.a(8))));
   }
   cur = 0;
   for (int l = 7; l >= 0; --l) {
     RN_TRY(wgrad_layer(c, w, l, rows, w.g[cur], 256, 256, l == 0 ? w.x0 : w.a(l), l == 5 ? w.x0 : none));
-    RN_TRY(launch_colsum(prec, w.g[cur], rows, 256, w.gB[l], c.st));
+    if (!c.fused_bias()) RN_TRY(launch_colsum(prec, w.g[cur], rows, 256, w.gB[l], c.st));
     if (l > 0) {
       RN_TRY(dgrad_layer(c, l, rows, w.g[cur], 256, 256, none, 0, 0, 0, 256, epi_masked(w.g[cur ^ 1], w.a(l))));
       cur ^= 1;
