@@ -401,17 +401,22 @@ wgrad_tc_kernel(const __grid_constant__ WgMaps maps, int64_t m, int64_t rows_per
 // of dY accumulating into separate TMEM buffers (X is read once), and the bias gradient (column sums
 // of dY) computed by the otherwise idle epilogue warps straight from the staged dY tiles.
 // ---------------------------------------------------------------------------------------------
-template <int NSLAB>
+// SPLIT = 3 (split-bf16): hi and lo planes of dY and X are staged (32-row blocks so that three stages still fit) and
+// every K step issues hi*hi + lo*hi + hi*lo; the bias gradient sums both planes.
+template <int NSLAB, int SPLIT>
 __global__ void __launch_bounds__(256, 1)
 wgrad2_tc_kernel(const __grid_constant__ WgMaps maps, int64_t m, int64_t rows_per_cta, int n_real, int kx, int k_real,
                  int stages, float* __restrict__ out, int out_ld, float* __restrict__ bias_out, int f16) {
-  constexpr int kRowBlk = 64;
+  constexpr int kPlanes = SPLIT == 3 ? 2 : 1;
+  constexpr int kRowBlk = SPLIT == 3 ? 32 : 64;
   constexpr int kBoxBytes = kRowBlk * 128;
-  constexpr int kDyBytes = 2 * NSLAB * kBoxBytes;
+  constexpr int kDyPlane = 2 * NSLAB * kBoxBytes;     // one plane of the dY tile
+  constexpr int kDyBytes = kPlanes * kDyPlane;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int xboxes = kx / 64;
-  const int stage_bytes = kDyBytes + xboxes * kBoxBytes;
+  const int x_plane = xboxes * kBoxBytes;
+  const int stage_bytes = kDyBytes + kPlanes * x_plane;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + stages * stage_bytes);
   uint64_t* full = bars;
   uint64_t* empty = bars + 8;
@@ -427,6 +432,10 @@ wgrad2_tc_kernel(const __grid_constant__ WgMaps maps, int64_t m, int64_t rows_pe
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&maps.dy_hi);
     tma_prefetch_desc(&maps.x_hi);
+    if (SPLIT == 3) {
+      tma_prefetch_desc(&maps.dy_lo);
+      tma_prefetch_desc(&maps.x_lo);
+    }
     for (int i = 0; i < stages; ++i) {
       mbar_init(&full[i], 1);
       mbar_init(&empty[i], do_bias ? 5 : 1);
@@ -451,8 +460,15 @@ wgrad2_tc_kernel(const __grid_constant__ WgMaps maps, int64_t m, int64_t rows_pe
         const int r0 = (int)(r_begin + (int64_t)b * kRowBlk);
         if (elect_one_sync()) {
           mbar_arrive_expect_tx(&full[stage], stage_tx);
+          // layout per stage: dY_hi | dY_lo | X_hi | X_lo
           for (int i = 0; i < 2 * NSLAB; ++i) tma_load_2d(sbase + i * kBoxBytes, &maps.dy_hi, &full[stage], i * 64, r0);
           for (int i = 0; i < xboxes; ++i) tma_load_2d(sbase + kDyBytes + i * kBoxBytes, &maps.x_hi, &full[stage], i * 64, r0);
+          if (SPLIT == 3) {
+            for (int i = 0; i < 2 * NSLAB; ++i)
+              tma_load_2d(sbase + kDyPlane + i * kBoxBytes, &maps.dy_lo, &full[stage], i * 64, r0);
+            for (int i = 0; i < xboxes; ++i)
+              tma_load_2d(sbase + kDyBytes + x_plane + i * kBoxBytes, &maps.x_lo, &full[stage], i * 64, r0);
+          }
         }
         __syncwarp();
         if (++stage == stages) { stage = 0; phase ^= 1; }
@@ -472,9 +488,14 @@ wgrad2_tc_kernel(const __grid_constant__ WgMaps maps, int64_t m, int64_t rows_pe
             const uint32_t koff = kk * kUmmaK * 128;
             const uint64_t db = make_desc(sb + koff, kBoxBytes, 1024);
 #pragma unroll
-            for (int sl = 0; sl < NSLAB; ++sl)
-              umma_bf16(tmem_base + sl * 256, make_desc(sa + sl * 2 * kBoxBytes + koff, kBoxBytes, 1024), db, idesc,
-                        (b | kk) ? 1u : 0u);
+            for (int sl = 0; sl < NSLAB; ++sl) {
+              const uint64_t da = make_desc(sa + sl * 2 * kBoxBytes + koff, kBoxBytes, 1024);
+              umma_bf16(tmem_base + sl * 256, da, db, idesc, (b | kk) ? 1u : 0u);
+              if (SPLIT == 3) {
+                umma_bf16(tmem_base + sl * 256, make_desc(sa + kDyPlane + sl * 2 * kBoxBytes + koff, kBoxBytes, 1024), db, idesc, 1u);
+                umma_bf16(tmem_base + sl * 256, da, make_desc(sb + x_plane + koff, kBoxBytes, 1024), idesc, 1u);
+              }
+            }
           }
           umma_commit(&empty[stage]);
           if (b == nblk - 1) umma_commit(&tfull[0]);
@@ -496,17 +517,20 @@ wgrad2_tc_kernel(const __grid_constant__ WgMaps maps, int64_t m, int64_t rows_pe
         for (int b = 0; b < nblk; ++b) {
           mbar_wait(&full[stage], phase);
           if (active) {
-            const uint8_t* base = smem + stage * stage_bytes + box * kBoxBytes + (fi & 7) * 2;
+#pragma unroll
+            for (int pl = 0; pl < kPlanes; ++pl) {
+              const uint8_t* base = smem + stage * stage_bytes + pl * kDyPlane + box * kBoxBytes + (fi & 7) * 2;
 #pragma unroll 8
-            for (int r = 0; r < kRowBlk; ++r) {
-              const uint32_t v = *reinterpret_cast<const uint32_t*>(base + r * 128 + ((((fi >> 3) ^ (r & 7))) << 4));
-              if (f16) {
-                const float2 f2 = unpack_f16x2(v);
-                s0 += f2.x;
-                s1 += f2.y;
-              } else {
-                s0 += __uint_as_float(v << 16);
-                s1 += __uint_as_float(v & 0xffff0000u);
+              for (int r = 0; r < kRowBlk; ++r) {
+                const uint32_t v = *reinterpret_cast<const uint32_t*>(base + r * 128 + ((((fi >> 3) ^ (r & 7))) << 4));
+                if (f16) {
+                  const float2 f2 = unpack_f16x2(v);
+                  s0 += f2.x;
+                  s1 += f2.y;
+                } else {
+                  s0 += __uint_as_float(v << 16);
+                  s1 += __uint_as_float(v & 0xffff0000u);
+                }
               }
             }
           }
@@ -578,33 +602,43 @@ int launch_gemm_tc(const GemmArgs& g, cudaStream_t st) {
 
 int launch_wgrad2_tc(const WgradArgs& g, cudaStream_t st) {
   if (g.x_f16 != g.dy_f16) return rn_set_error(RN_ERR_UNSUPPORTED, "wgrad2: dY and X must share one 16-bit format");
+  const bool x3 = g.prec == RN_PREC_BF16X3;
+  if (x3 && g.x_f16) return rn_set_error(RN_ERR_UNSUPPORTED, "wgrad2: the split mode is bf16");
+  const int row_blk = x3 ? 32 : 64;
   WgMaps maps;
   int rc;
-  if ((rc = make_map(&maps.dy_hi, g.dy.hi, g.m, g.dy_valid, g.dy.ld, 64))) return rc;
-  if ((rc = make_map(&maps.x_hi, g.x.hi, g.m, g.x_valid, g.x.ld, 64))) return rc;
-  memset(&maps.dy_lo, 0, sizeof(CUtensorMap));
-  memset(&maps.x_lo, 0, sizeof(CUtensorMap));
+  if ((rc = make_map(&maps.dy_hi, g.dy.hi, g.m, g.dy_valid, g.dy.ld, row_blk))) return rc;
+  if ((rc = make_map(&maps.x_hi, g.x.hi, g.m, g.x_valid, g.x.ld, row_blk))) return rc;
+  if ((rc = make_map(&maps.dy_lo, x3 ? g.dy.lo : nullptr, g.m, g.dy_valid, g.dy.ld, row_blk))) return rc;
+  if ((rc = make_map(&maps.x_lo, x3 ? g.x.lo : nullptr, g.m, g.x_valid, g.x.ld, row_blk))) return rc;
   const int nslab = g.n_real > 128 ? 2 : 1;
-  const int stage_bytes = (2 * nslab + g.kx / 64) * 8192;
+  const int box_bytes = row_blk * 128;
+  const int stage_bytes = (x3 ? 2 : 1) * (2 * nslab + g.kx / 64) * box_bytes;
   int stages = (232448 - 1024 - 512) / stage_bytes;
   if (stages > 6) stages = 6;
   const int smem = stages * stage_bytes + 1024 + 512;
   int ctas = num_sms();
-  int64_t blocks64 = (g.m + 63) / 64;
-  if (ctas > blocks64) ctas = (int)blocks64;
-  int64_t rows_per = ((blocks64 + ctas - 1) / ctas) * 64;
+  int64_t blocks = (g.m + row_blk - 1) / row_blk;
+  if (ctas > blocks) ctas = (int)blocks;
+  int64_t rows_per = ((blocks + ctas - 1) / ctas) * row_blk;
   const unsigned grid = (unsigned)((g.m + rows_per - 1) / rows_per);
   static bool once = false;
   if (!once) {
-    if ((rc = set_smem(wgrad2_tc_kernel<1>, 232448))) return rc;
-    if ((rc = set_smem(wgrad2_tc_kernel<2>, 232448))) return rc;
+    if ((rc = set_smem(wgrad2_tc_kernel<1, 1>, 232448))) return rc;
+    if ((rc = set_smem(wgrad2_tc_kernel<2, 1>, 232448))) return rc;
+    if ((rc = set_smem(wgrad2_tc_kernel<1, 3>, 232448))) return rc;
+    if ((rc = set_smem(wgrad2_tc_kernel<2, 3>, 232448))) return rc;
     once = true;
   }
+  const int f16 = (g.x_f16 && g.dy_f16) ? 1 : 0;
   rn_prof_begin(RN_PROF_WGRAD_TC, st, g.algo_flops);
-  if (nslab == 2)
-    wgrad2_tc_kernel<2><<<grid, 256, smem, st>>>(maps, g.m, rows_per, g.n_real, g.kx, g.k_real, stages, g.out, g.out_ld, g.bias_out, (g.x_f16 && g.dy_f16) ? 1 : 0);
-  else
-    wgrad2_tc_kernel<1><<<grid, 256, smem, st>>>(maps, g.m, rows_per, g.n_real, g.kx, g.k_real, stages, g.out, g.out_ld, g.bias_out, (g.x_f16 && g.dy_f16) ? 1 : 0);
+#define RN_WG2(NS, SP) wgrad2_tc_kernel<NS, SP><<<grid, 256, smem, st>>>(maps, g.m, rows_per, g.n_real, g.kx, g.k_real, stages, g.out, g.out_ld, g.bias_out, f16)
+  if (x3) {
+    if (nslab == 2) RN_WG2(2, 3); else RN_WG2(1, 3);
+  } else {
+    if (nslab == 2) RN_WG2(2, 1); else RN_WG2(1, 1);
+  }
+#undef RN_WG2
   rn_prof_end(RN_PROF_WGRAD_TC, st);
   RN_CUDA_CHECK_LAUNCH();
   return RN_OK;
@@ -615,7 +649,7 @@ int launch_wgrad_tc(const WgradArgs& g, cudaStream_t st) {
   if (g.prec == RN_PREC_FP16 && !g.all_slabs) return rn_set_error(RN_ERR_UNSUPPORTED, "wgrad_tc: the fp16 mode needs all_slabs");
   if (g.prec != RN_PREC_BF16 && g.prec != RN_PREC_BF16X3 && g.prec != RN_PREC_FP16) return rn_set_error(RN_ERR_ARG, "wgrad_tc: bf16 modes only");
   if (g.all_slabs) {
-    if ((g.prec != RN_PREC_BF16 && g.prec != RN_PREC_FP16) || g.n0 != 0 || g.n_real > 256) return rn_set_error(RN_ERR_ARG, "wgrad_tc: all_slabs needs bf16, n0 = 0, n_real <= 256");
+    if (g.n0 != 0 || g.n_real > 256) return rn_set_error(RN_ERR_ARG, "wgrad_tc: all_slabs needs n0 = 0, n_real <= 256");
     return launch_wgrad2_tc(g, st);
   }
   const bool x3 = g.prec == RN_PREC_BF16X3;

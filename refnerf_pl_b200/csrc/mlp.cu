@@ -501,8 +501,9 @@ int forward_chunk(const Ctx& c, Workspace& w, int64_t row0, int64_t rows, const 
 int wgrad_layer(const Ctx& c, Workspace& w, int l, int64_t rows, ActBuf dy, int dy_valid, int n_real_total, ActBuf x1,
                 ActBuf x2) {
   LayerDef d = layer_def(l);
-  if (c.chain) {
-    // bf16 tcgen05: one launch per X source covers all of dY; the first one also produces the bias gradient
+  if (c.chain || c.fused_bias()) {
+    // tcgen05 (bf16 / fp16 / split-bf16): one launch per X source covers all of dY (X is read once, not once per
+    // 128-column slab); the first one also produces the bias gradient
     WgradArgs g;
     g.prec = c.cfg->prec;
     g.impl = c.impl;
@@ -693,23 +694,24 @@ int backward_chunk(const Ctx& c, Workspace& w, int64_t row0, int64_t rows, const
                                    off(g.density, 1), off(g.normals_pred, 3), off(g.grad_pred, 3), off(g.roughness, 1),
                                    off(g.tint, 3), w.d_scal, nullptr, c.st));
   // heads
-  {
+  if (c.fused_bias()) {
+    // [d bottleneck | d scalar heads] live in one 192-wide buffer: one all-slab launch, bias gradient included
+    RN_TRY(wgrad_layer(c, w, kLayerH, rows, w.dheads, kHeadsPad, kHeadsReal, w.a(8), none));
+  } else {
     LayerDef d = layer_def(kLayerH);
     WgradArgs a;
     a.prec = prec; a.impl = c.impl; a.m = rows;
     a.x = w.a(8); a.x_valid = 256; a.kx = 256; a.k_real = 256; a.out_ld = d.k_tot();
     a.dy = w.d_bott; a.dy_valid = 128; a.n0 = 0; a.n_real = 128; a.out = w.gW[kLayerH];
-    a.bias_out = c.fused_bias() ? w.gB[kLayerH] : nullptr;
     a.algo_flops = 2.0 * (double)rows * 128 * 256;
     RN_TRY(launch_wgrad(a, c.st));
     a.dy = w.d_scal; a.dy_valid = 16; a.n0 = 0; a.n_real = kHeadScalars; a.out = w.gW[kLayerH] + (size_t)128 * d.k_tot();
-    a.bias_out = c.fused_bias() ? w.gB[kLayerH] + 128 : nullptr;
     a.algo_flops = 2.0 * (double)rows * kHeadScalars * 256;
     RN_TRY(launch_wgrad(a, c.st));
-    if (!c.fused_bias()) {
-      RN_TRY(launch_colsum(prec, w.d_bott, rows, 128, w.gB[kLayerH], c.st));
-      RN_TRY(launch_colsum(prec, w.d_scal, rows, 16, w.gB[kLayerH] + 128, c.st));
-    }
+    RN_TRY(launch_colsum(prec, w.d_bott, rows, 128, w.gB[kLayerH], c.st));
+    RN_TRY(launch_colsum(prec, w.d_scal, rows, 16, w.gB[kLayerH] + 128, c.st));
+  }
+  {
     RN_TRY(dgrad_layer(c, kLayerH, rows, w.d_bott, 128, 128, w.d_scal, 64, 16, 0, 256, epi_masked(w.g[0], w.a(8))));
   }
   cur = 0;
