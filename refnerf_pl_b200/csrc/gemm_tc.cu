@@ -117,7 +117,7 @@ gemm_tc_kernel(const __grid_constant__ TcMaps maps, int64_t m, int n, int kb1, i
   uint64_t* tempty = tfull + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
   const int64_t num_tiles = (m + kBM - 1) / kBM;
   const int kbt = kb1 + kb2;
 
@@ -140,8 +140,9 @@ gemm_tc_kernel(const __grid_constant__ TcMaps maps, int64_t m, int n, int kb1, i
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 0 && lane == 0) {
-    // ===== TMA producer =====
+  if (warp == 0) {
+    // ===== TMA producer (whole warp runs the loop, one elected lane issues: no divergence waterfall around the
+    // uniform-datapath TMA / MMA instructions, see chain_common.cuh) =====
     const uint32_t stage_tx = (uint32_t)C::kPlanes * (uint32_t)(C::kABytes + n * kBK * 2);
     int stage = 0;
     uint32_t phase = 0;
@@ -150,20 +151,23 @@ gemm_tc_kernel(const __grid_constant__ TcMaps maps, int64_t m, int n, int kb1, i
       for (int kb = 0; kb < kbt; ++kb) {
         mbar_wait(&empty[stage], phase ^ 1);
         uint8_t* sbase = smem + stage * C::kStageBytes;
-        mbar_arrive_expect_tx(&full[stage], stage_tx);
         const bool first = kb < kb1;
         const int ka = (first ? kb : kb - kb1) * kBK;
-        tma_load_2d(sbase, first ? &maps.a1_hi : &maps.a2_hi, &full[stage], ka, m0);
-        tma_load_2d(sbase + C::kPlanes * C::kABytes, &maps.b_hi, &full[stage], kb * kBK, 0);
-        if (SPLIT == 3) {
-          tma_load_2d(sbase + C::kABytes, first ? &maps.a1_lo : &maps.a2_lo, &full[stage], ka, m0);
-          tma_load_2d(sbase + 2 * C::kABytes + C::kBBytes, &maps.b_lo, &full[stage], kb * kBK, 0);
+        if (elect_one_sync()) {
+          mbar_arrive_expect_tx(&full[stage], stage_tx);
+          tma_load_2d(sbase, first ? &maps.a1_hi : &maps.a2_hi, &full[stage], ka, m0);
+          tma_load_2d(sbase + C::kPlanes * C::kABytes, &maps.b_hi, &full[stage], kb * kBK, 0);
+          if (SPLIT == 3) {
+            tma_load_2d(sbase + C::kABytes, first ? &maps.a1_lo : &maps.a2_lo, &full[stage], ka, m0);
+            tma_load_2d(sbase + 2 * C::kABytes + C::kBBytes, &maps.b_lo, &full[stage], kb * kBK, 0);
+          }
         }
+        __syncwarp();
         if (++stage == C::kStages) { stage = 0; phase ^= 1; }
       }
     }
-  } else if (warp == 1 && lane == 0) {
-    // ===== MMA issuer =====
+  } else if (warp == 1) {
+    // ===== MMA issuer (whole warp, one elected lane issues) =====
     const uint32_t idesc = make_idesc(n, 0, 0);
     int stage = 0;
     uint32_t phase = 0;
@@ -180,23 +184,26 @@ gemm_tc_kernel(const __grid_constant__ TcMaps maps, int64_t m, int n, int kb1, i
         const uint32_t sb_hi = sa_hi + C::kPlanes * C::kABytes;
         const uint32_t sa_lo = sa_hi + C::kABytes;
         const uint32_t sb_lo = sb_hi + C::kBBytes;
+        if (elect_one_sync()) {
 #pragma unroll
-        for (int kk = 0; kk < kBK / kUmmaK; ++kk) {
-          const uint32_t koff = kk * kUmmaK * 2;  // bytes inside the 128B swizzle atom
-          const uint64_t da = make_desc(sa_hi + koff, 16, 1024);
-          const uint64_t db = make_desc(sb_hi + koff, 16, 1024);
-          umma_bf16(tmem_d, da, db, idesc, (kb | kk) ? 1u : 0u);
-          if (SPLIT == 3) {
-            const uint64_t dal = make_desc(sa_lo + koff, 16, 1024);
-            const uint64_t dbl = make_desc(sb_lo + koff, 16, 1024);
-            umma_bf16(tmem_d, dal, db, idesc, 1u);
-            umma_bf16(tmem_d, da, dbl, idesc, 1u);
+          for (int kk = 0; kk < kBK / kUmmaK; ++kk) {
+            const uint32_t koff = kk * kUmmaK * 2;  // bytes inside the 128B swizzle atom
+            const uint64_t da = make_desc(sa_hi + koff, 16, 1024);
+            const uint64_t db = make_desc(sb_hi + koff, 16, 1024);
+            umma_bf16(tmem_d, da, db, idesc, (kb | kk) ? 1u : 0u);
+            if (SPLIT == 3) {
+              const uint64_t dal = make_desc(sa_lo + koff, 16, 1024);
+              const uint64_t dbl = make_desc(sb_lo + koff, 16, 1024);
+              umma_bf16(tmem_d, dal, db, idesc, 1u);
+              umma_bf16(tmem_d, da, dbl, idesc, 1u);
+            }
           }
+          umma_commit(&empty[stage]);  // frees the smem slot once the MMAs above have read it
+          if (kb == kbt - 1) umma_commit(&tfull[buf]);   // accumulator complete
         }
-        umma_commit(&empty[stage]);  // frees the smem slot once the MMAs above have read it
+        __syncwarp();
         if (++stage == C::kStages) { stage = 0; phase ^= 1; }
       }
-      umma_commit(&tfull[buf]);      // accumulator complete
       if (++buf == 2) { buf = 0; tphase ^= 1; }
     }
   } else if (warp >= 4) {
