@@ -279,3 +279,29 @@ def test_tiny_and_ragged_batches_match_per_layer_path(n_rays):
             assert torch.equal(ha[lvl][k], hb[lvl][k]), (n_rays, lvl, k)
         assert torch.equal(ra[lvl]['rgb'], rb[lvl]['rgb'])
     assert float((ga - gb).norm()) <= 1e-4 * float(gb.norm()) + 1e-12
+
+
+@pytest.mark.parametrize('n_rays', [1, 5, 130])
+def test_fp16_tiny_batches_track_parity_mode(n_rays):
+    """fp16 chains on ray counts below one super tile: the dynamic gradient scaling (amax / scale / rescale kernels on a
+    handful of rows, possibly all-zero seeds) must give finite gradients that track the parity mode."""
+    from refnerf_pl_b200 import synthetic, train_utils
+    p = O.init_params(seed=9, bias_std=0.1, weight_scale=1.1)
+    rays = synthetic.blender_rays(n_rays, seed=23)
+    gt = torch.tensor(synthetic.gt_rgb(n_rays, 23), device=DEV)
+    res = {}
+    for prec in ('bf16x3', 'fp16'):
+        model, cfg = build_model(prec)
+        load_params(model, p)
+        model.train(True)
+        r = rays_obj(rays)
+        rend, hist = model(r, 1.0, True)
+        loss, _ = train_utils.total_loss(model, r.viewdirs, r.lossmult, gt, rend, hist, cfg)
+        loss.backward()
+        g = torch.cat([q.grad.reshape(-1) for q in model.nerf_mlp.parameters()]).double()
+        assert torch.isfinite(g).all(), prec
+        res[prec] = (float(loss.detach()), g, rend[1]['rgb'].detach())
+    (l3, g3, c3), (l16, g16, c16) = res['bf16x3'], res['fp16']
+    assert abs(l16 - l3) <= 1e-3 * abs(l3) + 1e-6
+    assert float((c16 - c3).abs().max()) <= 1e-3
+    assert float((g16 - g3).norm()) <= 5e-2 * float(g3.norm()) + 1e-12
