@@ -147,8 +147,38 @@ def op_cases():
     print('wrote ops', len(out), 'arrays')
 
 
+def stepfun_util_cases():
+    """stepfun.sample / stepfun.resample as the reference's off-path callers use them (camera_utils.py:266: 1-D float64
+    path resampling; vis.py:144-145: 1-D intervals with [3, m] / [m] values) plus batched float32 inputs."""
+    ns, _ = ref_import.load('blender_refnerf.gin')
+    g = torch.Generator().manual_seed(3)
+    out = {}
+    theta = torch.sort(torch.rand(41, generator=g, dtype=torch.float64) * 6.28).values
+    lengths = torch.rand(40, generator=g, dtype=torch.float64) + 0.1
+    out.update(cam_theta=_np(theta), cam_lengths=_np(lengths),
+               cam_sample=_np(ns.stepfun.sample(theta, torch.log(lengths), 31)))
+    t = torch.sort(torch.rand(7, 33, generator=g)).values
+    wl = torch.randn(7, 32, generator=g)
+    out.update(s_t=_np(t), s_logits=_np(wl), s_lin=_np(ns.stepfun.sample(t, wl, 16)),
+               s_center=_np(ns.stepfun.sample(t, wl, 16, deterministic_center=True)))
+    dist_vis = torch.linspace(0, 1, 65)
+    d = torch.sort(torch.rand(33, generator=g)).values
+    d[0], d[-1] = 0.0, 1.0
+    r = torch.rand(3, 32, generator=g)
+    w = torch.rand(32, generator=g)
+    out.update(r_t=_np(dist_vis), r_tp=_np(d), r_v3=_np(r), r_v1=_np(w))
+    for ua in (False, True):
+        out[f'r_out3_{int(ua)}'] = _np(ns.stepfun.resample(dist_vis, d, r, use_avg=ua))
+        out[f'r_out1_{int(ua)}'] = _np(ns.stepfun.resample(dist_vis, d, w, use_avg=ua))
+    np.savez_compressed(os.path.join(OUT, 'stepfun_utils.npz'), **out)
+    print('wrote stepfun_utils', len(out), 'arrays')
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
+    if 'stepfun_utils' in sys.argv[1:]:
+        stepfun_util_cases()
+        return
     if 'trained' in sys.argv[1:]:
         # trained-scale case only (needs tests/golden/trained_sphere_params.npz, written on the GPU box by
         # tools/train_parity.py): rays of one Blender-shaped camera, most of them crossing the learnt sphere

@@ -42,7 +42,7 @@ def test_metadata_calls(lib):
         assert lib.rn_mlp_param_numel(i) == want, nme
         total += want
     assert total == 1110158            # parameter count of the Ref-NeRF NerfMLP
-    for prec in (0, 1, 2):
+    for prec in (0, 1, 2, 3):
         assert lib.rn_mlp_packed_bytes(prec) > 1_000_000
     cfg = _lib.RnMlpConfig(1, 1, 1, 0.5, -1.0, 1.0, 0.0, 0.001, 4096, 0)
     assert lib.rn_mlp_workspace_bytes(ctypes.byref(cfg), 1) > lib.rn_mlp_workspace_bytes(ctypes.byref(cfg), 0) > 0
