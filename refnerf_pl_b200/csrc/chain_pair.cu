@@ -345,6 +345,7 @@ chain_pair_kernel(const __grid_constant__ PairMaps maps, const __grid_constant__
                 tma_store_commit();
               }
             }
+            if (tr) p.trace[(opcount * 2 + t) * 8 + 5] = clock64();   // arrive + TMA store issue done (lane 0 of warp 4)
             if (L.save) {
               has_group |= 1u << t;
               newer &= ~(1u << t);
@@ -361,6 +362,7 @@ chain_pair_kernel(const __grid_constant__ PairMaps maps, const __grid_constant__
             }
             if (MODE == 0 && L.save_bits && row_ok)
               *(reinterpret_cast<uint4*>(L.save_bits + (size_t)row * 8) + h) = make_uint4(bits_out[0], bits_out[1], bits_out[2], bits_out[3]);
+            if (tr) p.trace[(opcount * 2 + t) * 8 + 6] = clock64();   // ReLU-bit store issued
           } else {
             const GemmEpilogue& ge = p.gepi[L.gepi];
             const int c_end = L.n < h * 128 + 128 ? L.n : h * 128 + 128;
@@ -514,10 +516,10 @@ int launch_chain(const ChainArgs& a, cudaStream_t st) {
     static long long h[64 * 2 * 8];
     cudaMemcpy(h, trace_buf, sizeof(h), cudaMemcpyDeviceToHost);
     const long long t0 = h[0];
-    printf("chain trace (mode %d, %d ops, m=%lld): per (op,tile): mma_wait_done mma_issued | epi_wait_begin epi_wait_end epi_end  [cycles since first]\n", mode, a.num_ops, (long long)a.m);
+    printf("chain trace (mode %d, %d ops, m=%lld): per (op,tile): mma_wait_done mma_issued | epi_wait_begin epi_wait_end epi_end | stores_issued bits_stored  [cycles since first]\n", mode, a.num_ops, (long long)a.m);
     for (int i = 0; i < 40; ++i)
-      printf("  op %2d tile %d: %8lld %8lld | %8lld %8lld %8lld\n", i / 2, i % 2, h[i * 8] - t0, h[i * 8 + 1] - t0, h[i * 8 + 2] - t0, h[i * 8 + 3] - t0,
-             h[i * 8 + 4] - t0);
+      printf("  op %2d tile %d: %8lld %8lld | %8lld %8lld %8lld | %8lld %8lld\n", i / 2, i % 2, h[i * 8] - t0, h[i * 8 + 1] - t0, h[i * 8 + 2] - t0,
+             h[i * 8 + 3] - t0, h[i * 8 + 4] - t0, h[i * 8 + 5] - t0, h[i * 8 + 6] - t0);
   }
   return RN_OK;
 }
