@@ -201,14 +201,15 @@ struct PairOp {
   int gepi;        // kind 1: which global epilogue
   int save;        // hidden: TMA-store the result through maps.save[op]
   const float* bias;       // forward hidden ops / global ops with a bias: [n] floats (padded to a multiple of 4)
-  const uint32_t* mask_bits;   // backward hidden ops: ReLU bits [m, 8]
-  uint32_t* save_bits;         // forward hidden ops: optional ReLU bits of the result [m, 8]
+  const uint32_t* mask_bits;   // backward hidden ops: ReLU bits (8 words per row, layout of relu_bits_index in gemm.cuh)
+  uint32_t* save_bits;         // forward hidden ops: optional ReLU bits of the result
 };
 struct PairParams {
   int num_ops;
   int in_kb;
   int in2_sync_op;   // -1, or: the second input is a save of this launch; the op before its reader orders store -> load
   int a_f16, b_f16;  // operand formats of the MMAs (0 bf16, 1 fp16); the activation tile / outputs use a's
+  int w_planes;      // chain_pair.cu: 2 = every weight K block arrives as a hi and a lo ring item (2 MMAs per K step)
   float seed_scale;  // seed ops: vec * seed_scale
   int64_t m;
   long long* trace;   // debug timeline (RN_CHAIN_TRACE=<launches>): written by CTA 0 only

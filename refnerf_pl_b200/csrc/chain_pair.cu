@@ -43,6 +43,7 @@ struct PairMaps {
   CUtensorMap in;
   CUtensorMap in2;
   CUtensorMap w[kMaxOps];
+  CUtensorMap w2[kMaxOps];   // lo plane of split-bf16 weights (w_planes = 2)
   CUtensorMap save[kMaxOps];
 };
 
@@ -119,6 +120,10 @@ chain_pair_kernel(const __grid_constant__ PairMaps maps, const __grid_constant__
         for (int kb = 0; kb < L.kb_act; ++kb) {
           const uint32_t s = acquire(0);
           load(s, (uint32_t)L.n * 128u, &maps.w[l], kb * kBK, (int)rank * nh);
+          if (p.w_planes == 2) {
+            const uint32_t s2 = acquire(0);
+            load(s2, (uint32_t)L.n * 128u, &maps.w2[l], kb * kBK, (int)rank * nh);
+          }
         }
         // a second input that is a save of this launch: its TMA stores must have completed (see the epilogue)
         if (L.kb_in && L.in2 && p.in2_sync_op >= 0) mbar_wait(in2_ready, st_iter & 1u);
@@ -130,6 +135,10 @@ chain_pair_kernel(const __grid_constant__ PairMaps maps, const __grid_constant__
             if (t == 0) {
               const uint32_t sw = acquire(0);
               load(sw, (uint32_t)L.n * 128u, &maps.w[l], (L.kb_act + kb) * kBK, (int)rank * nh);
+              if (p.w_planes == 2) {
+                const uint32_t sw2 = acquire(0);
+                load(sw2, (uint32_t)L.n * 128u, &maps.w2[l], (L.kb_act + kb) * kBK, (int)rank * nh);
+              }
             }
           }
         }
@@ -172,6 +181,54 @@ chain_pair_kernel(const __grid_constant__ PairMaps maps, const __grid_constant__
         const uint32_t idesc = make_idesc2(L.n, p.a_f16, p.b_f16);
         const uint32_t free_parity = (nreal & 1u) ^ 1u;   // epilogue of the previous GEMM op on this tile done
         ++nreal;
+        if (p.w_planes == 2) {
+          // split-bf16 weights against one-plane activations: every K block is a (hi, lo) pair of ring items and
+          // both row tiles consume it before the next one (eight resident items would not fit the ring), so the two
+          // accumulators fill side by side: dY * W_hi + dY * W_lo
+          for (int kb = 0; kb < L.kb_act; ++kb) {
+            wait_full(pos);
+            wait_full(pos + 1);
+            tc_fence_after();
+            for (int t = 0; t < 2; ++t) {
+              if (kb == 0) {
+                mbar_wait_cluster(&acc_free[t], free_parity);
+                if (seed_pending) mbar_wait_cluster(&seed_done[t], (nseed - 1u) & 1u);
+                tc_fence_after();
+              }
+              const uint32_t tmem_d = tmem_base + (uint32_t)t * 256u;
+              const uint32_t sa = smem_base + t * kActBytes + kb * kBlkBytes;
+              mma_kblock(tmem_d, sa, stage_addr(pos), idesc, kb == 0, t == 1 ? &ring_empty[pos % kRingStages] : nullptr, nullptr,
+                         nullptr);
+              mma_kblock(tmem_d, sa, stage_addr(pos + 1), idesc, false, t == 1 ? &ring_empty[(pos + 1) % kRingStages] : nullptr,
+                         (kb == L.kb_act - 1 && !L.kb_in) ? &acc_full[t] : nullptr, nullptr);
+            }
+            pos += 2;
+          }
+          if (L.kb_act) seed_pending = false;
+          for (int kb = 0; kb < L.kb_in; ++kb) {
+            const uint32_t px0 = pos, pwh = pos + 1, pwl = pos + 2, px1 = pos + 3;
+            pos += 4;
+            for (int t = 0; t < 2; ++t) {
+              if (!L.kb_act && kb == 0) {
+                mbar_wait_cluster(&acc_free[t], free_parity);
+                tc_fence_after();
+              }
+              const uint32_t px = t ? px1 : px0;
+              wait_full(px);
+              if (t == 0) {
+                wait_full(pwh);
+                wait_full(pwl);
+              }
+              tc_fence_after();
+              const uint32_t tmem_d = tmem_base + (uint32_t)t * 256u;
+              mma_kblock(tmem_d, stage_addr(px), stage_addr(pwh), idesc, !L.kb_act && kb == 0,
+                         t == 1 ? &ring_empty[pwh % kRingStages] : nullptr, nullptr, nullptr);
+              mma_kblock(tmem_d, stage_addr(px), stage_addr(pwl), idesc, false, &ring_empty[px % kRingStages],
+                         t == 1 ? &ring_empty[pwl % kRingStages] : nullptr, kb == L.kb_in - 1 ? &acc_full[t] : nullptr);
+            }
+          }
+          continue;
+        }
         // --- K blocks from the resident activation tiles: tile 0 then tile 1 over the same weight stages
         const uint32_t pos_w = pos;
         for (int t = 0; t < 2; ++t) {
@@ -231,11 +288,15 @@ chain_pair_kernel(const __grid_constant__ PairMaps maps, const __grid_constant__
     bool any_store = false;
     uint4 bits_next = make_uint4(0, 0, 0, 0);
     auto load_bits = [&](int64_t st, int l, int t) -> uint4 {
-      // ReLU bits of this thread's row for op l (this warp's 128 columns = words 4h .. 4h+3)
+      // ReLU bits of this thread's row for op l (this warp's 128 columns = words 4h .. 4h+3; relu_bits_index layout:
+      // the 32 rows of the warp are contiguous per word, so each of the four loads is one 128-byte line)
       uint4 b = make_uint4(0, 0, 0, 0);
       if (l < p.num_ops && st < num_super && p.op[l].kind != 1) {
-        const int64_t row = st * 512 + t * 256 + (int64_t)rank * 128 + r_in_tile;
-        if (row < p.m) b = __ldg(reinterpret_cast<const uint4*>(p.op[l].mask_bits + (size_t)row * 8) + h);
+        const int64_t row_w = st * 512 + t * 256 + (int64_t)rank * 128 + q * 32;
+        if (row_w < p.m) {
+          const uint32_t* bp = p.op[l].mask_bits + (size_t)(row_w >> 5) * 256 + (4 * h) * 32 + lane;
+          b = make_uint4(__ldg(bp), __ldg(bp + 32), __ldg(bp + 64), __ldg(bp + 96));
+        }
       }
       return b;
     };
@@ -360,8 +421,11 @@ chain_pair_kernel(const __grid_constant__ PairMaps maps, const __grid_constant__
                 mbar_arrive(in2_ready);
               }
             }
-            if (MODE == 0 && L.save_bits && row_ok)
-              *(reinterpret_cast<uint4*>(L.save_bits + (size_t)row * 8) + h) = make_uint4(bits_out[0], bits_out[1], bits_out[2], bits_out[3]);
+            if (MODE == 0 && L.save_bits && row - lane < p.m) {
+              uint32_t* bp = L.save_bits + (size_t)((row - lane) >> 5) * 256 + (4 * h) * 32 + lane;
+#pragma unroll
+              for (int g = 0; g < 4; ++g) bp[32 * g] = bits_out[g];
+            }
             if (tr) p.trace[(opcount * 2 + t) * 8 + 6] = clock64();   // ReLU-bit store issued
           } else {
             const GemmEpilogue& ge = p.gepi[L.gepi];
@@ -409,10 +473,10 @@ chain_pair_kernel(const __grid_constant__ PairMaps maps, const __grid_constant__
 }  // namespace
 
 int launch_chain(const ChainArgs& a, cudaStream_t st) {
-  if (a.impl == 1) {
-    if (a.act_f16 || a.w_f16) return rn_set_error(RN_ERR_UNSUPPORTED, "chain_ts: bf16 operands only");
-    return launch_chain_ts(a, st);
-  }
+  if (a.impl == 2) return launch_chain_x3(a, st);
+  if (a.impl != 0) return rn_set_error(RN_ERR_ARG, "chain: unknown implementation");
+  if (a.w_planes != 1 && a.w_planes != 2) return rn_set_error(RN_ERR_ARG, "chain: w_planes is 1 or 2");
+  if (a.w_planes == 2 && (a.act_f16 || a.w_f16)) return rn_set_error(RN_ERR_UNSUPPORTED, "chain: split weights are bf16");
   if (a.m <= 0) return RN_OK;
   if (a.act_f16 != a.w_f16) return rn_set_error(RN_ERR_UNSUPPORTED, "chain: activations and weights must share one 16-bit format");
   if (a.num_ops < 1 || a.num_ops > kMaxOps) return rn_set_error(RN_ERR_ARG, "chain: 1..12 ops");
@@ -428,12 +492,14 @@ int launch_chain(const ChainArgs& a, cudaStream_t st) {
   p.in2_sync_op = -1;
   p.a_f16 = a.act_f16;
   p.b_f16 = a.w_f16;
+  p.w_planes = a.w_planes;
   p.seed_scale = a.seed_scale;
   p.num_ops = a.num_ops;
   p.in_kb = a.in.hi ? a.in_cols / kBK : 0;
   p.m = a.m;
   for (int l = 0; l < kMaxOps; ++l) {
     memset(&maps.w[l], 0, sizeof(CUtensorMap));
+    memset(&maps.w2[l], 0, sizeof(CUtensorMap));
     memset(&maps.save[l], 0, sizeof(CUtensorMap));
     if (l >= a.num_ops) continue;
     const ChainOpArgs& L = a.op[l];
@@ -463,6 +529,10 @@ int launch_chain(const ChainArgs& a, cudaStream_t st) {
     }
     const int ktot = (L.kb_act + L.kb_in) * kBK;
     if ((rc = tc::make_map(&maps.w[l], L.w, L.n, ktot, L.w_ld, L.n / 2))) return rc;
+    if (a.w_planes == 2) {
+      if (!L.w_lo) return rn_set_error(RN_ERR_ARG, "chain: missing lo weight plane");
+      if ((rc = tc::make_map(&maps.w2[l], L.w_lo, L.n, ktot, L.w_ld, L.n / 2))) return rc;
+    }
     PairOp& o = p.op[l];
     o.n = L.n; o.kb_act = L.kb_act; o.kb_in = L.kb_in; o.in2 = L.in2;
     o.kind = L.kind; o.gepi = L.gepi; o.bias = L.bias;

@@ -70,11 +70,12 @@ struct ChainOpArgs {
   int mode = 0;              // hidden: 0 bias + ReLU, 1 ReLU mask
   int gepi = 0;              // global: epilogue index (0/1)
   const void* w = nullptr;   // bf16 weights [n, (kb_act + kb_in) * 64] K-major
+  const void* w_lo = nullptr;   // lo plane of split-bf16 weights (chain_x3.cu; chain_pair.cu with ChainArgs::w_planes = 2)
   int w_ld = 0;
   const float* bias = nullptr;
-  const uint32_t* mask_bits = nullptr;  // mode 1: ReLU bits of the matching forward activation, [m, 8] words
+  const uint32_t* mask_bits = nullptr;  // mode 1: ReLU bits of the matching forward activation (layout: relu_bits_index)
   void* save_hi = nullptr;              // optional bf16 [m,256] copy of the hidden result (TMA store)
-  uint32_t* save_bits = nullptr;        // mode 0: optional ReLU bits of the result, [m, 8] words
+  uint32_t* save_bits = nullptr;        // mode 0: optional ReLU bits of the result (8 words per row, relu_bits_index)
 };
 struct ChainArgs {
   int64_t m = 0;
@@ -83,7 +84,9 @@ struct ChainArgs {
   int in_valid = 0;          // valid columns of the input buffer (beyond: zero)
   ActBuf in2 = {nullptr, nullptr, 0};   // optional second input tensor [m, 64*k] (may be a save_hi buffer of an earlier op
   int in2_cols = 0, in2_valid = 0;      // of the same launch: the kernel orders the TMA store before the TMA load)
-  int impl = 0;              // 0: chain_pair.cu (SS operands, two row tiles), 1: chain_ts.cu (A operand in TMEM)
+  int impl = 0;              // 0: chain_pair.cu (one-plane activations, two row tiles), 2: chain_x3.cu (split-bf16 activations
+                             // AND weights, 3 MMAs per K step, one row tile, K-block-granular epilogue hand-off)
+  int w_planes = 1;          // chain_pair.cu: 2 = split-bf16 weights against one-plane activations (2 MMAs per K step)
   int act_f16 = 0;           // chain_pair.cu: inputs, activation tile and activation-format outputs are fp16 (else bf16)
   int w_f16 = 0;             // chain_pair.cu: weights are fp16 (else bf16); must equal act_f16 (mixed a/b formats fault)
   float seed_scale = 1.f;    // chain_pair.cu: factor applied to the vector of a seed op
@@ -93,7 +96,11 @@ struct ChainArgs {
   double algo_flops = 0.0;
 };
 int launch_chain(const ChainArgs& a, cudaStream_t st);      // chain_pair.cu: CTA pairs, cta_group::2, two row tiles in flight
-int launch_chain_ts(const ChainArgs& a, cudaStream_t st);   // chain_ts.cu: CTA pairs, A operand in TMEM, column halves
+int launch_chain_x3(const ChainArgs& a, cudaStream_t st);   // chain_x3.cu: CTA pairs, split-bf16 operands, one row tile
+// ReLU bit masks: 8 words per row (word w = columns [32w, 32w+32)), stored so that the 32 rows a warp owns are
+// contiguous per word: word index of (row, w) = ((row / 32) * 8 + w) * 32 + row % 32.  Buffers are sized for rows
+// rounded up to a multiple of 32.
+inline size_t relu_bits_bytes(int64_t rows) { return (size_t)((rows + 31) / 32) * 32 * 32; }
 
 int launch_gemm(const GemmArgs& g, cudaStream_t st);
 int launch_wgrad(const WgradArgs& g, cudaStream_t st);

@@ -57,6 +57,7 @@ struct PackedLayout {
   size_t wf_plane[kNumLayers], wt_plane[kNumLayers];  // byte stride between hi and lo planes
   size_t wd;
   size_t wcat;   // bf16 [256, 512]: [Wt(V0) | Wt(V5)[256:512, :]] -- d v0 = [dY0 | dY5] * wcat^T in ONE dgrad op (fused chains)
+  size_t wcat_plane;   // byte stride between its hi and lo planes (split-bf16)
   size_t total;
 };
 
@@ -78,7 +79,8 @@ inline PackedLayout packed_layout(int prec) {
   p.wd = off;
   off += align256(256 * 4);
   p.wcat = off;
-  off += align256((size_t)256 * 512 * 2);
+  p.wcat_plane = align256((size_t)256 * 512 * 2);
+  off += p.wcat_plane * pl;
   p.total = off;
   return p;
 }

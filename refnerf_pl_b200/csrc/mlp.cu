@@ -173,15 +173,17 @@ struct Saved {
   float *heads_raw, *rgb_raw;
   size_t bytes;
 };
-Saved carve_saved(void* base, int prec, int64_t rows) {
+// `hprec`: format of the hidden activations (the fused split-bf16 chains keep only their hi plane: wgrad runs on
+// bf16 operands and the dgrad chains need the ReLU bits only)
+Saved carve_saved(void* base, int prec, int hprec, int64_t rows) {
   Saved s;
   Carver c{reinterpret_cast<uint8_t*>(base)};
   s.x0 = c.act(prec, rows, kEncPad);
   s.v0 = c.act(prec, rows, kViewPad);
-  for (int i = 0; i < 8; ++i) s.sp[i] = c.act(prec, rows, 256);
-  for (int i = 0; i < 8; ++i) s.vw[i] = c.act(prec, rows, 256);
-  for (int i = 0; i < 8; ++i) s.msp[i] = (uint32_t*)c.take((size_t)rows * 32);
-  for (int i = 0; i < 8; ++i) s.mvw[i] = (uint32_t*)c.take((size_t)rows * 32);
+  for (int i = 0; i < 8; ++i) s.sp[i] = c.act(hprec, rows, 256);
+  for (int i = 0; i < 8; ++i) s.vw[i] = c.act(hprec, rows, 256);
+  for (int i = 0; i < 8; ++i) s.msp[i] = (uint32_t*)c.take(relu_bits_bytes(rows));
+  for (int i = 0; i < 8; ++i) s.mvw[i] = (uint32_t*)c.take(relu_bits_bytes(rows));
   s.heads_raw = (float*)c.take((size_t)rows * 16 * 4);
   s.rgb_raw = (float*)c.take((size_t)rows * 4 * 4);
   s.bytes = c.off;
@@ -195,40 +197,43 @@ ActBuf rows_from(ActBuf b, int prec, int64_t row0) {
 
 // mode 0: eval forward, 1: training forward (+normals pass), 2: backward.  With `external` the chain inputs,
 // hidden activations and raw head outputs live in a Saved region (see use_saved) instead of the workspace.
-Workspace carve(void* base, int prec, int64_t rc, int mode, bool external = false) {
+// `x3chain`: fused split-bf16 chains -- chain inputs in two planes, hidden activations and every gradient tile in
+// one bf16 plane
+Workspace carve(void* base, int prec, int64_t rc, int mode, bool external = false, bool x3chain = false) {
   Workspace w;
   Carver c{reinterpret_cast<uint8_t*>(base)};
+  const int hprec = x3chain ? RN_PREC_BF16 : prec;
   w.nsp = (mode == 0 && !external) ? 2 : 8;
   w.nvw = (mode == 2 || external) ? 8 : 2;
   if (!external) {
     w.x0 = c.act(prec, rc, kEncPad);
     w.v0 = c.act(prec, rc, kViewPad);
-    for (int i = 0; i < w.nsp; ++i) w.sp[i] = c.act(prec, rc, 256);
-    for (int i = 0; i < w.nvw; ++i) w.vw[i] = c.act(prec, rc, 256);
-    for (int i = 0; i < 8; ++i) w.msp[i] = w.nsp == 8 ? (uint32_t*)c.take((size_t)rc * 32) : nullptr;
-    for (int i = 0; i < 8; ++i) w.mvw[i] = w.nvw == 8 ? (uint32_t*)c.take((size_t)rc * 32) : nullptr;
+    for (int i = 0; i < w.nsp; ++i) w.sp[i] = c.act(hprec, rc, 256);
+    for (int i = 0; i < w.nvw; ++i) w.vw[i] = c.act(hprec, rc, 256);
+    for (int i = 0; i < 8; ++i) w.msp[i] = w.nsp == 8 ? (uint32_t*)c.take(relu_bits_bytes(rc)) : nullptr;
+    for (int i = 0; i < 8; ++i) w.mvw[i] = w.nvw == 8 ? (uint32_t*)c.take(relu_bits_bytes(rc)) : nullptr;
     w.heads_raw = (float*)c.take((size_t)rc * 16 * 4);
     w.rgb_raw = (float*)c.take((size_t)rc * 4 * 4);
   }
-  if (mode == 1) {
+  if (mode == 1 && !x3chain) {   // (the fused chains keep the running gradient tile on chip)
     w.g[0] = c.act(prec, rc, 256);
     w.g[1] = c.act(prec, rc, 256);
   }
   if (mode >= 1) w.gx0 = (float*)c.take((size_t)rc * 128 * 4);
   if (mode == 2) {
-    for (int i = 0; i < 8; ++i) w.gs[i] = c.act(prec, rc, 256);   // dY of the 8 layers of the net being back-propagated
+    for (int i = 0; i < 8; ++i) w.gs[i] = c.act(hprec, rc, 256);   // dY of the 8 layers of the net being back-propagated
     w.g[0] = w.gs[0];
     w.g[1] = w.gs[1];
     w.dv0f = (float*)c.take((size_t)rc * 256 * 4);
     w.dcolor = (float*)c.take((size_t)rc * 8 * 4);
     // d heads = [d bottleneck (128) | d scalar heads (11, padded to 16) | unused]: one 192-wide buffer so the
     // heads dgrad reads it as a single K extent
-    w.dheads = c.act(prec, rc, 192);
+    w.dheads = c.act(hprec, rc, 192);
     w.d_bott = w.dheads;
     w.d_scal = w.dheads;
-    w.d_scal.hi = reinterpret_cast<uint8_t*>(w.dheads.hi) + 128 * elem_bytes(prec);
+    w.d_scal.hi = reinterpret_cast<uint8_t*>(w.dheads.hi) + 128 * elem_bytes(hprec);
     if (w.dheads.lo) w.d_scal.lo = reinterpret_cast<uint8_t*>(w.dheads.lo) + 128 * 2;
-    w.d_rgb_raw = c.act(prec, rc, 16);
+    w.d_rgb_raw = c.act(hprec, rc, 16);
     w.stage16 = (float*)c.take((size_t)rc * 16 * 4);
     w.scal = (float*)c.take(256);
     for (int l = 0; l < kNumLayers; ++l) {
@@ -241,18 +246,21 @@ Workspace carve(void* base, int prec, int64_t rc, int mode, bool external = fals
   return w;
 }
 // point the chunk's activation buffers at rows [row0, ..) of the saved region
-void use_saved(Workspace& w, const Saved& s, int prec, int64_t row0) {
+void use_saved(Workspace& w, const Saved& s, int prec, int hprec, int64_t row0) {
   w.x0 = rows_from(s.x0, prec, row0);
   w.v0 = rows_from(s.v0, prec, row0);
   for (int i = 0; i < 8; ++i) {
-    w.sp[i] = rows_from(s.sp[i], prec, row0);
-    w.vw[i] = rows_from(s.vw[i], prec, row0);
-    w.msp[i] = s.msp[i] + (size_t)row0 * 8;
+    w.sp[i] = rows_from(s.sp[i], hprec, row0);
+    w.vw[i] = rows_from(s.vw[i], hprec, row0);
+    w.msp[i] = s.msp[i] + (size_t)row0 * 8;   // row0 is a multiple of 128: whole 32-row groups
     w.mvw[i] = s.mvw[i] + (size_t)row0 * 8;
   }
   w.heads_raw = s.heads_raw + (size_t)row0 * 16;
   w.rgb_raw = s.rgb_raw + (size_t)row0 * 4;
 }
+
+inline bool cfg_x3chain(const RnMlpConfig* cfg) { return cfg->prec == RN_PREC_BF16X3 && cfg->gemm_impl == 0; }
+inline int cfg_hprec(const RnMlpConfig* cfg) { return cfg_x3chain(cfg) ? RN_PREC_BF16 : cfg->prec; }
 
 struct Packed {
   const uint8_t* base;
@@ -270,6 +278,7 @@ struct Packed {
   const float* bias(int l) const { return reinterpret_cast<const float*>(base + lay.bias[l]); }
   const float* wd() const { return reinterpret_cast<const float*>(base + lay.wd); }
   const void* wcat() const { return base + lay.wcat; }
+  const void* wcat_lo() const { return prec == RN_PREC_BF16X3 ? base + lay.wcat + lay.wcat_plane : nullptr; }
 };
 
 struct Ctx {
@@ -280,9 +289,12 @@ struct Ctx {
   cudaStream_t st;
   MlpScalars sc;
   int impl;
-  bool chain = false;  // bf16 / fp16: fused chains
+  bool chain = false;  // bf16 / fp16 / split-bf16 with gemm_impl 0: fused chains
   bool f16 = false;    // fp16 mode: weights, activations and (dynamically scaled) gradient tiles are fp16
-  int chain_impl = 0;  // ChainArgs::impl
+  bool x3 = false;     // fused split-bf16: forward and normals chains on chain_x3.cu (3 MMAs per K step), loss backward
+                       // with one-plane bf16 gradient tiles against split weights (2 MMAs), bf16 wgrad
+  int chain_impl = 0;  // ChainArgs::impl of the forward / normals chains
+  int hprec() const { return x3 ? RN_PREC_BF16 : cfg->prec; }   // format of hidden activations and gradient tiles
   // per-layer tcgen05 wgrad kernels also produce the bias gradient (no separate column-sum pass over dY)
   bool fused_bias() const { return !chain && impl == 0 && cfg->prec != RN_PREC_FP32; }
   bool algo = true;  // launches carry algorithmic FLOPs (false while recomputing activations in backward)
@@ -369,6 +381,7 @@ int chain_layers(const Ctx& c, int l0, int lh, int64_t rows, ActBuf in, int in_c
     L.mode = 0;
     L.gepi = 0;
     L.w = c.pk.wf_hi(l);
+    L.w_lo = c.pk.wf_lo(l);
     L.w_ld = d.k_tot();
     L.bias = c.pk.bias(l);
     L.save_hi = (keep && i < 8) ? (spatial ? keep->a(i + 1).hi : keep->b(i + 1).hi) : nullptr;
@@ -390,6 +403,7 @@ ChainOpArgs bwd_op(const Ctx& c, int l, int in_row0, int n, int kb_act, int kb_i
   L.kind = mask ? 0 : 1;
   L.mode = 1;
   L.w = c.pk.wt_hi(l, in_row0);
+  L.w_lo = c.pk.wt_lo(l, in_row0);
   L.w_ld = layer_def(l).nt_pad;
   L.mask_bits = mask;
   L.save_hi = save;
@@ -409,7 +423,7 @@ int normals_chain(const Ctx& c, Workspace& w, int64_t rows) {
   a.m = rows;
   a.act_f16 = a.w_f16 = c.f16;
   a.seed_scale = c.f16 ? kNormalsSeedScale : 1.f;
-  const bool gen_seed = c.chain_impl == 0;
+  const bool gen_seed = true;   // the seed gradient (raw_density weight row where a8 > 0) is generated in the kernel
   int n = 0;
   if (gen_seed) {
     ChainOpArgs& S = a.op[n++];
@@ -462,10 +476,7 @@ int forward_chunk(const Ctx& c, Workspace& w, int64_t row0, int64_t rows, const 
   }
   if (want_normals) {
     // d raw_density / d x0 through the spatial net (models.py:603-609); result is a constant
-    if (c.chain && c.chain_impl == 1)
-      RN_TRY(launch_density_grad_seed_bits(w.ma(8), c.pk.wd(), w.g[0], rows, c.st));
-    else if (!c.chain)
-      RN_TRY(launch_density_grad_seed(prec, w.a(8), c.pk.wd(), w.g[0], rows, c.st));
+    if (!c.chain) RN_TRY(launch_density_grad_seed(prec, w.a(8), c.pk.wd(), w.g[0], rows, c.st));
     if (c.chain) {
       RN_TRY(normals_chain(c, w, rows));
     } else {
@@ -505,7 +516,7 @@ int wgrad_layer(const Ctx& c, Workspace& w, int l, int64_t rows, ActBuf dy, int 
     // tcgen05 (bf16 / fp16 / split-bf16): one launch per X source covers all of dY (X is read once, not once per
     // 128-column slab); the first one also produces the bias gradient
     WgradArgs g;
-    g.prec = c.cfg->prec;
+    g.prec = c.hprec();
     g.impl = c.impl;
     g.m = rows;
     g.dy = dy; g.dy_valid = dy_valid; g.n0 = 0; g.n_real = n_real_total;
@@ -550,7 +561,8 @@ int wgrad_layer(const Ctx& c, Workspace& w, int l, int64_t rows, ActBuf dy, int 
 
 // backward of one chunk with fused dgrad chains (bf16): the chains save dY of every layer, the wgrads follow
 int backward_chunk_chain(const Ctx& c, Workspace& w, int64_t row0, int64_t rows, const RnMlpOutputs& g) {
-  const int prec = c.cfg->prec;
+  const int prec = c.hprec();
+  const int wpl = c.x3 ? 2 : 1;
   const ActBuf none = {nullptr, nullptr, 0};
   auto off = [&](const float* p, int per) -> const float* { return p ? p + row0 * per : nullptr; };
   // fp16 mode: the gradient tiles entering the two dgrad chains are scaled by a power of two chosen from their
@@ -570,10 +582,11 @@ int backward_chunk_chain(const Ctx& c, Workspace& w, int64_t row0, int64_t rows,
     RN_TRY(launch_color_bwd(prec, w.rgb_raw, w.heads_raw, rows, c.sc, off(g.rgb, 3), off(g.diffuse, 3), off(g.specular, 3),
                             w.d_rgb_raw, w.dcolor, c.st));
   }
-  const bool fuse_dv0 = c.chain_impl == 0;   // SS chain: d v0 = [dY0 | dY5] * wcat^T as ONE op, dY5 re-read from its save
+  const bool fuse_dv0 = true;   // d v0 = [dY0 | dY5] * wcat^T as ONE op, dY5 re-read from its save
   {  // view net: rgb head, V7..V0
     ChainArgs a;
-    a.impl = c.chain_impl;
+    a.impl = 0;
+    a.w_planes = wpl;
     a.act_f16 = a.w_f16 = c.f16;
     a.m = rows;
     a.in = w.d_rgb_raw;
@@ -599,7 +612,7 @@ int backward_chunk_chain(const Ctx& c, Workspace& w, int64_t row0, int64_t rows,
     if (fuse_dv0) {
       ChainOpArgs& F = a.op[n];
       F.n = 256; F.kb_act = 4; F.kb_in = 4; F.in2 = 1; F.kind = 1; F.mode = 1; F.gepi = 0;
-      F.w = c.pk.wcat(); F.w_ld = 512;
+      F.w = c.pk.wcat(); F.w_lo = c.pk.wcat_lo(); F.w_ld = 512;
       ++n;
       a.in2 = w.gs[5];
       a.in2_cols = 256;
@@ -643,7 +656,8 @@ int backward_chunk_chain(const Ctx& c, Workspace& w, int64_t row0, int64_t rows,
   }
   {  // spatial net: heads, S7..S1 (no gradient w.r.t. x0 is needed: sdist is detached)
     ChainArgs a;
-    a.impl = c.chain_impl;
+    a.impl = 0;
+    a.w_planes = wpl;
     a.act_f16 = a.w_f16 = c.f16;
     a.m = rows;
     a.in = w.dheads;
@@ -743,9 +757,11 @@ int make_ctx(Ctx& c, const RnMlpConfig* cfg, const void* packed, const float* td
   c.sc = {cfg->srgb_mapping, cfg->srgb_normalization, cfg->density_bias, cfg->roughness_bias,
           cfg->rgb_premultiplier, cfg->rgb_bias, cfg->rgb_padding};
   c.impl = cfg->gemm_impl == 1 ? 1 : 0;
-  c.chain = (cfg->prec == RN_PREC_BF16 || cfg->prec == RN_PREC_FP16) && (cfg->gemm_impl == 0 || cfg->gemm_impl == 3);
+  if (cfg->gemm_impl == 3) return rn_set_error(RN_ERR_UNSUPPORTED, "rn_mlp: gemm_impl 3 (TMEM-operand chain experiment) was removed");
+  c.chain = (cfg->prec == RN_PREC_BF16 || cfg->prec == RN_PREC_FP16 || cfg->prec == RN_PREC_BF16X3) && cfg->gemm_impl == 0;
   c.f16 = cfg->prec == RN_PREC_FP16;
-  c.chain_impl = cfg->gemm_impl == 3 ? 1 : 0;
+  c.x3 = c.chain && cfg->prec == RN_PREC_BF16X3;
+  c.chain_impl = c.x3 ? 2 : 0;
   return RN_OK;
 }
 
@@ -767,9 +783,9 @@ extern "C" size_t rn_mlp_packed_bytes(int prec) {
 extern "C" size_t rn_mlp_workspace_bytes(const RnMlpConfig* cfg, int training) {
   if (!cfg || cfg->chunk_rows <= 0) return 0;
   const bool ext = training == 2;
-  size_t b = carve(nullptr, cfg->prec, cfg->chunk_rows, training ? 2 : 0, ext).bytes;
+  size_t b = carve(nullptr, cfg->prec, cfg->chunk_rows, training ? 2 : 0, ext, cfg_x3chain(cfg)).bytes;
   if (training) {
-    size_t b1 = carve(nullptr, cfg->prec, cfg->chunk_rows, 1, ext).bytes;
+    size_t b1 = carve(nullptr, cfg->prec, cfg->chunk_rows, 1, ext, cfg_x3chain(cfg)).bytes;
     if (b1 > b) b = b1;
     b += (size_t)cfg->chunk_rows * 16 * 4;  // scratch head outputs of the recompute pass
   }
@@ -778,7 +794,7 @@ extern "C" size_t rn_mlp_workspace_bytes(const RnMlpConfig* cfg, int training) {
 
 extern "C" size_t rn_mlp_saved_bytes(const RnMlpConfig* cfg, int64_t n_rows) {
   if (!cfg || n_rows <= 0) return 0;
-  return carve_saved(nullptr, cfg->prec, n_rows).bytes;
+  return carve_saved(nullptr, cfg->prec, cfg_hprec(cfg), n_rows).bytes;
 }
 
 extern "C" int rn_mlp_pack(const float* const* params, void* packed, int prec, void* stream) {
@@ -831,12 +847,13 @@ extern "C" int rn_mlp_pack(const float* const* params, void* packed, int prec, v
     copy_f32(params[pi + 1], bias, d.n_real);
   }
   copy_f32(params[kParamDensity], reinterpret_cast<float*>(base + lay.wd), 256);
-  if (prec == RN_PREC_BF16 || prec == RN_PREC_FP16) {
+  if (prec != RN_PREC_FP32) {
     // wcat[j, 0:256] = W_V0[:, j], wcat[j, 256:512] = W_V5[:, 256 + j]  (j = view-net input feature, 201 real)
     void* wc = base + lay.wcat;
+    void* wc_lo = base + lay.wcat + lay.wcat_plane;
     const int p0 = layer_param(kLayerV0), p5 = layer_param(kLayerV0 + 5);
-    seg(params[p0], kViewReal, 256, kViewReal, 1, wc, nullptr, 512, 0, 0);
-    seg(params[p5] + 256, 256 + kViewReal, 256, kViewReal, 1, wc, nullptr, 512, 0, 256);
+    seg(params[p0], kViewReal, 256, kViewReal, 1, wc, wc_lo, 512, 0, 0);
+    seg(params[p5] + 256, 256 + kViewReal, 256, kViewReal, 1, wc, wc_lo, 512, 0, 256);
   }
   flush(tw);
   flush(tb);
@@ -856,16 +873,16 @@ extern "C" int rn_mlp_forward(const RnMlpConfig* cfg, const void* packed, const 
   const bool want_normals = out->normals != nullptr;
   const int64_t rows_total = n_rays * s;
   const int64_t rc = cfg->chunk_rows;
-  Workspace w = carve(workspace, cfg->prec, rc, want_normals ? 1 : 0, saved != nullptr);
+  Workspace w = carve(workspace, cfg->prec, rc, want_normals ? 1 : 0, saved != nullptr, c.x3);
   if (w.bytes > workspace_bytes) return rn_set_error(RN_ERR_ARG, "rn_mlp_forward: workspace too small");
   Saved sv;
   if (saved) {
-    sv = carve_saved(saved, cfg->prec, rows_total);
+    sv = carve_saved(saved, cfg->prec, c.hprec(), rows_total);
     if (sv.bytes > saved_bytes) return rn_set_error(RN_ERR_ARG, "rn_mlp_forward: saved region too small");
   }
   for (int64_t row0 = 0; row0 < rows_total; row0 += rc) {
     const int64_t rows = rows_total - row0 < rc ? rows_total - row0 : rc;
-    if (saved) use_saved(w, sv, cfg->prec, row0);
+    if (saved) use_saved(w, sv, cfg->prec, c.hprec(), row0);
     RN_TRY(forward_chunk(c, w, row0, rows, *out, want_normals, true));
   }
   return RN_OK;
@@ -880,10 +897,10 @@ extern "C" int rn_mlp_backward(const RnMlpConfig* cfg, const void* packed, const
   if (!g || !grads) return rn_set_error(RN_ERR_ARG, "rn_mlp_backward: null gradients");
   const int64_t rows_total = n_rays * s;
   const int64_t rc = cfg->chunk_rows;
-  Workspace w = carve(workspace, cfg->prec, rc, 2, saved != nullptr);
+  Workspace w = carve(workspace, cfg->prec, rc, 2, saved != nullptr, c.x3);
   Saved sv;
   if (saved) {
-    sv = carve_saved(const_cast<void*>(saved), cfg->prec, rows_total);
+    sv = carve_saved(const_cast<void*>(saved), cfg->prec, c.hprec(), rows_total);
     if (sv.bytes > saved_bytes) return rn_set_error(RN_ERR_ARG, "rn_mlp_backward: saved region too small");
   }
   const size_t scratch_off = w.bytes;
@@ -944,7 +961,7 @@ extern "C" int rn_mlp_backward(const RnMlpConfig* cfg, const void* packed, const
     tmp.grad_pred = scratch + 5 * rc - row0 * 3;
     tmp.tint = scratch + 8 * rc - row0 * 3;
     if (saved) {
-      use_saved(w, sv, cfg->prec, row0);
+      use_saved(w, sv, cfg->prec, c.hprec(), row0);
     } else {
       c.algo = false;
       RN_TRY(forward_chunk(c, w, row0, rows, tmp, false, false));

@@ -203,25 +203,6 @@ density_grad_seed_kernel(ActBuf a8, const float* __restrict__ wd, ActBuf out, in
   act_store8<PREC>(out, (size_t)row, col, v);
 }
 
-// same from the 1-bit ReLU masks the fused forward chain writes (chain_pair.cu: word w of a row covers columns
-// [32w, 32w+32); pair i = columns 2i, 2i+1 owns bits i and 16+i): 32 B instead of 512 B read per row
-__global__ void __launch_bounds__(256)
-density_grad_seed_bits_kernel(const uint32_t* __restrict__ bits, const float* __restrict__ wd, ActBuf out, int64_t rows) {
-  const int64_t g = (int64_t)blockIdx.x * 256 + threadIdx.x;  // group of 8 columns
-  const int64_t row = g >> 5;
-  const int col = (int)(g & 31) * 8;
-  if (row >= rows) return;
-  const uint32_t w = __ldg(bits + (size_t)row * 8 + (col >> 5));
-  const int p0 = (col & 31) >> 1;   // first of the 4 pairs
-  float v[8];
-#pragma unroll
-  for (int e = 0; e < 8; ++e) {
-    const int bit = (e & 1) ? 16 + p0 + (e >> 1) : p0 + (e >> 1);
-    v[e] = ((w >> bit) & 1u) ? wd[col + e] : 0.f;
-  }
-  act_store8<RN_PREC_BF16>(out, (size_t)row, col, v);
-}
-
 // ------------------------------------------------------------------------------------------
 // integrated directional encoding (ref_utils.py:98-161), deg_view = 5.
 // Polynomials in z are evaluated by Horner in fp64 from the reference's fp32-rounded coefficients:
@@ -792,13 +773,6 @@ int launch_ipe_grad_normals(const float* gx0, int ld, const float* tdist, const 
                             cudaStream_t st) {
   if (rows <= 0) return RN_OK;
   ipe_grad_normals_kernel<<<nblk(rows, kEncRows), 256, 0, st>>>(gx0, ld, tdist, origins, dirs, radii, s, row0, rows, normals_out, gscale);
-  RN_CUDA_CHECK_LAUNCH();
-  return RN_OK;
-}
-
-int launch_density_grad_seed_bits(const uint32_t* bits, const float* wd, ActBuf out, int64_t rows, cudaStream_t st) {
-  if (rows <= 0) return RN_OK;
-  density_grad_seed_bits_kernel<<<nblk(rows * 32, 256), 256, 0, st>>>(bits, wd, out, rows);
   RN_CUDA_CHECK_LAUNCH();
   return RN_OK;
 }

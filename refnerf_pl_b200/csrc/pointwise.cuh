@@ -18,8 +18,6 @@ int launch_ipe_grad_normals(const float* gx0, int ld, const float* tdist, const 
                             cudaStream_t st);
 // seed of the normals pass: out[r, j] = wd[j] * (a8[r, j] > 0)
 int launch_density_grad_seed(int prec, ActBuf a8, const float* wd, ActBuf out, int64_t rows, cudaStream_t st);
-// the same from the 1-bit ReLU masks of a8 written by the fused forward chain (bf16 output)
-int launch_density_grad_seed_bits(const uint32_t* bits, const float* wd, ActBuf out, int64_t rows, cudaStream_t st);
 // K2: heads activations + reflect + IDE + n.v -> v0[:, 128:256] and the per-sample outputs
 int launch_heads_prologue_fwd(int prec, const float* heads_raw, const float* viewdirs, int s, int64_t row0, int64_t rows,
                               MlpScalars sc, ActBuf v0, float* density, float* normals_pred, float* grad_pred,
