@@ -11,7 +11,10 @@
 //     block of the next A operand to the MMA warp through its own mbarrier (act_ready[c]); the MMAs of op l+1 on K
 //     block c therefore start as soon as that block is written and run (3 x 512 cycles per K block) while the
 //     epilogue warps finish the remaining blocks.  Only the first block's epilogue is exposed.
-//   * chain-input K blocks (layer 0, the skip layers) do not depend on the previous epilogue and are issued first.
+//   * the chain input of the first op is loaded by TMA straight into the (then dead) activation tile as soon as the
+//     previous tile's last MMA has retired, after an L2 prefetch issued one tile ahead; the skip layer's input K
+//     blocks stream through the ring, interleaved with its activation K blocks so that their load latency hides
+//     behind the MMAs of a resident block.
 //   * weight K blocks [N/2 rows per CTA x 64] x {hi, lo} stream through a 3-stage TMA ring (32 KB stages).
 //   * saves for the wgrad kernels (hi plane only: wgrad runs on bf16 operands) and activation-format outputs of
 //     global ops (the bottleneck -> v0 hi/lo) leave as TMA stores issued by a dedicated store warp straight from
@@ -36,7 +39,8 @@ constexpr int kStageBytes = 2 * kPlaneBytes;   // hi | lo
 constexpr int kActPlane = 4 * kPlaneBytes;     // 64 KB: one plane of the activation tile (4 K blocks)
 constexpr int kSmemRing = 2 * kActPlane;       // act_hi | act_lo | ring
 constexpr int kSmemBars = kSmemRing + kStages * kStageBytes;
-constexpr int kSmemTotal = kSmemBars + 256;
+constexpr int kSmemBias = kSmemBars + 256;     // [op parity][column half h][4 K blocks x 32 floats]
+constexpr int kSmemTotal = kSmemBias + 2048;
 static_assert(kSmemTotal <= 232448, "shared memory budget");
 
 struct X3Maps {
@@ -59,7 +63,15 @@ chain_x3_kernel(const __grid_constant__ X3Maps maps, const __grid_constant__ Pai
   uint64_t* act_ready = bars + 12;     // [4] leader's: 16 arrivals: K block c of the activation tile is written
   uint64_t* written = bars + 16;       // per CTA: 8 arrivals: the tile part a store needs is in shared memory
   uint64_t* drained = bars + 17;       // per CTA: the store warp's TMA stores have read the tile
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
+  uint64_t* in_full = bars + 18;       // leader's: the first op's chain input has landed in the activation tile (tx bytes)
+  uint64_t* saves_drained = bars + 19; // per CTA: the last save of the tile has been read (the next tile's input may land)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
+  // the first op reads the chain input only: it is loaded straight into activation K blocks [in_blk0, 4)
+  const bool direct_in = p.op[0].kind != 2 && p.op[0].kb_in > 0;
+  const int in_blk0 = 4 - p.op[0].kb_in;
+  int last_save = -1;
+  for (int l = 0; l < p.num_ops; ++l)
+    if (p.op[l].kind == 0 && p.op[l].save) last_save = l;
 
   const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
@@ -86,6 +98,8 @@ chain_x3_kernel(const __grid_constant__ X3Maps maps, const __grid_constant__ Pai
     for (int i = 0; i < 4; ++i) mbar_init(&act_ready[i], 16);
     mbar_init(written, 8);
     mbar_init(drained, 1);
+    mbar_init(in_full, 1);
+    mbar_init(saves_drained, 1);
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc2(tmem_slot, kTmemCols);
@@ -111,18 +125,53 @@ chain_x3_kernel(const __grid_constant__ X3Maps maps, const __grid_constant__ Pai
       }
       __syncwarp();
     };
-    for (int64_t tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+    const uint32_t in_full_leader = map_to_cta(smem_u32(in_full), 0);
+    uint32_t tile_iter = 0;
+    for (int64_t tile = cluster_id; tile < num_tiles; tile += num_clusters, ++tile_iter) {
       const int row0 = (int)(tile * 256 + (int64_t)rank * 128);
+      if (p.in_kb && tile + num_clusters < num_tiles && elect_one_sync()) {
+        // next tile's chain input -> L2 (its TMA load is issued at the tile boundary and sits on the critical path)
+        const int rown = (int)((tile + num_clusters) * 256 + (int64_t)rank * 128);
+        for (int kb = 0; kb < p.in_kb; ++kb) {
+          tma_prefetch_l2_2d(&maps.in_hi, kb * kBK, rown);
+          tma_prefetch_l2_2d(&maps.in_lo, kb * kBK, rown);
+        }
+      }
+      __syncwarp();
       for (int l = 0; l < p.num_ops; ++l) {
         const PairOp& L = p.op[l];
         if (L.kind == 2) continue;
         const int nh = L.n >> 1;
         const uint32_t wbytes = (uint32_t)L.n * 256u;   // 2 planes x 2 CTAs x (n/2 rows x 128 B)
-        for (int kb = 0; kb < L.kb_in; ++kb) {
-          load2(4u * kPlaneBytes, &maps.in_hi, &maps.in_lo, kb * kBK, row0);
-          load2(wbytes, &maps.w_hi[l], &maps.w_lo[l], (L.kb_act + kb) * kBK, (int)rank * nh);
+        if (l == 0 && direct_in) {
+          // first weight block(s) first, then the input tile (it has to wait for the previous tile), then the rest
+          const int early = L.kb_in < 2 ? L.kb_in : 2;
+          for (int kb = 0; kb < early; ++kb) load2(wbytes, &maps.w_hi[l], &maps.w_lo[l], kb * kBK, (int)rank * nh);
+          if (tile_iter) {
+            // every MMA of the previous tile has retired (release of its last ring item) and its saves have been read
+            mbar_wait(&ring_empty[(pos - early - 1) % kStages], ((pos - early - 1) / kStages) & 1u);
+            if (last_save >= 0) mbar_wait(saves_drained, (tile_iter - 1) & 1u);
+          }
+          if (elect_one_sync()) {
+            if (rank == 0) mbar_arrive_expect_tx(in_full, (uint32_t)L.kb_in * 4u * kPlaneBytes);
+            for (int kb = 0; kb < L.kb_in; ++kb) {
+              tma_load_2d_pair(smem_base + (in_blk0 + kb) * kPlaneBytes, &maps.in_hi, in_full_leader, kb * kBK, row0);
+              tma_load_2d_pair(smem_base + kActPlane + (in_blk0 + kb) * kPlaneBytes, &maps.in_lo, in_full_leader, kb * kBK, row0);
+            }
+          }
+          __syncwarp();
+          for (int kb = early; kb < L.kb_in; ++kb) load2(wbytes, &maps.w_hi[l], &maps.w_lo[l], kb * kBK, (int)rank * nh);
+          continue;
         }
-        for (int kb = 0; kb < L.kb_act; ++kb) load2(wbytes, &maps.w_hi[l], &maps.w_lo[l], kb * kBK, (int)rank * nh);
+        // skip layers: input K block i, then activation K block i (the MMAs of the resident block cover the loads)
+        const int nmax = L.kb_in > L.kb_act ? L.kb_in : L.kb_act;
+        for (int kb = 0; kb < nmax; ++kb) {
+          if (kb < L.kb_in) {
+            load2(4u * kPlaneBytes, &maps.in_hi, &maps.in_lo, kb * kBK, row0);
+            load2(wbytes, &maps.w_hi[l], &maps.w_lo[l], (L.kb_act + kb) * kBK, (int)rank * nh);
+          }
+          if (kb < L.kb_act) load2(wbytes, &maps.w_hi[l], &maps.w_lo[l], kb * kBK, (int)rank * nh);
+        }
       }
     }
   } else if (warp == 1 && rank == 0) {
@@ -153,7 +202,8 @@ chain_x3_kernel(const __grid_constant__ X3Maps maps, const __grid_constant__ Pai
       }
       __syncwarp();
     };
-    for (int64_t tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+    uint32_t tile_iter = 0;
+    for (int64_t tile = cluster_id; tile < num_tiles; tile += num_clusters, ++tile_iter) {
       for (int l = 0; l < p.num_ops; ++l, ++opcount) {
         const PairOp& L = p.op[l];
         if (L.kind == 2) {   // seed op: the epilogue warps generate the activation tile, no MMA
@@ -170,28 +220,47 @@ chain_x3_kernel(const __grid_constant__ X3Maps maps, const __grid_constant__ Pai
         bool first = true;
         const int nkb = L.kb_in + L.kb_act;
         int done = 0;
-        for (int kb = 0; kb < L.kb_in; ++kb) {
-          wait_full(pos);
-          wait_full(pos + 1);
-          tc_fence_after();
-          ++done;
-          const uint32_t sa = stage_addr(pos), sb = stage_addr(pos + 1);
-          mma_kblock(tmem_d, sa, sa + kPlaneBytes, sb, sb + kPlaneBytes, idesc, first, &ring_empty[pos % kStages],
-                     &ring_empty[(pos + 1) % kStages], done == nkb ? &acc_full[buf] : nullptr);
-          pos += 2;
-          first = false;
-        }
-        for (int kb = 0; kb < L.kb_act; ++kb) {
-          if (need_acq) mbar_wait_cluster(&act_ready[kb], aver & 1u);
-          wait_full(pos);
-          tc_fence_after();
-          if (tr && kb == 0) p.trace[opcount * 8 + 1] = clock64();
-          ++done;
-          const uint32_t sb = stage_addr(pos);
-          mma_kblock(tmem_d, smem_base + kb * kPlaneBytes, smem_base + kActPlane + kb * kPlaneBytes, sb, sb + kPlaneBytes,
-                     idesc, first, &ring_empty[pos % kStages], done == nkb ? &acc_full[buf] : nullptr, nullptr);
-          ++pos;
-          first = false;
+        if (l == 0 && direct_in) {
+          // the chain input sits in activation K blocks [in_blk0, 4): only the weights come through the ring
+          mbar_wait_cluster(in_full, tile_iter & 1u);
+          for (int kb = 0; kb < L.kb_in; ++kb) {
+            wait_full(pos);
+            tc_fence_after();
+            if (tr && kb == 0) p.trace[opcount * 8 + 1] = clock64();
+            ++done;
+            const uint32_t sb = stage_addr(pos);
+            mma_kblock(tmem_d, smem_base + (in_blk0 + kb) * kPlaneBytes, smem_base + kActPlane + (in_blk0 + kb) * kPlaneBytes, sb,
+                       sb + kPlaneBytes, idesc, first, &ring_empty[pos % kStages], done == nkb ? &acc_full[buf] : nullptr, nullptr);
+            ++pos;
+            first = false;
+          }
+        } else {
+          const int nmax = L.kb_in > L.kb_act ? L.kb_in : L.kb_act;
+          for (int kb = 0; kb < nmax; ++kb) {
+            if (kb < L.kb_in) {
+              wait_full(pos);
+              wait_full(pos + 1);
+              tc_fence_after();
+              ++done;
+              const uint32_t sa = stage_addr(pos), sb = stage_addr(pos + 1);
+              mma_kblock(tmem_d, sa, sa + kPlaneBytes, sb, sb + kPlaneBytes, idesc, first, &ring_empty[pos % kStages],
+                         &ring_empty[(pos + 1) % kStages], done == nkb ? &acc_full[buf] : nullptr);
+              pos += 2;
+              first = false;
+            }
+            if (kb < L.kb_act) {
+              if (need_acq) mbar_wait_cluster(&act_ready[kb], aver & 1u);
+              wait_full(pos);
+              tc_fence_after();
+              if (tr && kb == 0) p.trace[opcount * 8 + 1] = clock64();
+              ++done;
+              const uint32_t sb = stage_addr(pos);
+              mma_kblock(tmem_d, smem_base + kb * kPlaneBytes, smem_base + kActPlane + kb * kPlaneBytes, sb, sb + kPlaneBytes,
+                         idesc, first, &ring_empty[pos % kStages], done == nkb ? &acc_full[buf] : nullptr, nullptr);
+              ++pos;
+              first = false;
+            }
+          }
         }
         if (tr) p.trace[opcount * 8 + 2] = clock64();
         if (L.kb_act && need_acq) {
@@ -232,6 +301,7 @@ chain_x3_kernel(const __grid_constant__ X3Maps maps, const __grid_constant__ Pai
             any = true;
           }
           mbar_arrive(drained);
+          if (l == last_save) mbar_arrive(saves_drained);
         }
         __syncwarp();
       }
@@ -247,6 +317,10 @@ chain_x3_kernel(const __grid_constant__ X3Maps maps, const __grid_constant__ Pai
     const uint32_t act_row_hi = smem_base + (uint32_t)(r_in_tile * 128);
     const uint32_t act_row_lo = act_row_hi + kActPlane;
     const uint32_t swz = (uint32_t)(r_in_tile & 7);
+    // bias / seed-vector staging: two buffers (op parity) x two column halves x 128 floats (this warp's 32 columns of
+    // each K block).  The four warps of a column half write identical values, so no cross-warp barrier is needed:
+    // every warp only relies on its own stores; a warp two ops ahead cannot exist (acc_free has 16 arrivals).
+    const uint32_t bias_half = smem_base + kSmemBias + (uint32_t)h * 512u;
     uint32_t gemm_idx = 0, ndrain = 0, opcount = 0;
     bool save_outstanding = false;
     auto wait_drained = [&]() {
@@ -275,6 +349,17 @@ chain_x3_kernel(const __grid_constant__ X3Maps maps, const __grid_constant__ Pai
       for (int l = 0; l < p.num_ops; ++l, ++opcount) {
         const PairOp& L = p.op[l];
         const bool seed = MODE == 1 && L.kind == 2;
+        const float* bias_ptr = L.kind == 1 ? p.gepi[L.gepi].bias : ((MODE == 0 || seed) ? L.bias : nullptr);
+        const uint32_t bias_buf = bias_half + (opcount & 1u) * 1024u;
+        if (bias_ptr) {
+          const int col = 64 * (lane >> 3) + 32 * h + 4 * (lane & 7);
+          float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (col < L.n) bv = __ldg(reinterpret_cast<const float4*>(bias_ptr + col));
+          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(bias_buf + 16u * lane), "f"(bv.x), "f"(bv.y), "f"(bv.z),
+                       "f"(bv.w)
+                       : "memory");
+          __syncwarp();
+        }
         uint32_t bw[4] = {0u, 0u, 0u, 0u};
         if (MODE == 1 && (L.kind == 0 || seed) && row_w < p.m) {
 #pragma unroll
@@ -285,11 +370,10 @@ chain_x3_kernel(const __grid_constant__ X3Maps maps, const __grid_constant__ Pai
           wait_drained();
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
-            const float4* vp = reinterpret_cast<const float4*>(L.bias + 64 * c + 32 * h);
             uint32_t hi[16], lo[16];
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-              const float4 b = __ldg(vp + i);
+              const float4 b = lds128f(bias_buf + (uint32_t)(c * 128 + 16 * i));
               const float v0 = (bw[c] >> (2 * i) & 1u) ? b.x * p.seed_scale : 0.f;
               const float v1 = (bw[c] >> (16 + 2 * i) & 1u) ? b.y * p.seed_scale : 0.f;
               const float v2 = (bw[c] >> (2 * i + 1) & 1u) ? b.z * p.seed_scale : 0.f;
@@ -324,10 +408,9 @@ chain_x3_kernel(const __grid_constant__ X3Maps maps, const __grid_constant__ Pai
             if (c < 3) tmem_ld32(taddr + (uint32_t)(64 * (c + 1) + 32 * h), nxt);
             uint32_t hi[16], lo[16];
             if (MODE == 0) {
-              const float4* bp = reinterpret_cast<const float4*>(L.bias + 64 * c + 32 * h);
 #pragma unroll
               for (int i = 0; i < 8; ++i) {
-                const float4 b = __ldg(bp + i);
+                const float4 b = lds128f(bias_buf + (uint32_t)(c * 128 + 16 * i));
                 const float v0 = fmaxf(__uint_as_float(cur[4 * i]) + b.x, 0.f);
                 const float v1 = fmaxf(__uint_as_float(cur[4 * i + 1]) + b.y, 0.f);
                 const float v2 = fmaxf(__uint_as_float(cur[4 * i + 2]) + b.z, 0.f);
@@ -346,15 +429,17 @@ chain_x3_kernel(const __grid_constant__ X3Maps maps, const __grid_constant__ Pai
             }
             store_block(c, hi, lo);
             __syncwarp();
-            if (lane == 0) mbar_arrive_cluster_addr(ready_addr0 + 8u * c);
+            if (lane == 0) {
+              // (the store warp's signal goes first: no warp can reach the next store event before every warp has
+              // signalled this one, because the next op's accumulator needs this op's last block from all of them)
+              if (c == 3 && L.save) mbar_arrive(written);
+              mbar_arrive_cluster_addr(ready_addr0 + 8u * c);
+            }
             if (tr && c == 0) p.trace[opcount * 8 + 5] = clock64();
           }
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) {
-            mbar_arrive_cluster_addr(free_addr0 + 8u * buf);
-            if (L.save) mbar_arrive(written);
-          }
+          if (lane == 0) mbar_arrive_cluster_addr(free_addr0 + 8u * buf);
           if (L.save) save_outstanding = true;
           if (MODE == 0 && L.save_bits && row_w < p.m) {
 #pragma unroll
@@ -373,13 +458,13 @@ chain_x3_kernel(const __grid_constant__ X3Maps maps, const __grid_constant__ Pai
             uint32_t r[32];
             tmem_ld32(taddr + (uint32_t)col0, r);
             tmem_ld_wait();
+            const uint32_t bsm = bias_buf + (uint32_t)((gi >> 1) * 128);   // this group's 32 bias values
             if (col0 < out_cols) {
-              const float4* bp = reinterpret_cast<const float4*>(ge.bias + col0);
               uint32_t hi[16], lo[16];
 #pragma unroll
               for (int i = 0; i < 8; ++i) {
                 float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (ge.bias) b = __ldg(bp + i);
+                if (bias_ptr) b = lds128f(bsm + 16u * i);
                 split2(__uint_as_float(r[4 * i]) + b.x, __uint_as_float(r[4 * i + 1]) + b.y, hi[2 * i], lo[2 * i]);
                 split2(__uint_as_float(r[4 * i + 2]) + b.z, __uint_as_float(r[4 * i + 3]) + b.w, hi[2 * i + 1], lo[2 * i + 1]);
               }
@@ -391,11 +476,10 @@ chain_x3_kernel(const __grid_constant__ X3Maps maps, const __grid_constant__ Pai
                   float v[16];
 #pragma unroll
                   for (int e = 0; e < 16; ++e) v[e] = __uint_as_float(r[16 * hh + e]);
-                  if (ge.bias) {
-                    const float4* bp = reinterpret_cast<const float4*>(ge.bias + col0 + 16 * hh);
+                  if (bias_ptr) {
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
-                      const float4 b = __ldg(bp + i);
+                      const float4 b = lds128f(bsm + (uint32_t)(64 * hh + 16 * i));
                       v[4 * i] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w;
                     }
                   }

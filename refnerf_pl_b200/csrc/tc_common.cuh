@@ -31,6 +31,7 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   const uint32_t addr = smem_u32(bar);
+#pragma unroll 1   // (ptxas otherwise unrolls the poll 64x: ~100 KB kernels that thrash the instruction cache)
   for (int spin = 0; spin < kSpinLimit; ++spin) {
     uint32_t done;
     asm volatile(

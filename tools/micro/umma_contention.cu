@@ -32,7 +32,7 @@ constexpr int kBars = kAct + kW + kScratch;
 constexpr int kSmem = kBars + 256;
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
-contention_kernel(const __grid_constant__ CUtensorMap wmap, int mode, int batches, long long* cycles, float* sink, unsigned char* gdst) {
+contention_kernel(const __grid_constant__ CUtensorMap wmap, int mode, int batches, long long* cycles, float* sink, unsigned char* gdst, int nn) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* done = reinterpret_cast<uint64_t*>(smem + kBars);   // MMA batch complete (multicast commit)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + 2);
@@ -64,7 +64,7 @@ contention_kernel(const __grid_constant__ CUtensorMap wmap, int mode, int batche
   if (warp == 1 && rank == 0) {
     // 16 MMAs per batch (one 256 x 256 x 256 layer on one row tile), alternating accumulators, one commit per batch;
     // the issuing warp waits for batch b-2 before issuing batch b (two batches in flight, like the chain's ping-pong)
-    const uint32_t idesc = make_idesc2(256);
+    const uint32_t idesc = make_idesc2(nn);   // N = 256 (chain_pair / chain_x3 full-width ops) or 128 (column halves)
     const long long t0 = clock64();
     for (int b = 0; b < batches; ++b) {
       if (b >= 2) mbar_wait(&done[b & 1], (uint32_t)((b >> 1) - 1) & 1u);
@@ -147,11 +147,12 @@ contention_kernel(const __grid_constant__ CUtensorMap wmap, int mode, int batche
   if (warp == 2) tmem_dealloc2(tmem_base, 512);
 }
 
-// usage: umma_contention [batches] [clusters]   (clusters = 74 loads every SM of a B200: shows what the power cap does
+// usage: umma_contention [batches] [clusters] [N]   (clusters = 74 loads every SM of a B200: shows what the power cap does
 // to the cycles per MMA when the whole chip runs tensor work)
 int main(int argc, char** argv) {
   const int batches = argc > 1 ? atoi(argv[1]) : 2000;
   const int clusters = argc > 2 ? atoi(argv[2]) : 1;
+  const int nn = argc > 3 ? atoi(argv[3]) : 256;
   long long* cyc;
   float* sink;
   unsigned char* gdst;
@@ -167,7 +168,7 @@ int main(int argc, char** argv) {
   const char* names[9] = {"idle", "st.shared.v4 stream", "ld.shared.v4 broadcast", "tcgen05.ld stream", "st.shared + tcgen05.ld",
                           "bulk copy shared->global", "TMA loads global->shared", "commit per K block", "sts + tld + TMA + commits"};
   for (int mode = 0; mode < 9; ++mode) {
-    contention_kernel<<<2 * clusters, 384, kSmem>>>(wmap, mode, batches, cyc, sink, gdst);
+    contention_kernel<<<2 * clusters, 384, kSmem>>>(wmap, mode, batches, cyc, sink, gdst, nn);
     cudaError_t e = cudaDeviceSynchronize();
     if (e != cudaSuccess) {
       printf("mode %d (%s): %s\n", mode, names[mode], cudaGetErrorString(e));
@@ -179,8 +180,8 @@ int main(int argc, char** argv) {
     double sum = 0;
     for (int i = 0; i < clusters; ++i) { lo = c[i] < lo ? c[i] : lo; hi = c[i] > hi ? c[i] : hi; sum += (double)c[i]; }
     const double per = (double)batches * 16;
-    printf("mode %d  %-28s %7.1f cycles / MMA (min %.1f max %.1f over %d clusters; M256 N256 K16, cta_group::2, %d batches of 16)\n", mode,
-           names[mode], sum / clusters / per, lo / per, hi / per, clusters, batches);
+    printf("mode %d  %-28s %7.1f cycles / MMA (min %.1f max %.1f over %d clusters; M256 N%d K16, cta_group::2, %d batches of 16)\n", mode,
+           names[mode], sum / clusters / per, lo / per, hi / per, clusters, nn, batches);
   }
   return 0;
 }
