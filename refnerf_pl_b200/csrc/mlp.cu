@@ -153,7 +153,7 @@ struct Carver {
 struct Workspace {
   ActBuf x0, v0, sp[8], vw[8], g[2], gs[8], dheads, d_bott, d_scal, d_rgb_raw;
   uint32_t *msp[8], *mvw[8];   // ReLU bits of the hidden activations (fused chains), valid when nsp / nvw == 8
-  float *heads_raw, *rgb_raw, *gx0, *dv0f, *dcolor;
+  float *heads_raw, *rgb_raw, *gx0, *gx0b, *dv0f, *dcolor;
   float *stage16, *scal;   // fp16 mode: f32 staging of the 16-wide chain seeds; amax / scale scalars (pointwise.cu)
   float* gW[kNumLayers];
   float* gB[kNumLayers];
@@ -220,6 +220,7 @@ Workspace carve(void* base, int prec, int64_t rc, int mode, bool external = fals
     w.g[1] = c.act(prec, rc, 256);
   }
   if (mode >= 1) w.gx0 = (float*)c.take((size_t)rc * 128 * 4);
+  w.gx0b = (mode == 1 && x3chain) ? (float*)c.take((size_t)rc * 128 * 4) : nullptr;
   if (mode == 2) {
     for (int i = 0; i < 8; ++i) w.gs[i] = c.act(hprec, rc, 256);   // dY of the 8 layers of the net being back-propagated
     w.g[0] = w.gs[0];
@@ -390,6 +391,29 @@ int chain_layers(const Ctx& c, int l0, int lh, int64_t rows, ActBuf in, int in_c
   }
   final_epi.bias = c.pk.bias(lh);
   a.gepi[0] = final_epi;
+  if (c.x3 && lh == kLayerH) {
+    // chain_x3.cu: global ops are at most 128 wide -> the heads layer runs as two ops over the same activation tile:
+    // the bottleneck (128 columns, leaves in activation format) and the 11 scalar heads (16 columns, f32)
+    // The scalar heads go first: the bottleneck's epilogue stages its output in the activation tile, which the other
+    // op still has to read.
+    LayerDef d = layer_def(lh);
+    ChainOpArgs& S = a.op[8];
+    ChainOpArgs& B = a.op[9];
+    B = S;
+    B.n = kBottleneck;
+    S.n = kHeadsPad - kBottleneck;
+    S.gepi = 1;
+    S.w = reinterpret_cast<const uint8_t*>(c.pk.wf_hi(lh)) + (size_t)kBottleneck * d.k_tot() * 2;
+    S.w_lo = reinterpret_cast<const uint8_t*>(c.pk.wf_lo(lh)) + (size_t)kBottleneck * d.k_tot() * 2;
+    GemmEpilogue eb = final_epi, es = final_epi;
+    eb.f32 = nullptr; eb.f32_cols = 0;
+    es.out = ActBuf{nullptr, nullptr, 0}; es.out_cols = 0;
+    es.f32_col0 = 0;
+    es.bias = c.pk.bias(lh) + kBottleneck;
+    a.gepi[0] = eb;
+    a.gepi[1] = es;
+    a.num_ops = 10;
+  }
   a.algo_flops = c.algo ? flops : 0.0;
   return launch_chain(a, c.st);
 }
@@ -452,7 +476,8 @@ int normals_chain(const Ctx& c, Workspace& w, int64_t rows) {
   ++n;
   a.num_ops = n;
   a.gepi[0] = epi_f32(w.gx0, 128, 128, 0);
-  a.gepi[1] = epi_f32(w.gx0, 128, 128, 1);
+  // chain_x3: the layer-0 share goes to its own buffer (ipe_grad_normals adds the two): no read-modify-write in the epilogue
+  a.gepi[1] = w.gx0b ? epi_f32(w.gx0b, 128, 128, 0) : epi_f32(w.gx0, 128, 128, 1);
   a.algo_flops = c.algo ? flops : 0.0;
   return launch_chain(a, c.st);
 }
@@ -489,7 +514,7 @@ int forward_chunk(const Ctx& c, Workspace& w, int64_t row0, int64_t rows, const 
       }
       RN_TRY(dgrad_layer(c, 0, rows, w.g[cur], 256, 256, none, 0, 0, 0, kEncPad, epi_f32(w.gx0, 128, 128, 1)));
     }
-    RN_TRY(launch_ipe_grad_normals(w.gx0, 128, c.tdist, c.origins, c.dirs, c.radii, c.s, row0, rows,
+    RN_TRY(launch_ipe_grad_normals(w.gx0, (c.chain && w.gx0b) ? w.gx0b : nullptr, 128, c.tdist, c.origins, c.dirs, c.radii, c.s, row0, rows,
                                    o.normals + row0 * 3, (c.chain && c.f16) ? 1.f / kNormalsSeedScale : 1.f, c.st));
   }
   // outputs of the heads are written even in the recompute pass (cheap); callers pass scratch or real outputs

@@ -128,7 +128,7 @@ encode_kernel(const float* __restrict__ tdist, const float* __restrict__ origins
 // d raw_density / d means from d raw_density / d features (closed form), then
 // normals = -l2_normalize(.)  (models.py:603-609, ref_utils.py:40-42)
 __global__ void __launch_bounds__(256)
-ipe_grad_normals_kernel(const float* __restrict__ gx0, int ld, const float* __restrict__ tdist,
+ipe_grad_normals_kernel(const float* __restrict__ gx0, const float* __restrict__ gx0b, int ld, const float* __restrict__ tdist,
                         const float* __restrict__ origins, const float* __restrict__ dirs,
                         const float* __restrict__ radii, int s, int64_t row0, int64_t rows,
                         float* __restrict__ normals_out, float gscale) {
@@ -138,7 +138,11 @@ ipe_grad_normals_kernel(const float* __restrict__ gx0, int ld, const float* __re
     const int rr = g / 24, c4 = g - rr * 24;
     const int64_t lr = (int64_t)blockIdx.x * kEncRows + rr;
     if (lr >= rows) continue;
-    const float4 v = *reinterpret_cast<const float4*>(gx0 + (size_t)lr * ld + c4 * 4);
+    float4 v = *reinterpret_cast<const float4*>(gx0 + (size_t)lr * ld + c4 * 4);
+    if (gx0b) {   // second partial sum (the skip layer's share of the gradient), kept apart to avoid a read-modify-write
+      const float4 u = *reinterpret_cast<const float4*>(gx0b + (size_t)lr * ld + c4 * 4);
+      v.x += u.x; v.y += u.y; v.z += u.z; v.w += u.w;
+    }
     float* t = tile + rr * 97 + c4 * 4;
     t[0] = v.x; t[1] = v.y; t[2] = v.z; t[3] = v.w;
   }
@@ -768,11 +772,11 @@ int launch_encode(int prec, const float* tdist, const float* origins, const floa
   return RN_OK;
 }
 
-int launch_ipe_grad_normals(const float* gx0, int ld, const float* tdist, const float* origins, const float* dirs,
+int launch_ipe_grad_normals(const float* gx0, const float* gx0b, int ld, const float* tdist, const float* origins, const float* dirs,
                             const float* radii, int s, int64_t row0, int64_t rows, float* normals_out, float gscale,
                             cudaStream_t st) {
   if (rows <= 0) return RN_OK;
-  ipe_grad_normals_kernel<<<nblk(rows, kEncRows), 256, 0, st>>>(gx0, ld, tdist, origins, dirs, radii, s, row0, rows, normals_out, gscale);
+  ipe_grad_normals_kernel<<<nblk(rows, kEncRows), 256, 0, st>>>(gx0, gx0b, ld, tdist, origins, dirs, radii, s, row0, rows, normals_out, gscale);
   RN_CUDA_CHECK_LAUNCH();
   return RN_OK;
 }

@@ -12,8 +12,8 @@ struct MlpScalars {
 // K1: cast_rays + lift + IPE for rows [row0, row0+rows) of the level -> out[:, 0:ncols] (cols >= 96 zero)
 int launch_encode(int prec, const float* tdist, const float* origins, const float* dirs, const float* radii, int s,
                   int64_t row0, int64_t rows, ActBuf out, int ncols, cudaStream_t st);
-// normals = -l2_normalize(d raw_density / d means) from gx0 = d raw_density / d ipe features
-int launch_ipe_grad_normals(const float* gx0, int ld, const float* tdist, const float* origins, const float* dirs,
+// normals = -l2_normalize(d raw_density / d means) from gx0 (+ gx0b if given) = d raw_density / d ipe features
+int launch_ipe_grad_normals(const float* gx0, const float* gx0b, int ld, const float* tdist, const float* origins, const float* dirs,
                             const float* radii, int s, int64_t row0, int64_t rows, float* normals_out, float gscale,
                             cudaStream_t st);
 // seed of the normals pass: out[r, j] = wd[j] * (a8[r, j] > 0)
