@@ -50,10 +50,23 @@ RN_API int rn_abi_version(void);
  * integrate_weights (stepfun.py:134-258), math.sorted_interp (math.py:88-111) and the s_to_t ray
  * warp (coord.py:98).  sdist_in [N,s_in+1], weights_in [N,s_in], u [s_out] (the linspace grid of
  * stepfun.py:195-204), near/far [N].  Outputs sdist_out, tdist_out [N,s_out+1]; optional (may be
- * NULL) cw_out [N,s_in+1] and idx_out [N,s_out] (int32, idx = #{cw <= u} - 1). */
-RN_API int rn_resample(const float* sdist_in, const float* weights_in, const float* u, const float* near_, const float* far_,
+ * NULL) cw_out [N,s_in+1] and idx_out [N,s_out] (int32, idx = #{cw <= u} - 1).
+ * The CDF is accumulated in fp64 and rounded per prefix, as torch.cumsum does for a float row on the CPU.
+ * cw_in (optional, [N,s_in+1]): use this CDF instead of computing one from the weights (weights_in may then be NULL);
+ * the search + interpolation stage is bit-exact against math.sorted_interp on the same CDF. */
+RN_API int rn_resample(const float* sdist_in, const float* weights_in, const float* cw_in, const float* u, const float* near_, const float* far_,
                 int64_t n_rays, int s_in, int s_out, float padding, float anneal, float dom_lo, float dom_hi,
                 float* sdist_out, float* tdist_out, float* cw_out, int32_t* idx_out, void* stream);
+
+/* ---- K4a': max_dilate_weights ------------------------------------------------------------------
+ * Replaces stepfun.max_dilate_weights / max_dilate / weight_to_pdf / pdf_to_weight (stepfun.py:92-131) and, with
+ * trim = 1, the [1:-1] trim of its caller (models.py:177-187).  t [N,s+1] sorted fenceposts, w [N,s] weights.
+ * trim = 0: t_out [N,3s+1], w_out [N,3s];  trim = 1: t_out [N,3s-1], w_out [N,3s-2].
+ * A warp per ray: 3-way merge by rank, range-max of the pdf over the window of dilated intervals containing each new
+ * fencepost (sparse table in shared memory) instead of the reference's dense [3s+1, s] mask.  No gradient (the
+ * resampler that consumes the result is detached, models.py:208-215). */
+RN_API int rn_max_dilate_weights(const float* t, const float* w, int64_t n_rays, int s, float dilation, float dom_lo,
+                          float dom_hi, int renormalize, int trim, float* t_out, float* w_out, void* stream);
 
 /* ---- K4b: alpha compositing ---------------------------------------------------------------
  * Replaces render.compute_alpha_weights (render.py:132-149) and render.volumetric_rendering

@@ -174,8 +174,73 @@ def stepfun_util_cases():
     print('wrote stepfun_utils', len(out), 'arrays')
 
 
+def geometry_losses_case(name='llff_geom_losses', n_rays=160, seed=21):
+    """configs/llff_refnerf_geometry_losses.gin as RefNeRFSystem.training_step runs it (nerf_system.py:84-191): main
+    forward, sample_noisy_rays on the first 128 rays x 4 angles, second forward, every loss term of the config --
+    computed by the UNMODIFIED reference functions (internal/sample_utils.py, internal/train_utils.py:207-325)."""
+    ns, config = ref_import.load('llff_refnerf_geometry_losses.gin')
+    from internal import sample_utils as ref_sample_utils
+    torch.manual_seed(0)
+    model = ns.models.construct_model(ns.utils.dummy_rays(), config)
+    p = O.init_params(seed=3, bias_std=0.05, weight_scale=1.3)
+    _load_params(model, p)
+    rays_np = synthetic.llff_rays(n_rays, seed=seed)
+    rays = ns.utils.Rays(**{k: torch.tensor(v) for k, v in rays_np.items()})
+    gt = torch.tensor(synthetic.gt_rgb(n_rays, seed))
+    warm = 0.5
+    model.train(True)
+    rend, hist = model(rays, 1.0, True)
+    # the reference draws the rotation angles with uniform_ on a fresh tensor: reproduce the draw, then replay the seed
+    torch.manual_seed(1234)
+    angles = torch.zeros(config.sample_noise_angles * 3).uniform_(
+        0, config.sample_angle_range / 180 * np.pi * warm).reshape(-1, 3)
+    torch.manual_seed(1234)
+    noisy = ref_sample_utils.sample_noisy_rays(rays, rend[-1], config.sample_angle_range, config.sample_noise_size,
+                                               config.sample_noise_angles, warm)
+    rend_n, _ = model(noisy, 1.0, True)
+
+    class B:
+        pass
+    batch = B()
+    batch.rgb = _np(gt)
+    tu = ns.train_utils
+    losses = {'data': tu.compute_data_loss(batch, rend, rays, config)[0],
+              'orientation': tu.orientation_loss(rays, model, hist, config),
+              'predicted_normals': tu.predicted_normal_loss(model, hist, config)}
+    (losses['diffuse_consistency'], losses['specular_consistency'],
+     losses['normals_consistency']) = tu.noisy_consistency_loss(model, rend, rend_n, config, warm)
+    losses['acc'] = tu.accumulated_weights_loss(rend, config)
+    losses['distance_consistency'] = tu.noisy_distance_consistency_loss(model, rays, noisy, rend, rend_n, config, warm)
+    losses['weights_entropy'] = tu.weights_entropy_loss(model, rend, hist, config, warm)
+    loss = torch.sum(torch.stack(list(losses.values())))
+    model.zero_grad()
+    loss.backward()
+    out = {'meta_seed': np.int64(3), 'meta_bias_std': np.float64(0.05), 'meta_weight_scale': np.float64(1.3),
+           'gt_rgb': _np(gt), 'warmup_ratio': np.float64(warm), 'xyz_angles': _np(angles), 'train_loss': _np(loss),
+           'param_checksum': np.float64(sum(float(v.double().abs().sum()) for v in p.values()))}
+    for k, v in rays_np.items():
+        out['rays_' + k] = v
+    for k in ('origins', 'directions', 'viewdirs'):
+        out['noisy_' + k] = _np(getattr(noisy, k))
+    for k, v in losses.items():
+        out['loss_' + k] = _np(v)
+    for lvl in range(2):
+        for k in ('rgb', 'diffuse', 'specular', 'distance', 'acc', 'normals', 'normals_pred'):
+            out[f'rend{lvl}_{k}'] = _np(rend[lvl][k])
+            out[f'noisy_rend{lvl}_{k}'] = _np(rend_n[lvl][k])
+    for k, v in model.nerf_mlp.named_parameters():
+        g = _np(v.grad).reshape(-1)
+        out['grad_norm_' + k] = np.float64(np.sqrt((g.astype(np.float64) ** 2).sum()))
+        out['grad_sub_' + k] = g[::97].copy()
+    np.savez_compressed(os.path.join(OUT, name + '.npz'), **out)
+    print('wrote', name, len(out), 'arrays; losses:', {k: float(v) for k, v in losses.items()})
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
+    if 'geometry' in sys.argv[1:]:
+        geometry_losses_case()
+        return
     if 'stepfun_utils' in sys.argv[1:]:
         stepfun_util_cases()
         return

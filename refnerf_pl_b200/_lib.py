@@ -30,7 +30,8 @@ _P = c_void_p
 _SIGNATURES = {
     'rn_last_error': (c_char_p, []),
     'rn_abi_version': (c_int, []),
-    'rn_resample': (c_int, [_P, _P, _P, _P, _P, c_int64, c_int, c_int, c_float, c_float, c_float, c_float, _P, _P, _P, _P, _P]),
+    'rn_resample': (c_int, [_P, _P, _P, _P, _P, _P, c_int64, c_int, c_int, c_float, c_float, c_float, c_float, _P, _P, _P, _P, _P]),
+    'rn_max_dilate_weights': (c_int, [_P, _P, c_int64, c_int, c_float, c_float, c_float, c_int, c_int, _P, _P, _P]),
     'rn_composite_fwd': (c_int, [_P] * 11 + [c_int64, c_int, c_float, _P, _P, _P, _P, _P]),
     'rn_composite_bwd': (c_int, [_P] * 15 + [c_int64, c_int, c_float] + [_P] * 7 + [_P]),
     'rn_lossfun_outer_fwd': (c_int, [_P, _P, _P, _P, c_int64, c_int, c_int, _P, _P]),

@@ -90,8 +90,31 @@ class Config:
     predicted_normal_loss_mult: float = 0.0
     predicted_normal_coarse_loss_mult: float = 0.0
     distortion_loss_mult: float = 0.01  # never read by the reference
+    patch_size: int = 1
+    sample_angle_range: float = 5
     sample_noise_size: int = 128
     sample_noise_angles: int = 1
+    consistency_warmup_steps: float = 0.
+    consistency_decay_steps: float = 1.
+    consistency_normal_loss_mult: float = 0.0
+    consistency_normal_coarse_loss_mult: float = 0.0
+    consistency_normal_loss_target: str = 'normals_pred'
+    consistency_diffuse_loss_type: str = 'mse'
+    consistency_diffuse_loss_mult: float = 0.0
+    consistency_diffuse_coarse_loss_mult: float = 0.0
+    consistency_specular_loss_type: str = 'mse'
+    consistency_specular_loss_mult: float = 0.0
+    consistency_specular_coarse_loss_mult: float = 0.0
+    consistency_distance_loss_type: str = 'mse'
+    consistency_distance_loss_mult: float = 0.0
+    consistency_distance_coarse_loss_mult: float = 0.0
+    accumulated_weights_loss_mult: float = 0.0
+    depth_smoothness_loss_mult: float = 0.0
+    depth_smoothness_coarse_loss_mult: float = 0.0
+    acc_threshold_for_consistency_loss: float = 0.0
+    weights_entropy_loss_mult: float = 0.0
+    weights_entropy_coarse_loss_mult: float = 0.0
+    acc_threshold_for_weights_entropy_loss: float = 0.0
     srgb_mapping_when_rendering: bool = False
     srgb_mapping_type: str = 'linear'
     supervised_by_linear_rgb: bool = False

@@ -15,11 +15,29 @@ __device__ __forceinline__ float nan_to_zero_clip01(float r) {
   return fminf(fmaxf(r, 0.f), 1.f);     // +-inf -> clip
 }
 
+// inclusive prefix sum across the warp in fp64 (the CDF accumulator, see below)
+__device__ __forceinline__ double warp_scan_incl_f64(double v, int lane) {
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const double t = __shfl_up_sync(RN_FULL, v, o);
+    if (lane >= o) v += t;
+  }
+  return v;
+}
+
 // ---------------------------------------------------------------------------------------------
 // resample: models.py:200-203 + stepfun.py:134-258 + math.py:88-111 + coord.py:98
+//
+// CDF arithmetic: the reference's `torch.cumsum` (stepfun.py:149-154) accumulates a float row in DOUBLE on the CPU
+// (ATen's acc_type<float, is_cuda=false>) and rounds every prefix to float.  The kernels do the same -- fp64 prefix
+// sums of the fp32 probabilities, rounded once -- so that the CDF differs from the reference's only through the
+// softmax (exp and the order of its normalising sum), and the fp64 sums make it monotone without a running max.
+// `cw_in` (optional) replaces the computed CDF: the search + interpolation stage can then be checked bit for bit
+// against the reference's own CDF.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kWarps * 32)
-resample_kernel(const float* __restrict__ sdist_in, const float* __restrict__ w_in, const float* __restrict__ u,
+resample_kernel(const float* __restrict__ sdist_in, const float* __restrict__ w_in, const float* __restrict__ cw_in,
+                const float* __restrict__ u,
                 const float* __restrict__ near_, const float* __restrict__ far_, int64_t n_rays, int s_in, int s_out,
                 float padding, float anneal, float dom_lo, float dom_hi, float* __restrict__ sdist_out,
                 float* __restrict__ tdist_out, float* __restrict__ cw_out, int32_t* __restrict__ idx_out) {
@@ -36,6 +54,10 @@ resample_kernel(const float* __restrict__ sdist_in, const float* __restrict__ w_
   for (int i = lane; i <= s_in; i += 32) ts[i] = tin[i];
   __syncwarp();
 
+  if (cw_in) {
+    const float* ci = cw_in + ray * (s_in + 1);
+    for (int i = lane; i <= s_in; i += 32) cw[i] = ci[i];
+  } else {
   // logits (models.py:200-203) and their max
   const float* win = w_in + ray * s_in;
   float m = -INFINITY;
@@ -54,22 +76,19 @@ resample_kernel(const float* __restrict__ sdist_in, const float* __restrict__ w_
   }
   sum = warp_sum(sum);
   __syncwarp();
-  // CDF: cw[j] = min(1, sum_{i<j} w_i), cw[0] = 0, cw[s_in] = 1 (stepfun.py:149-154)
-  // (a parallel prefix sum is not monotone to the last ulp; the running max restores the monotonicity a
-  //  sequential cumsum of non-negative terms has, which the binary search below relies on)
-  float carry = 0.f, cmax = 0.f;
+  // CDF: cw[j] = min(1, sum_{i<j} w_i), cw[0] = 0, cw[s_in] = 1 (stepfun.py:149-154), fp64 prefix sums
+  double carry = 0.0;
   for (int base = 0; base < s_in; base += 32) {
     int i = base + lane;
-    float w = (i < s_in) ? __fdiv_rn(cw[i + 1], sum) : 0.f;
-    float c = warp_scan_incl(w, lane) + carry;
+    const double w = (i < s_in) ? (double)__fdiv_rn(cw[i + 1], sum) : 0.0;
+    const double c = warp_scan_incl_f64(w, lane) + carry;
     carry = __shfl_sync(RN_FULL, c, 31);
-    c = fmaxf(warp_scan_max(c, lane), cmax);
-    cmax = __shfl_sync(RN_FULL, c, 31);
-    if (i < s_in - 1) cw[i + 1] = fminf(c, 1.f);
+    if (i < s_in - 1) cw[i + 1] = fminf((float)c, 1.f);
   }
   if (lane == 0) {
     cw[0] = 0.f;
     cw[s_in] = 1.f;
+  }
   }
   __syncwarp();
   if (cw_out) {
@@ -119,7 +138,8 @@ resample_kernel(const float* __restrict__ sdist_in, const float* __restrict__ w_
 // prefix sums are 3 local adds + one warp scan instead of four 32-wide scans, loads / stores are vectorised or
 // staged, and the four binary searches of a lane run interleaved.
 __global__ void __launch_bounds__(kWarps * 32)
-resample128_kernel(const float* __restrict__ sdist_in, const float* __restrict__ w_in, const float* __restrict__ u,
+resample128_kernel(const float* __restrict__ sdist_in, const float* __restrict__ w_in, const float* __restrict__ cw_in,
+                   const float* __restrict__ u,
                    const float* __restrict__ near_, const float* __restrict__ far_, int64_t n_rays, float padding,
                    float anneal, float dom_lo, float dom_hi, float* __restrict__ sdist_out, float* __restrict__ tdist_out,
                    float* __restrict__ cw_out, int32_t* __restrict__ idx_out) {
@@ -133,11 +153,16 @@ resample128_kernel(const float* __restrict__ sdist_in, const float* __restrict__
   float* ts = sm_t[warp];
   float* cw = sm_cw[warp];
   float* cs = sm_c[warp];
-  const float4 w4 = __ldg(reinterpret_cast<const float4*>(w_in + ray * s) + lane);
+  const float4 w4 = cw_in ? make_float4(0.f, 0.f, 0.f, 0.f) : __ldg(reinterpret_cast<const float4*>(w_in + ray * s) + lane);
   const float4 u4 = __ldg(reinterpret_cast<const float4*>(u) + lane);
   const float* tin = sdist_in + ray * (s + 1);
   for (int i = lane; i <= s; i += 32) ts[i] = __ldg(tin + i);
+  if (cw_in) {
+    const float* ci = cw_in + ray * (s + 1);
+    for (int i = lane; i <= s; i += 32) cw[i] = __ldg(ci + i);
+  }
   __syncwarp();
+  if (!cw_in) {
   float t[5];
 #pragma unroll
   for (int k = 0; k < 5; ++k) t[k] = ts[4 * lane + k];
@@ -157,27 +182,23 @@ resample128_kernel(const float* __restrict__ sdist_in, const float* __restrict__
     sum += e[k];
   }
   sum = warp_sum(sum);
-  // CDF: cw[j] = min(1, sum_{i<j} p_i) with a running max (monotone to the last ulp), cw[0] = 0, cw[128] = 1
-  float c[4], run = 0.f;
+  // CDF: cw[j] = min(1, float(sum_{i<j} p_i)) with the sum in fp64 (see the header), cw[0] = 0, cw[128] = 1
+  double c[4], run = 0.0;
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
-    run += __fdiv_rn(e[k], sum);
+    run += (double)__fdiv_rn(e[k], sum);
     c[k] = run;
   }
-  const float scan = warp_scan_incl(run, lane);
-  const float off = scan - run;
-  float prev_max = warp_scan_max(off + c[3], lane);        // inclusive running max of the lanes' last values
-  prev_max = __shfl_up_sync(RN_FULL, prev_max, 1);
-  if (lane == 0) prev_max = 0.f;
-  float cm = prev_max;
+  double excl = __shfl_up_sync(RN_FULL, warp_scan_incl_f64(run, lane), 1);
+  if (lane == 0) excl = 0.0;
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
-    cm = fmaxf(cm, off + c[k]);
     const int j = 4 * lane + k + 1;          // cw index
-    if (j < s) cw[j] = fminf(cm, 1.f);
+    if (j < s) cw[j] = fminf((float)(excl + c[k]), 1.f);
   }
   if (lane == 0) cw[0] = 0.f;
   if (lane == 31) cw[s] = 1.f;
+  }
   __syncwarp();
   if (cw_out) {
     float* o = cw_out + ray * (s + 1);
@@ -949,6 +970,113 @@ normal_losses_kernel(const float* __restrict__ w, const float* __restrict__ norm
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// max_dilate_weights: stepfun.py:92-131 (+ the [1:-1] trim of its caller, models.py:186-187)
+//
+// The reference sorts the 3S+1 fenceposts t U (t[:-1] - eps) U (t[1:] + eps) and evaluates, for every new fencepost,
+// a dense [3S+1, S] mask "which dilated interval contains me" followed by a masked max.  Here one warp owns a ray:
+//   * the three source lists are each sorted already, so the sort is a 3-way merge: every source element finds its
+//     rank with two binary searches in the other two lists (ties: t before t0 before t1, any stable order gives the
+//     same sorted VALUES) and scatters its domain-clipped value;
+//   * t0 and t1 are monotone, so the intervals [t0_j, t1_j) containing a fencepost tau form one index window
+//     [#{t1 <= tau}, #{t0 <= tau} - 1]: two more binary searches and a range-max query on a sparse table of the pdf
+//     (log2(S) levels in shared memory) replace the mask;
+//   * weights = pdf * width, optional renormalisation by the warp-reduced sum.
+// fp32 operations are the reference's (explicit rn intrinsics), so the fenceposts are bit-exact; the weights differ
+// only through the order of the renormalising sum.
+// ---------------------------------------------------------------------------------------------
+// (count_le: defined with the interlevel loss above)
+__device__ __forceinline__ int count_lt(const float* a, int n, float x) {   // #{i < n : a[i] < x}
+  int lo = 0, hi = n;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (a[mid] < x) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+
+__global__ void __launch_bounds__(kWarps * 32)
+max_dilate_kernel(const float* __restrict__ t_in, const float* __restrict__ w_in, int64_t n_rays, int s, int levels,
+                  float dilation, float dom_lo, float dom_hi, int renormalize, int trim, float* __restrict__ t_out,
+                  float* __restrict__ w_out) {
+  extern __shared__ float smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m = 3 * s + 1;                         // dilated fenceposts
+  const int per_warp = (s + 1) + 2 * s + m + levels * s;
+  float* ts = smem + warp * per_warp;              // t        [s+1]
+  float* t0 = ts + (s + 1);                        // t[:-1] - dilation   [s]
+  float* t1 = t0 + s;                              // t[1:]  + dilation   [s]
+  float* td = t1 + s;                              // sorted + clipped    [3s+1]
+  float* tab = td + m;                             // sparse table of the pdf: tab[k*s + j] = max p[j .. j + 2^k - 1]
+  const int64_t ray = (int64_t)blockIdx.x * kWarps + warp;
+  if (ray >= n_rays) return;
+  const float eps2 = RN_EPS32 * RN_EPS32;
+  const float* tin = t_in + ray * (s + 1);
+  const float* win = w_in + ray * s;
+  for (int i = lane; i <= s; i += 32) ts[i] = tin[i];
+  __syncwarp();
+  for (int j = lane; j < s; j += 32) {
+    t0[j] = __fsub_rn(ts[j], dilation);
+    t1[j] = __fadd_rn(ts[j + 1], dilation);
+    tab[j] = __fdiv_rn(win[j], fmaxf(eps2, __fsub_rn(ts[j + 1], ts[j])));   // weight_to_pdf, stepfun.py:92-94
+  }
+  __syncwarp();
+  for (int k = 1; k < levels; ++k) {
+    const int half = 1 << (k - 1);
+    for (int j = lane; j < s; j += 32) {
+      const float a = tab[(k - 1) * s + j];
+      const float b = (j + half < s) ? tab[(k - 1) * s + j + half] : a;
+      tab[k * s + j] = fmaxf(a, b);
+    }
+    __syncwarp();
+  }
+  // 3-way merge by rank, values clipped to the domain (stepfun.py:113-116)
+  auto clipd = [&](float x) { return fminf(fmaxf(x, dom_lo), dom_hi); };
+  for (int i = lane; i <= s; i += 32) {
+    const float x = ts[i];
+    td[i + count_lt(t0, s, x) + count_lt(t1, s, x)] = clipd(x);
+  }
+  for (int j = lane; j < s; j += 32) {
+    const float x0 = t0[j], x1 = t1[j];
+    td[j + count_le(ts, s + 1, x0) + count_lt(t1, s, x0)] = clipd(x0);
+    td[j + count_le(ts, s + 1, x1) + count_le(t0, s, x1)] = clipd(x1);
+  }
+  __syncwarp();
+  // pdf at every new fencepost but the last: max over the window of dilated intervals that contain it (:118-126);
+  // weights = pdf * width (:127), optionally renormalised (:129-130).  With `trim` the first and last fencepost /
+  // weight are dropped on the way out (models.py:186-187).
+  float* wo = w_out + ray * (trim ? (m - 3) : (m - 1));
+  auto out_index = [&](int i) -> int { return trim ? ((i >= 1 && i < m - 2) ? i - 1 : -1) : i; };
+  float part = 0.f;
+  for (int i = lane; i < m - 1; i += 32) {
+    const float tau = td[i];
+    const int jlo = count_le(t1, s, tau);          // intervals with t1_j <= tau are over
+    const int jhi = count_le(t0, s, tau) - 1;      // intervals with t0_j <= tau have begun
+    float pd = 0.f;                                // (the reference's masked max runs over zeros as well)
+    if (jhi >= jlo) {
+      const int k = 31 - __clz(jhi - jlo + 1);
+      pd = fmaxf(pd, fmaxf(tab[k * s + jlo], tab[k * s + jhi - (1 << k) + 1]));
+    }
+    const float wv = __fmul_rn(pd, __fsub_rn(td[i + 1], tau));
+    part += wv;                                    // the sum runs over ALL weights, trimmed or not
+    const int o = out_index(i);
+    if (o >= 0) wo[o] = wv;
+  }
+  if (renormalize) {
+    const float denom = fmaxf(eps2, warp_sum(part));
+    for (int i = lane; i < m - 1; i += 32) {       // every lane rescales exactly the elements it wrote
+      const int o = out_index(i);
+      if (o >= 0) wo[o] = __fdiv_rn(wo[o], denom);
+    }
+  }
+  float* to = t_out + ray * (trim ? (m - 2) : m);
+  if (trim) {
+    for (int i = lane; i < m - 2; i += 32) to[i] = td[i + 1];
+  } else {
+    for (int i = lane; i < m; i += 32) to[i] = td[i];
+  }
+}
+
 inline unsigned blocks_for(int64_t n_rays) { return (unsigned)((n_rays + kWarps - 1) / kWarps); }
 
 template <typename K>
@@ -963,23 +1091,39 @@ int ensure_smem(K kernel, size_t bytes) {
 
 }  // namespace
 
-extern "C" int rn_resample(const float* sdist_in, const float* weights_in, const float* u, const float* near_,
+extern "C" int rn_resample(const float* sdist_in, const float* weights_in, const float* cw_in, const float* u, const float* near_,
                            const float* far_, int64_t n_rays, int s_in, int s_out, float padding, float anneal,
                            float dom_lo, float dom_hi, float* sdist_out, float* tdist_out, float* cw_out,
                            int32_t* idx_out, void* stream) {
   if (n_rays < 0 || s_in < 1 || s_out < 2) return rn_set_error(RN_ERR_ARG, "rn_resample: need s_in >= 1 and s_out >= 2");
+  if (!weights_in && !cw_in) return rn_set_error(RN_ERR_ARG, "rn_resample: need weights or a CDF");
   if (n_rays == 0) return RN_OK;
   if (s_in == 128 && s_out == 128) {
     resample128_kernel<<<blocks_for(n_rays), kWarps * 32, 0, (cudaStream_t)stream>>>(
-        sdist_in, weights_in, u, near_, far_, n_rays, padding, anneal, dom_lo, dom_hi, sdist_out, tdist_out, cw_out, idx_out);
+        sdist_in, weights_in, cw_in, u, near_, far_, n_rays, padding, anneal, dom_lo, dom_hi, sdist_out, tdist_out, cw_out, idx_out);
     RN_CUDA_CHECK_LAUNCH();
     return RN_OK;
   }
   size_t smem = (size_t)kWarps * (2 * (s_in + 1) + s_out) * sizeof(float);
   if (int rc = ensure_smem(resample_kernel, smem)) return rc;
   resample_kernel<<<blocks_for(n_rays), kWarps * 32, smem, (cudaStream_t)stream>>>(
-      sdist_in, weights_in, u, near_, far_, n_rays, s_in, s_out, padding, anneal, dom_lo, dom_hi, sdist_out, tdist_out,
+      sdist_in, weights_in, cw_in, u, near_, far_, n_rays, s_in, s_out, padding, anneal, dom_lo, dom_hi, sdist_out, tdist_out,
       cw_out, idx_out);
+  RN_CUDA_CHECK_LAUNCH();
+  return RN_OK;
+}
+
+extern "C" int rn_max_dilate_weights(const float* t, const float* w, int64_t n_rays, int s, float dilation, float dom_lo,
+                                     float dom_hi, int renormalize, int trim, float* t_out, float* w_out, void* stream) {
+  if (n_rays < 0 || s < 1 || s > 1024) return rn_set_error(RN_ERR_ARG, "rn_max_dilate_weights: need 1 <= s <= 1024");
+  if (n_rays == 0) return RN_OK;
+  int levels = 1;
+  while ((1 << levels) <= s) ++levels;            // floor(log2 s) + 1 sparse-table levels
+  const size_t smem = (size_t)kWarps * ((s + 1) + 2 * s + (3 * s + 1) + (size_t)levels * s) * sizeof(float);
+  if (smem > 200 * 1024) return rn_set_error(RN_ERR_UNSUPPORTED, "rn_max_dilate_weights: too many samples for the shared-memory tables");
+  if (int rc = ensure_smem(max_dilate_kernel, smem)) return rc;
+  max_dilate_kernel<<<blocks_for(n_rays), kWarps * 32, smem, (cudaStream_t)stream>>>(t, w, n_rays, s, levels, dilation, dom_lo, dom_hi,
+                                                                                     renormalize, trim, t_out, w_out);
   RN_CUDA_CHECK_LAUNCH();
   return RN_OK;
 }

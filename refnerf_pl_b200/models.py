@@ -11,6 +11,8 @@ import math as python_math
 from typing import Any, Callable, Tuple
 
 import numpy as np
+import dataclasses
+
 import torch
 from torch import nn
 
@@ -141,6 +143,19 @@ class MLP(nn.Module):
         named = dict(self.named_parameters())
         return [named[n] for n in _lib.param_names()]
 
+    def invalidate_packed(self):
+        """Drop the packed-weight cache.  It is keyed on (data_ptr, _version) of every parameter, which in-place updates
+        through `.data` (EMA, manual weight surgery) do not change: call this after such an update."""
+        self._packed = {}
+
+    def load_state_dict(self, *a, **k):
+        self._packed = {}
+        return super().load_state_dict(*a, **k)
+
+    def _apply(self, fn, *a, **k):
+        self._packed = {}
+        return super()._apply(fn, *a, **k)
+
     def packed_weights(self):
         prec = _lib.PREC_BY_NAME[self.precision]
         ps = self.ordered_params()
@@ -169,7 +184,8 @@ class MLP(nn.Module):
                               flat(g.radii, 1), self.ordered_params(), self.packed_weights(), training,
                               _lib.PREC_BY_NAME[self.precision], self.srgb_mapping, self.srgb_mapping_normalization,
                               float(self.density_bias), float(self.roughness_bias), float(self.rgb_premultiplier),
-                              float(self.rgb_bias), float(self.rgb_padding), int(self.chunk_rows), int(self.gemm_impl))
+                              float(self.rgb_bias), float(self.rgb_padding), int(self.chunk_rows), int(self.gemm_impl),
+                              bool(training and torch.is_grad_enabled()))
         density, rgb, normals, npred, gpred, tint, diffuse, spec, rough, _saved = out
         v3 = lambda t: t.reshape(lead + (s, 3))
         return dict(density=density.reshape(lead + (s,)), rgb=v3(rgb), normals=v3(normals) if training else None,
@@ -185,20 +201,6 @@ class NerfMLP(MLP):
 @configs.configurable
 class PropMLP(MLP):
     pass
-
-
-def _max_dilate_weights(t, w, dilation, domain, renormalize):
-    """stepfun.py:102-131 (disabled in every shipped config): sort-and-scan on the GPU."""
-    eps = torch.finfo(torch.float32).eps ** 2
-    p = w / torch.clamp(t[..., 1:] - t[..., :-1], min=eps)
-    t0, t1 = t[..., :-1] - dilation, t[..., 1:] + dilation
-    td = torch.clip(torch.sort(torch.cat([t, t0, t1], dim=-1), dim=-1).values, domain[0], domain[1])
-    inside = (t0[..., None, :] <= td[..., None]) & (t1[..., None, :] > td[..., None])
-    pd = torch.where(inside, p[..., None, :], torch.zeros_like(p[..., None, :])).amax(dim=-1)[..., :-1]
-    wd = pd * (td[..., 1:] - td[..., :-1])
-    if renormalize:
-        wd = wd / torch.clamp(wd.sum(dim=-1, keepdim=True), min=eps)
-    return td, wd
 
 
 _SRGB_MAPPINGS = ('none', 'linear', 'norm_linear', 'srgb', 'norm_srgb')
@@ -305,9 +307,9 @@ class Model(nn.Module):
             dilation = self.dilation_bias + self.dilation_multiplier * (self.init_s_far - self.init_s_near) / prod_num_samples
             prod_num_samples *= num_samples
             if i_level > 0 and (self.dilation_bias > 0 or self.dilation_multiplier > 0):
-                sdist, weights = _max_dilate_weights(sdist, weights.detach(), dilation,
-                                                     (self.init_s_near, self.init_s_far), True)
-                sdist, weights = sdist[..., 1:-1].contiguous(), weights[..., 1:-1].contiguous()
+                # stepfun.max_dilate_weights + the [1:-1] trim (models.py:177-187): one warp-per-ray kernel
+                sdist, weights = ops.max_dilate_weights(sdist.detach(), weights.detach(), float(dilation),
+                                                        float(self.init_s_near), float(self.init_s_far), True, True)
             if self.anneal_slope > 0:
                 s_ = self.anneal_slope
                 anneal = float((s_ * train_frac) / ((s_ - 1) * train_frac + 1))
@@ -362,23 +364,71 @@ def construct_model(rays, config, device='cuda', **model_kwargs):
     return Model(config=config, **model_kwargs).to(device)
 
 
-def render_image(render_fn, rays, config, verbose=True, device=None):
-    """models.py:763-825: chunked full-image render in eval mode."""
+def _write_chunk(buffers, chunk_renderings, idx0, n, num_rays):
+    """Copy one chunk's final-level rendering (and the ray_* bundles of every level) into the frame buffers."""
+    final = chunk_renderings[-1]
+    for k, v in final.items():
+        if k.startswith('ray_'):
+            continue
+        v = v.detach()
+        if k not in buffers:
+            buffers[k] = v.new_empty((num_rays,) + tuple(v.shape[1:]))
+        buffers[k][idx0:idx0 + n].copy_(v[:n])
+    for k in chunk_renderings[0]:
+        if k.startswith('ray_'):
+            buffers.setdefault(k, []).append([r[k].detach().clone() for r in chunk_renderings])
+
+
+def render_image(render_fn, rays, config, verbose=True, device=None, use_graph=None):
+    """models.py:763-825: chunked full-image render in eval mode -> dict of [H, W, ...] tensors (+ ray_* bundles).
+
+    Same chunking contract as the reference (`config.render_chunk_size` rays per `render_fn` call), but the per-chunk
+    Python / launch overhead of its loop (157 iterations x ~60 launches for an 800x800 frame at the reference's chunk of
+    4096, models.py:788-803) is taken off the critical path:
+      * every chunk's outputs are written straight into pre-sized [H*W, ...] frame buffers (no list of chunk dicts, no
+        `merge_chunks` concatenation, utils.py:192-204);
+      * when the frame has at least two full chunks and runs on CUDA without autograd, ONE chunk's forward is captured
+        into a CUDA graph over static ray buffers and replayed for every full chunk (`use_graph=False` disables it;
+        a ragged last chunk runs eagerly).  The graph replays exactly the kernels of the eager call.
+    """
     height, width = rays.origins.shape[:2]
     num_rays = height * width
     rays = rays.reshape(num_rays, -1)
-    chunks = []
-    for idx0 in range(0, num_rays, config.render_chunk_size):
-        chunk_rays = rays[idx0:idx0 + config.render_chunk_size]
+    chunk = int(config.render_chunk_size)
+    on_cuda = isinstance(rays.origins, torch.Tensor) and rays.origins.is_cuda
+    n_full = num_rays // chunk
+    if use_graph is None:
+        use_graph = on_cuda and n_full >= 2 and not torch.is_grad_enabled()
+    buffers = {}
+    start_eager = 0
+    if use_graph:
+        fields = [f.name for f in dataclasses.fields(rays)]
+        static = utils.Rays(**{k: getattr(rays, k)[:chunk].clone() for k in fields})
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):          # warm-up outside the capture: weight packing, smem attributes, caches
+            render_fn(static)
+        torch.cuda.current_stream().wait_stream(side)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            static_out, _ = render_fn(static)
+        for c in range(n_full):
+            idx0 = c * chunk
+            for k in fields:
+                getattr(static, k).copy_(getattr(rays, k)[idx0:idx0 + chunk])
+            graph.replay()
+            _write_chunk(buffers, static_out, idx0, chunk, num_rays)
+        start_eager = n_full * chunk
+    for idx0 in range(start_eager, num_rays, chunk):
+        chunk_rays = rays[idx0:idx0 + chunk]
         chunk_renderings, _ = render_fn(chunk_rays)
-        chunk_rendering = chunk_renderings[-1]
-        for k in chunk_renderings[0]:
-            if k.startswith('ray_'):
-                chunk_rendering[k] = [r[k] for r in chunk_renderings]
-        chunks.append({k: utils.recursive_detach(v) for k, v in chunk_rendering.items()})
-    rendering = utils.merge_chunks(chunks)
-    for k, z in rendering.items():
-        if not k.startswith('ray_'):
+        _write_chunk(buffers, chunk_renderings, idx0, min(chunk, num_rays - idx0), num_rays)
+    rendering = {}
+    for k, z in buffers.items():
+        if k.startswith('ray_'):
+            n_levels = len(z[0])
+            rendering[k] = [torch.cat([c[i] for c in z], dim=0) for i in range(n_levels)]
+        else:
             rendering[k] = z.reshape((height, width) + z.shape[1:])
     keys = [k for k in rendering if k.startswith('ray_')]
     if keys:

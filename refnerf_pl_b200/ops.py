@@ -58,9 +58,27 @@ def resample(sdist: Tensor, weights: Tensor, near: Tensor, far: Tensor, num_samp
     cw = torch.empty((n, s_in + 1) if want_aux else (0,), device=dev, dtype=torch.float32)
     idx = torch.empty((n, num_samples) if want_aux else (0,), device=dev, dtype=torch.int32)
     u = sample_grid(num_samples, dev)
-    _lib.check(lib.rn_resample(_ptr(sdist), _ptr(weights), _ptr(u), _ptr(near), _ptr(far), n, s_in, num_samples,
+    _lib.check(lib.rn_resample(_ptr(sdist), _ptr(weights), None, _ptr(u), _ptr(near), _ptr(far), n, s_in, num_samples,
                                padding, anneal, dom_lo, dom_hi, _ptr(so), _ptr(to), _ptr(cw), _ptr(idx), _stream()))
     return [so, to, cw, idx]
+
+
+def resample_from_cdf(sdist: Tensor, cw: Tensor, near: Tensor, far: Tensor, num_samples: int, dom_lo: float = 0.0,
+                      dom_hi: float = 1.0):
+    """Search + interpolation stage of the resampler on a GIVEN CDF `cw` [N, s_in+1] (math.sorted_interp, math.py:88-111,
+    and the fencepost construction of stepfun.py:246-258) -> (sdist_out, tdist_out, idx).  Test surface: fed with the
+    reference's own CDF the interval indices and fenceposts must match the reference bit for bit."""
+    lib = _lib.load()
+    sdist, cw, near, far = _f32c(sdist), _f32c(cw), _f32c(near), _f32c(far)
+    n, s1 = cw.shape
+    dev = sdist.device
+    so = torch.empty((n, num_samples + 1), device=dev, dtype=torch.float32)
+    to = torch.empty_like(so)
+    idx = torch.empty((n, num_samples), device=dev, dtype=torch.int32)
+    u = sample_grid(num_samples, dev)
+    _lib.check(lib.rn_resample(_ptr(sdist), None, _ptr(cw), _ptr(u), _ptr(near), _ptr(far), n, s1 - 1, num_samples,
+                               0.0, 1.0, dom_lo, dom_hi, _ptr(so), _ptr(to), None, _ptr(idx), _stream()))
+    return so, to, idx
 
 
 @resample.register_fake
@@ -69,6 +87,29 @@ def _(sdist, weights, near, far, num_samples, padding, anneal, dom_lo, dom_hi, w
     so = sdist.new_empty((n, num_samples + 1))
     return [so, torch.empty_like(so), sdist.new_empty((n, s_in + 1) if want_aux else (0,)),
             sdist.new_empty((n, num_samples) if want_aux else (0,), dtype=torch.int32)]
+
+
+@torch.library.custom_op(f'{NS}::max_dilate_weights', mutates_args=(), device_types='cuda')
+def max_dilate_weights(t: Tensor, w: Tensor, dilation: float, dom_lo: float, dom_hi: float, renormalize: bool,
+                       trim: bool) -> List[Tensor]:
+    """stepfun.max_dilate_weights (stepfun.py:102-131); trim=True also drops the first / last fencepost and weight as
+    models.py:186-187 does.  t [N,s+1], w [N,s] -> [t_dilated, w_dilated].  No gradient (its consumer is detached)."""
+    lib = _lib.load()
+    t, w = _f32c(t), _f32c(w)
+    n, s = w.shape
+    cut = 2 if trim else 0
+    to = torch.empty((n, 3 * s + 1 - cut), device=t.device, dtype=torch.float32)
+    wo = torch.empty((n, 3 * s - cut), device=t.device, dtype=torch.float32)
+    _lib.check(lib.rn_max_dilate_weights(_ptr(t), _ptr(w), n, s, dilation, dom_lo, dom_hi, int(renormalize), int(trim),
+                                         _ptr(to), _ptr(wo), _stream()))
+    return [to, wo]
+
+
+@max_dilate_weights.register_fake
+def _(t, w, dilation, dom_lo, dom_hi, renormalize, trim):
+    n, s = w.shape
+    cut = 2 if trim else 0
+    return [t.new_empty((n, 3 * s + 1 - cut)), t.new_empty((n, 3 * s - cut))]
 
 
 # ------------------------------------------------------------------------------------------
@@ -355,9 +396,10 @@ def mlp_pack(params: Sequence[Tensor], prec: int) -> Tensor:
 def mlp_forward(tdist: Tensor, origins: Tensor, dirs: Tensor, viewdirs: Tensor, radii: Tensor, params: Sequence[Tensor],
                 packed: Tensor, training: bool, prec: int, srgb_mapping: bool, srgb_norm: bool, density_bias: float,
                 roughness_bias: float, rgb_premultiplier: float, rgb_bias: float, rgb_padding: float, chunk_rows: int,
-                gemm_impl: int) -> List[Tensor]:
+                gemm_impl: int, keep_saved: bool) -> List[Tensor]:
     """-> [density [N,S], rgb, normals (empty in eval), normals_pred, grad_pred, tint, diffuse, specular [N,S,3],
-    roughness [N,S,1], saved (uint8: activations kept for the backward; empty in eval / when over the cap)].
+    roughness [N,S,1], saved (uint8: activations kept for the backward; empty in eval / when over the cap / when
+    `keep_saved` is False, e.g. a training-mode forward under torch.no_grad())].
     `params` only carries autograd edges; the arithmetic reads `packed`."""
     lib = _lib.load()
     n, s1 = tdist.shape
@@ -371,9 +413,14 @@ def mlp_forward(tdist: Tensor, origins: Tensor, dirs: Tensor, viewdirs: Tensor, 
         chunk_rows = default_chunk_rows(n * s, training)
     cfg = _mlp_config(prec, srgb_mapping, srgb_norm, density_bias, roughness_bias, rgb_premultiplier, rgb_bias,
                       rgb_padding, chunk_rows, gemm_impl)
-    saved_bytes = lib.rn_mlp_saved_bytes(ctypes.byref(cfg), n * s) if training else 0
+    saved_bytes = lib.rn_mlp_saved_bytes(ctypes.byref(cfg), n * s) if (training and keep_saved) else 0
     if saved_bytes > SAVED_BYTES_CAP:
         saved_bytes = 0
+    if saved_bytes:   # bound by what is actually free as well (the backward then recomputes chunk by chunk)
+        free_b, _ = torch.cuda.mem_get_info(dev)
+        cached = torch.cuda.memory_reserved(dev) - torch.cuda.memory_allocated(dev)
+        if saved_bytes > 0.8 * (free_b + cached):
+            saved_bytes = 0
     saved = torch.empty((saved_bytes,), device=dev, dtype=torch.uint8)
     ws_bytes = lib.rn_mlp_workspace_bytes(ctypes.byref(cfg), (2 if saved_bytes else 1) if training else 0)
     ws = torch.empty((ws_bytes,), device=dev, dtype=torch.uint8)
@@ -388,7 +435,7 @@ def mlp_forward(tdist: Tensor, origins: Tensor, dirs: Tensor, viewdirs: Tensor, 
 
 @mlp_forward.register_fake
 def _(tdist, origins, dirs, viewdirs, radii, params, packed, training, prec, srgb_mapping, srgb_norm, density_bias,
-      roughness_bias, rgb_premultiplier, rgb_bias, rgb_padding, chunk_rows, gemm_impl):
+      roughness_bias, rgb_premultiplier, rgb_bias, rgb_padding, chunk_rows, gemm_impl, keep_saved):
     n, s1 = tdist.shape
     s = s1 - 1
     f = lambda *shape: tdist.new_empty(shape)
@@ -441,7 +488,7 @@ def _(tdist, origins, dirs, viewdirs, radii, packed, saved, grads, prec, srgb_ma
 def _mlp_setup(ctx, inputs, output):
     (tdist, origins, dirs, viewdirs, radii, params, packed, training, *scalars) = inputs
     ctx.save_for_backward(tdist, origins, dirs, viewdirs, radii, packed, output[9])
-    ctx.scalars = scalars
+    ctx.scalars = scalars[:-1]   # (keep_saved belongs to the forward only)
     ctx.param_shapes = [p.shape for p in params]
     ctx.mark_non_differentiable(output[2], output[9])  # density-gradient normals are a constant
     ctx.set_materialize_grads(False)
@@ -454,7 +501,7 @@ def _mlp_backward(ctx, grads):
     g = [grads[i] if grads[i] is not None else empty for i in order]
     flat = mlp_backward(tdist, origins, dirs, viewdirs, radii, packed, saved, g, *ctx.scalars)
     pg = [t.view(shape) for t, shape in zip(flat.split(_param_sizes()), ctx.param_shapes)]
-    return (None, None, None, None, None, pg, None, None) + (None,) * len(ctx.scalars)
+    return (None, None, None, None, None, pg, None, None) + (None,) * (len(ctx.scalars) + 1)
 
 
 torch.library.register_autograd(f'{NS}::mlp_forward', _mlp_backward, setup_context=_mlp_setup)

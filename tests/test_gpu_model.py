@@ -305,3 +305,141 @@ def test_fp16_tiny_batches_track_parity_mode(n_rays):
     assert abs(l16 - l3) <= 1e-3 * abs(l3) + 1e-6
     assert float((c16 - c3).abs().max()) <= 1e-3
     assert float((g16 - g3).norm()) <= 5e-2 * float(g3.norm()) + 1e-12
+
+
+def test_geometry_config_training_losses_vs_reference_fixture():
+    """BASELINE config 5 (configs/llff_refnerf_geometry_losses.gin) as one training step through this package:
+    main forward, device-side noisy rays, second forward, data + orientation + predicted-normal + consistency
+    (diffuse / specular / normals, 'var') + distance-consistency + acc + weights-entropy losses, backward -- against
+    the unmodified reference's values and gradients (tests/golden/llff_geom_losses.npz)."""
+    from refnerf_pl_b200 import train_utils
+    from tests._cases import GOLDEN, RAY_KEYS
+    g = np.load(os.path.join(GOLDEN, 'llff_geom_losses.npz'))
+    model, cfg = build_model('bf16x3', gin='llff_refnerf_geometry_losses.gin')
+    load_params(model, case_params(g))
+    model.train(True)
+    r = rays_obj({k: torch.tensor(g['rays_' + k]) for k in RAY_KEYS})
+    gt = torch.tensor(g['gt_rgb'], device=DEV)
+    warm = float(g['warmup_ratio'])
+    step = int(round(warm * cfg.consistency_warmup_steps * cfg.max_steps))
+    assert abs(train_utils.consistency_warmup_ratio(cfg, step) - warm) < 1e-9
+    loss, losses, stats, rend, hist = train_utils.training_losses(model, r, gt, cfg, 1.0, step, xyz_angles=g['xyz_angles'])
+    got = {k: float(v) for k, v in losses.items()}
+    got['orientation+predicted'] = got.pop('normals')
+    ref = {k[5:]: float(g[k]) for k in g.files if k.startswith('loss_')}
+    ref['orientation+predicted'] = ref.pop('orientation') + ref.pop('predicted_normals')
+    rep = {}
+    for k, v in ref.items():
+        rep[k] = abs(got[k] - v) / (abs(v) + 1e-3 * abs(float(g['train_loss'])) * 1e-3)
+        assert abs(got[k] - v) <= 2e-3 * abs(v) + 1e-9, (k, got[k], v)
+    assert abs(float(loss) - float(g['train_loss'])) <= 1e-3 * abs(float(g['train_loss']))
+    loss.backward()
+    bad = {}
+    for kname, p in model.nerf_mlp.named_parameters():
+        ref_norm = float(g['grad_norm_' + kname])
+        e_norm = abs(float(p.grad.double().norm()) - ref_norm) / max(ref_norm, 1e-30)
+        sub, ref_sub = p.grad.reshape(-1)[::97].cpu().numpy(), g['grad_sub_' + kname]
+        e_sub = float(np.linalg.norm(sub - ref_sub) / max(np.linalg.norm(ref_sub), 1e-30))
+        rep['grad_' + kname] = max(e_norm, e_sub)
+        if max(e_norm, e_sub) > 1e-2:
+            bad[kname] = max(e_norm, e_sub)
+    _report('llff_geom_losses/bf16x3/step', rep)
+    assert not bad, bad
+
+
+@pytest.mark.parametrize('variant', ['anneal', 'dilate', 'anneal+dilate', 'levels3'])
+def test_model_options_off_the_shipped_configs_match_oracle(variant):
+    """Model options every shipped gin leaves at their neutral value (models.py:168-203): the annealed
+    resampling logits (anneal_slope > 0, train_frac < 1), max-dilated proposal weights (dilation_multiplier /
+    dilation_bias > 0, the rn_max_dilate_weights kernel + the 382-bin resampler) and num_levels != 2, against the CPU
+    oracle on the same rays and weights."""
+    from refnerf_pl_b200 import synthetic
+    mk = {}
+    if 'anneal' in variant:
+        mk['anneal_slope'] = 10.0
+    if 'dilate' in variant:
+        mk.update(dilation_multiplier=0.5, dilation_bias=0.0025)
+    if variant == 'levels3':
+        mk['num_levels'] = 3
+    train_frac = 0.3
+    p = O.init_params(seed=12, bias_std=0.1, weight_scale=1.6)
+    rays = synthetic.blender_rays(40, seed=31)
+    model, _ = build_model('bf16x3', model_kwargs=mk)
+    load_params(model, p)
+    model.eval()
+    with torch.no_grad():
+        rend, hist = model(rays_obj(rays), train_frac, True)
+    rt = {k: torch.tensor(v) for k, v in rays.items()}
+    with torch.no_grad():
+        orend, ohist = O.model_forward(p, rt, train_frac, True, False, model_cfg=mk)
+    assert len(rend) == len(orend) == mk.get('num_levels', 2)
+    for lvl in range(len(rend)):
+        sd, osd = hist[lvl]['sdist'].cpu(), ohist[lvl]['sdist']
+        if lvl == 0:
+            assert torch.equal(sd, osd)
+        else:
+            assert float((sd - osd).abs().max()) <= 2e-3, (variant, lvl)
+        assert float((rend[lvl]['rgb'].cpu() - orend[lvl]['rgb']).abs().max()) <= 1e-3, (variant, lvl)
+        assert float((rend[lvl]['acc'].cpu() - orend[lvl]['acc']).abs().max()) <= 1e-3, (variant, lvl)
+
+
+def test_render_image_graph_and_eager_match_oracle():
+    """models.render_image (models.py:763-825): a small frame rendered in chunks -- CUDA-graph replay over a fixed chunk
+    with direct writes into the [H,W,.] buffers, a ragged last chunk, and the plain eager loop -- all give the same
+    frame, and that frame matches the CPU oracle evaluated on every ray at once."""
+    from refnerf_pl_b200 import models, synthetic, utils
+    h, w = 20, 24
+    p = O.init_params(seed=13, bias_std=0.1, weight_scale=1.4)
+    rays = synthetic.blender_rays(h * w, seed=41)
+    model, cfg = build_model('bf16x3')
+    load_params(model, p)
+    model.eval()
+    frame = utils.Rays(**{k: torch.tensor(v).reshape(h, w, -1) for k, v in rays.items()}).to(DEV)
+    fn = lambda r: model(r, 1.0, True)
+    outs = {}
+    with torch.no_grad():
+        for name, chunk, graph in (('graph', 96, True), ('ragged', 100, True), ('eager', 96, False), ('one', 4096, None)):
+            cfg.render_chunk_size = chunk
+            outs[name] = models.render_image(fn, frame, cfg, use_graph=graph)
+    ref = outs['one']
+    assert ref['rgb'].shape == (h, w, 3) and ref['acc'].shape == (h, w) and ref['distance_median'].dtype == torch.float64
+    for name in ('graph', 'ragged', 'eager'):
+        for k in ('rgb', 'diffuse', 'specular', 'distance', 'acc', 'normals_pred', 'roughness', 'distance_median'):
+            assert torch.equal(outs[name][k], ref[k]), (name, k)
+        assert len(outs[name]['ray_sdist']) == 2 and outs[name]['ray_sdist'][0].shape[-1] == 129
+    rt = {k: torch.tensor(v) for k, v in rays.items()}
+    with torch.no_grad():
+        orend, _ = O.model_forward(p, rt, 1.0, True, False)
+    for k in ('rgb', 'acc', 'distance'):
+        a = ref[k].reshape(h * w, -1).cpu()
+        b = orend[-1][k].reshape(h * w, -1)
+        assert float((a - b).abs().max()) <= (1e-3 if k != 'distance' else 5e-3), k
+
+
+def test_training_mode_forward_under_no_grad_keeps_no_activations():
+    """a training-mode forward under torch.no_grad() (e.g. a validation pass that wants the density-gradient
+    normals) must not allocate the saved-activation region; packed weights follow load_state_dict / .to()."""
+    from refnerf_pl_b200 import synthetic
+    model, _ = build_model('bf16x3')
+    model.train(True)
+    r = rays_obj(synthetic.blender_rays(2048, seed=3))
+    model(r, 1.0, False)
+    torch.cuda.synchronize()
+    torch.cuda.reset_peak_memory_stats()
+    base = torch.cuda.memory_allocated()
+    with torch.no_grad():
+        rend, hist = model(r, 1.0, False)
+    torch.cuda.synchronize()
+    peak_nograd = torch.cuda.max_memory_allocated() - base
+    assert hist[0]['normals'] is not None
+    torch.cuda.reset_peak_memory_stats()
+    rend, hist = model(r, 1.0, False)
+    torch.cuda.synchronize()
+    peak_grad = torch.cuda.max_memory_allocated() - base
+    assert peak_nograd < 0.7 * peak_grad, (peak_nograd, peak_grad)
+    before = rend[1]['rgb'].detach().clone()
+    sd = {k: v * 1.5 for k, v in model.nerf_mlp.state_dict().items()}
+    model.nerf_mlp.load_state_dict(sd)
+    with torch.no_grad():
+        rend2, _ = model(r, 1.0, False)
+    assert float((rend2[1]['rgb'] - before).abs().max()) > 1e-4   # new weights are in use

@@ -44,10 +44,40 @@ def test_resample_golden(ops, gold):
     last = torch.clamp(2 * centers[..., -1:] - mid[..., -1:], max=1.0)
     assert torch.equal(so, torch.cat([first, mid, last], -1))
     assert torch.equal(to, so)  # near=0, far=1
-    # against the reference's own outputs: indices agree except where u is within an ulp of a CDF knot
-    mism = (idx.numpy() != gold['rs_idx']).mean()
-    assert mism <= 2e-3, mism
+    # against the reference's own outputs: the CDF differs only through the softmax (CUDA expf vs the CPU's vectorised
+    # exp, order of the normalising sum; the cumulative sum itself is fp64 on both sides), so indices can differ only
+    # where u lies within those few ulps of a CDF knot.  The measured rate is logged.
+    mism = float((idx.numpy() != gold['rs_idx']).mean())
+    cw_ulp = float(np.abs(cw.numpy() - gold['rs_cw']).max() / 2.0 ** -24)
+    import json, os
+    os.makedirs('gpurun_out', exist_ok=True)
+    with open('gpurun_out/parity_report.jsonl', 'a') as f:
+        f.write(json.dumps({'case': 'resample_golden', 'index_mismatch_rate_vs_reference': mism,
+                            'mismatching_indices': int((idx.numpy() != gold['rs_idx']).sum()), 'indices': int(idx.numel()),
+                            'cdf_max_abs_diff_in_ulp_of_1': cw_ulp,
+                            'sdist_max_abs_diff': float(np.abs(so.numpy() - gold['rs_sdist']).max())}) + '\n')
+    assert mism <= 5e-4, mism
     assert np.abs(so.numpy() - gold['rs_sdist']).max() <= 1e-5   # few-ulp CDF differences / narrow CDF steps
+
+
+def test_resample_search_stage_bit_exact_on_reference_cdf(ops, gold):
+    """north_star: "resampled interval indices must match bit-exactly".  Fed with the REFERENCE's CDF (gold rs_cw, from
+    the unmodified reference), the kernel's search + interpolation + fencepost stage must reproduce the reference's
+    interval indices and resampled fenceposts bit for bit -- including zero-weight runs and duplicate fenceposts."""
+    t, cw = torch.tensor(gold['rs_t']), torch.tensor(gold['rs_cw'])
+    n = t.shape[0]
+    near, far = torch.zeros(n, 1, device=DEV), torch.ones(n, 1, device=DEV)
+    so, to, idx = ops.resample_from_cdf(t.to(DEV), cw.to(DEV), near, far, 128)
+    assert np.array_equal(idx.cpu().numpy(), gold['rs_idx'])
+    assert np.array_equal(so.cpu().numpy(), gold['rs_sdist'])
+    # generic (s_in != 128) kernel on the same data: resample 128 bins to 64 samples, against the oracle on that CDF
+    so64, _, idx64 = ops.resample_from_cdf(t.to(DEV), cw.to(DEV), near, far, 64)
+    u64 = O.sample_grid(64).expand(n, 64)
+    assert torch.equal(idx64.cpu().long(), O.interval_index(u64, cw))
+    c = O.sorted_interp(u64, cw, t)
+    mid = (c[..., 1:] + c[..., :-1]) / 2
+    ref = torch.cat([torch.clamp(2 * c[..., :1] - mid[..., :1], min=0.0), mid, torch.clamp(2 * c[..., -1:] - mid[..., -1:], max=1.0)], -1)
+    assert torch.equal(so64.cpu(), ref)
 
 
 def test_resample_level0_constant(ops, gold):
@@ -258,3 +288,29 @@ def test_pixels_to_rays_matches_reference_golden(golden_dir):
         out2 = camera_utils.pixels_to_rays(px, py, p2c[ci.long()], c2w[ci.long()], pixtocam_ndc=p2c[0] if ndc else None)
         for a, b in zip(out, out2):
             assert torch.equal(a, b)
+
+
+def test_max_dilate_weights_golden_and_oracle(ops, gold):
+    """stepfun.max_dilate_weights (stepfun.py:102-131): fenceposts bit-exact, weights within 1e-7 of the unmodified
+    reference (ops.npz dil_t / dil_w); the trimmed form equals the [1:-1] slice (models.py:186-187); random rays with
+    duplicate fenceposts, zero weights and bins far narrower than the dilation against the oracle."""
+    t, w = torch.tensor(gold['lo_t']), torch.tensor(gold['lo_w'])
+    td, wd = ops.max_dilate_weights(t.to(DEV), w.to(DEV), 0.01, 0.0, 1.0, True, False)
+    assert np.array_equal(td.cpu().numpy(), gold['dil_t'])
+    assert np.abs(wd.cpu().numpy() - gold['dil_w']).max() <= 1e-7
+    tt, wt = ops.max_dilate_weights(t.to(DEV), w.to(DEV), 0.01, 0.0, 1.0, True, True)
+    assert torch.equal(tt, td[:, 1:-1]) and torch.equal(wt, wd[:, 1:-1])
+    g = torch.Generator().manual_seed(5)
+    for s, dil in ((128, 0.0064), (128, 0.05), (37, 0.002), (1, 0.1)):
+        n = 301
+        t = torch.sort(torch.rand(n, s + 1, generator=g) ** 3, -1).values      # crowded near 0: many bins inside +-dilation
+        if s > 8:
+            t[::3, 4:8] = t[::3, 4:5]                                         # duplicate fenceposts
+        w = torch.rand(n, s, generator=g)
+        w[1::4] = 0.0
+        for renorm in (True, False):
+            rt, rw = O.max_dilate_weights(t, w, dil, domain=(0.0, 1.0), renormalize=renorm)
+            kt, kw = ops.max_dilate_weights(t.to(DEV), w.to(DEV), dil, 0.0, 1.0, renorm, False)
+            assert torch.equal(kt.cpu(), rt), (s, dil)
+            scale = max(1.0, float(rw.abs().max()))
+            assert float((kw.cpu() - rw).abs().max()) <= 2e-7 * scale, (s, dil, renorm)

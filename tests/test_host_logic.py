@@ -103,3 +103,45 @@ def test_colour_and_normal_helpers():
         assert torch.equal(r, ns.ref_utils.reflect(d, n))
         m = ref_utils.l2_normalize(torch.randn(200, 3, generator=g))
         assert float(ref_utils.compute_weighted_mae(w, n, m)) == pytest.approx(float(ns.ref_utils.compute_weighted_mae(w, n, m)), rel=1e-6)
+
+
+def test_geometry_losses_and_noisy_rays_match_reference_fixture():
+    """configs/llff_refnerf_geometry_losses.gin glue (sample_utils.py:40-80, train_utils.py:207-325) on the renderings
+    the unmodified reference produced (tests/golden/llff_geom_losses.npz, oracle/make_golden.py geometry): the noisy
+    rays and every rendering-level loss term must reproduce the reference's values."""
+    import os
+    import numpy as np
+    import torch
+    from refnerf_pl_b200 import configs, sample_utils, train_utils, utils
+    from tests._cases import GOLDEN, RAY_KEYS
+    g = np.load(os.path.join(GOLDEN, 'llff_geom_losses.npz'))
+    root = os.path.dirname(GOLDEN.rstrip('/'))
+    configs.clear_bindings()
+    configs.parse_gin_files_and_bindings([os.path.join(os.path.dirname(root), 'configs', 'llff_refnerf_geometry_losses.gin')])
+    cfg = configs.Config()
+    assert cfg.sample_noise_angles == 4 and cfg.consistency_diffuse_loss_type == 'var'
+    rays = utils.Rays(**{k: torch.tensor(g['rays_' + k]) for k in RAY_KEYS})
+    rend = [{k: torch.tensor(g[f'rend{l}_{k}']) for k in ('rgb', 'diffuse', 'specular', 'distance', 'acc', 'normals', 'normals_pred')}
+            for l in range(2)]
+    rend_n = [{k: torch.tensor(g[f'noisy_rend{l}_{k}']) for k in ('rgb', 'diffuse', 'specular', 'distance', 'acc', 'normals', 'normals_pred')}
+              for l in range(2)]
+    warm = float(g['warmup_ratio'])
+    noisy = sample_utils.sample_noisy_rays(rays, rend[-1], cfg.sample_angle_range, cfg.sample_noise_size,
+                                           cfg.sample_noise_angles, warm, xyz_angles=g['xyz_angles'])
+    for k in ('origins', 'directions', 'viewdirs'):
+        assert np.abs(getattr(noisy, k).numpy() - g['noisy_' + k]).max() <= 1e-6, k
+    assert noisy.origins.shape == (512, 3) and noisy.near.shape == (512, 1)
+
+    class M:
+        num_levels = 2
+    close = lambda a, key: abs(float(a) - float(g[key])) <= 2e-5 * abs(float(g[key])) + 1e-12
+    d, s, n = train_utils.noisy_consistency_loss(M, rend, rend_n, cfg, warm)
+    assert close(d, 'loss_diffuse_consistency') and close(s, 'loss_specular_consistency') and close(n, 'loss_normals_consistency')
+    assert close(train_utils.noisy_distance_consistency_loss(M, rays, noisy, rend, rend_n, cfg, warm), 'loss_distance_consistency')
+    assert close(train_utils.accumulated_weights_loss(rend, cfg), 'loss_acc')
+    gt = torch.tensor(g['gt_rgb'])
+    assert close(train_utils.compute_data_loss(gt, rend, rays.lossmult, cfg)[0], 'loss_data')
+    # warm-up schedule of nerf_system.py:97-113
+    assert train_utils.consistency_warmup_ratio(cfg, 0) == 0.0
+    assert abs(train_utils.consistency_warmup_ratio(cfg, 75000) - 0.5) < 1e-12
+    assert train_utils.consistency_warmup_ratio(cfg, 200000) == 1.0
