@@ -150,7 +150,9 @@ typedef struct RnMlpConfig {
   float rgb_bias;
   float rgb_padding;        /* models.py:729                                               */
   int chunk_rows;           /* rows processed per internal chunk (multiple of 128)         */
-  int gemm_impl;            /* 0 = default (fused SS chains in bf16), 1 = SIMT GEMMs, 2 = per-layer tcgen05, 3 = fused TS chains (A operand in TMEM) */
+  int gemm_impl;            /* 0 = default (fused tcgen05 chains: bf16 / fp16 / split-bf16), 1 = SIMT GEMMs, 2 = per-layer tcgen05 */
+  int deterministic_wgrad;  /* 1 = weight / bias gradients are reduced over the row-split CTAs in a fixed order (per-CTA partial
+                               tiles + one reduction pass) instead of with floating-point atomics: bit-reproducible steps */
 } RnMlpConfig;
 
 /* bytes of the packed-weight blob / of the scratch workspace for the given chunk size.
@@ -205,6 +207,13 @@ RN_API int rn_wgrad_test(const float* dy, const float* x, int64_t m, int n, int 
 RN_API int rn_gemm_bench(int64_t m, int prec, int impl, int iters, float* ms_out, void* scratch, size_t scratch_bytes,
                   void* stream);
 
+/* fp16 mode only: how many times (per wgrad launch and thread) a gradient element saturated the fp16 range since the
+ * last reset.  The dgrad chains run in one power-of-two scale per chain chosen from the chain's seed tile; an element
+ * growing more than 16x through a chain is clamped to +-65504 by the saturating conversion, which would bias the weight
+ * gradients silently.  0 = no clamping happened.  Synchronises the device; reset != 0 clears the counter.
+ * (The split-bf16 and bf16 modes have fp32's exponent range and need no such check.) */
+RN_API int64_t rn_fp16_saturation_count(int reset);
+
 /* ---- instrumentation -------------------------------------------------------------------------
  * rn_launch_count: kernels launched by this library since load (process-wide).
  * rn_prof_enable(1) makes the GEMM launchers bracket every launch with CUDA events on the launching
@@ -214,6 +223,9 @@ RN_API int rn_gemm_bench(int64_t m, int prec, int impl, int iters, float* ms_out
 RN_API int64_t rn_launch_count(void);
 RN_API int rn_prof_enable(int on);
 RN_API int rn_prof_summary(int cls, int64_t* launches, double* total_ms, double* algo_flops);
+/* the same plus the FLOPs the tensor pipe executed for those launches (padded shapes x MMAs per K step: 3 for the
+ * split-bf16 forward / normals chains, 2 for its loss-backward chains, 1 otherwise) */
+RN_API int rn_prof_summary2(int cls, int64_t* launches, double* total_ms, double* algo_flops, double* exec_flops);
 
 #ifdef __cplusplus
 }

@@ -18,7 +18,7 @@ NUM_PARAMS = 46
 class RnMlpConfig(Structure):
     _fields_ = [('prec', c_int), ('srgb_mapping', c_int), ('srgb_normalization', c_int), ('density_bias', c_float),
                 ('roughness_bias', c_float), ('rgb_premultiplier', c_float), ('rgb_bias', c_float),
-                ('rgb_padding', c_float), ('chunk_rows', c_int), ('gemm_impl', c_int)]
+                ('rgb_padding', c_float), ('chunk_rows', c_int), ('gemm_impl', c_int), ('deterministic_wgrad', c_int)]
 
 
 class RnMlpOutputs(Structure):
@@ -60,6 +60,8 @@ _SIGNATURES = {
     'rn_launch_count': (c_int64, []),
     'rn_prof_enable': (c_int, [c_int]),
     'rn_prof_summary': (c_int, [c_int, POINTER(c_int64), POINTER(c_double), POINTER(c_double)]),
+    'rn_fp16_saturation_count': (c_int64, [c_int]),
+    'rn_prof_summary2': (c_int, [c_int, POINTER(c_int64), POINTER(c_double), POINTER(c_double), POINTER(c_double)]),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)

@@ -18,7 +18,7 @@
 //     prefetched one tile ahead by the dgrad chains; eval touches HBM only for the chain input and the head outputs.
 //
 // Roles per CTA (384 threads): warp 0 TMA producer, warp 1 MMA issuer (leader CTA only), warp 2 TMEM
-// allocator, warps 4-11 epilogue (warp % 4 = TMEM lane quadrant, (warp - 4) / 4 = column half).
+// allocator, warp 3 store warp (TMA saves), warps 4-11 epilogue (warp % 4 = TMEM lane quadrant, (warp - 4) / 4 = column half).
 #include <stdio.h>
 #include <stdlib.h>
 
@@ -62,7 +62,9 @@ chain_pair_kernel(const __grid_constant__ PairMaps maps, const __grid_constant__
   uint64_t* seed_done = bars + 22;     // [2]  leader's: 16 arrivals (seed op: activation tile generated).  A separate
                                        //      barrier: a warp's seed arrival must not be able to land in the acc_free
                                        //      phase of the op before it (no wait separates the two arrivals)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 24);
+  uint64_t* save_ready = bars + 24;    // [2]  per CTA: 8 arrivals (epilogue warps: their part of act[t] is written and fenced)
+  uint64_t* save_drained = bars + 26;  // [2]  per CTA: 1 arrival (store warp: the TMA saves of act[t] have read shared memory)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 28);
 
   const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
@@ -82,7 +84,11 @@ chain_pair_kernel(const __grid_constant__ PairMaps maps, const __grid_constant__
       mbar_init(&acc_full[i], 1);
       mbar_init(&acc_free[i], 16);
     }
-    mbar_init(in2_ready, 8);
+    mbar_init(in2_ready, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&save_ready[i], 8);
+      mbar_init(&save_drained[i], 1);
+    }
     mbar_init(&seed_done[0], 16);
     mbar_init(&seed_done[1], 16);
     fence_barrier_init();
@@ -272,6 +278,54 @@ chain_pair_kernel(const __grid_constant__ PairMaps maps, const __grid_constant__
         }
       }
     }
+  } else if (warp == 3) {
+    // ===== store warp: issues the TMA saves of both tiles (one [128 x 64] box per K block) so that the epilogue warps
+    // never block on the TMA queue; signals save_drained[t] once the stores of act[t] have READ shared memory, and
+    // in2_ready once a save that this launch re-loads is complete in global memory =====
+    uint32_t nsave0 = 0, nsave1 = 0;
+    bool any = false;
+    for (int64_t st = cluster_id; st < num_super; st += num_clusters) {
+      for (int l = 0; l < p.num_ops; ++l) {
+        const PairOp& L = p.op[l];
+        const bool hidden = L.kind == 0 || (MODE == 1 && L.kind == 2);
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+          if (hidden && L.save) {
+            const uint32_t n = t ? nsave1 : nsave0;
+            mbar_wait(&save_ready[t], n & 1u);
+            if (t) ++nsave1; else ++nsave0;
+            const int64_t row0 = st * 512 + t * 256 + (int64_t)rank * 128;
+            if (elect_one_sync()) {
+              if (row0 < p.m) {
+#pragma unroll
+                for (int c = 0; c < 4; ++c)
+                  tma_store_2d(&maps.save[l], smem_base + (uint32_t)(t * kActBytes + c * kBlkBytes), c * 64, (int)row0);
+              }
+              tma_store_commit();
+              // the next save of this tile is at least one op (> 2 000 cycles) away: waiting here costs nothing and keeps
+              // the hand-back unconditional (no dependence on a later save being issued)
+              tma_store_wait_read<0>();
+              mbar_arrive(&save_drained[t]);
+            }
+            __syncwarp();
+            any = true;
+          }
+          if (l == p.in2_sync_op && t == 1) {
+            // the save that a later op of this super tile re-loads (at least 3 ops older) must be complete in global memory
+            if (elect_one_sync()) {
+              if (hidden && L.save) asm volatile("cp.async.bulk.wait_group 2;" ::: "memory");
+              else asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+              mbar_arrive(in2_ready);
+            }
+            __syncwarp();
+          }
+        }
+      }
+    }
+    if (any) {
+      if (elect_one_sync()) tma_store_wait_all();
+      __syncwarp();
+    }
   } else if (warp >= 4) {
     // ===== epilogue warps: q = TMEM lane quadrant (32 rows), h = column half (128 columns = K blocks 2h, 2h+1) =====
     const int q = (warp - 4) & 3;
@@ -284,8 +338,8 @@ chain_pair_kernel(const __grid_constant__ PairMaps maps, const __grid_constant__
     const uint32_t seed_addr0 = map_to_cta(smem_u32(&seed_done[0]), 0);
     uint32_t opcount = 0;
     uint32_t nfull = 0;                  // accumulator commits consumed so far (seed ops have none)
-    uint32_t has_group = 0, newer = 0;   // TMA-store bookkeeping, bit t (see below)
-    bool any_store = false;
+    uint32_t outstanding = 0;            // bit t: a save of act[t] has been handed to the store warp and not yet seen drained
+    uint32_t drained_phase = 0;          // bit t: parity of the next save_drained[t] phase to wait for
     uint4 bits_next = make_uint4(0, 0, 0, 0);
     auto load_bits = [&](int64_t st, int l, int t) -> uint4 {
       // ReLU bits of this thread's row for op l (this warp's 128 columns = words 4h .. 4h+3; relu_bits_index layout:
@@ -335,13 +389,11 @@ chain_pair_kernel(const __grid_constant__ PairMaps maps, const __grid_constant__
           }
           const uint32_t taddr = tmem_base + (uint32_t)t * 256u + ((uint32_t)(q * 32) << 16) + (uint32_t)(h * 128);
           if (hidden) {
-            if (has_group >> t & 1u) {
-              // the TMA stores that read this warp's part of act[t] must have drained it before it is overwritten
-              if (lane == 0) {
-                if (newer >> t & 1u) tma_store_wait_read<1>(); else tma_store_wait_read<0>();
-              }
-              __syncwarp();
-              has_group &= ~(1u << t);
+            if (outstanding >> t & 1u) {
+              // the TMA stores that read act[t] must have drained it before it is overwritten
+              mbar_wait(&save_drained[t], drained_phase >> t & 1u);
+              drained_phase ^= 1u << t;
+              outstanding &= ~(1u << t);
             }
             const uint32_t act_row = smem_base + (uint32_t)(t * kActBytes + r_in_tile * 128);
             const uint32_t bits_arr[4] = {bits_cur.x, bits_cur.y, bits_cur.z, bits_cur.w};
@@ -393,34 +445,12 @@ chain_pair_kernel(const __grid_constant__ PairMaps maps, const __grid_constant__
             __syncwarp();
             if (tr) p.trace[(opcount * 2 + t) * 8 + 4] = clock64();
             if (lane == 0) {
+              // (the store warp's signal goes first: see chain_x3.cu for why no warp can then reach the next save early)
+              if (L.save) mbar_arrive(&save_ready[t]);
               mbar_arrive_cluster_addr((seed ? seed_addr0 : free_addr0) + 8u * t);
-              if (L.save) {
-                const int64_t row_w = st * 512 + t * 256 + (int64_t)rank * 128 + q * 32;
-                if (row_w < p.m) {
-                  for (int cc = 0; cc < 2; ++cc) {
-                    const int c = 2 * h + cc;
-                    tma_store_2d(&maps.save[l], smem_base + (uint32_t)(t * kActBytes + c * kBlkBytes + q * 32 * 128), c * 64,
-                                 (int)row_w);
-                  }
-                }
-                tma_store_commit();
-              }
             }
             if (tr) p.trace[(opcount * 2 + t) * 8 + 5] = clock64();   // arrive + TMA store issue done (lane 0 of warp 4)
-            if (L.save) {
-              has_group |= 1u << t;
-              newer &= ~(1u << t);
-              if (has_group >> (t ^ 1) & 1u) newer |= 1u << (t ^ 1);
-              any_store = true;
-            }
-            if (l == p.in2_sync_op && t == 1) {
-              // every store group older than this op's two has fully completed -> the producer may re-load that save
-              if (lane == 0) {
-                if (L.save) asm volatile("cp.async.bulk.wait_group 2;" ::: "memory");
-                else asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
-                mbar_arrive(in2_ready);
-              }
-            }
+            if (L.save) outstanding |= 1u << t;
             if (MODE == 0 && L.save_bits && row - lane < p.m) {
               uint32_t* bp = L.save_bits + (size_t)((row - lane) >> 5) * 256 + (4 * h) * 32 + lane;
 #pragma unroll
@@ -462,7 +492,6 @@ chain_pair_kernel(const __grid_constant__ PairMaps maps, const __grid_constant__
         if (!seed) ++nfull;
       }
     }
-    if (any_store && lane == 0) tma_store_wait_all();
   }
   tc_fence_before();
   __syncthreads();
@@ -538,7 +567,7 @@ int launch_chain(const ChainArgs& a, cudaStream_t st) {
     o.kind = L.kind; o.gepi = L.gepi; o.bias = L.bias;
     o.mask_bits = L.mask_bits; o.save_bits = L.save_bits;
     o.save = (L.kind == 0 && L.save_hi) ? 1 : 0;
-    if (o.save && (rc = tc::make_map(&maps.save[l], L.save_hi, a.m, 256, 256, 32))) return rc;
+    if (o.save && (rc = tc::make_map(&maps.save[l], L.save_hi, a.m, 256, 256, 128))) return rc;
     if (L.kind == 0) {
       if (mode < 0) mode = L.mode;
       if (L.mode != mode) return rn_set_error(RN_ERR_ARG, "chain: forward and backward hidden ops cannot be mixed");
@@ -569,7 +598,10 @@ int launch_chain(const ChainArgs& a, cudaStream_t st) {
     cudaMemsetAsync(trace_buf, 0, 64 * 2 * 8 * sizeof(long long), st);
     p.trace = trace_buf;
   }
-  rn_prof_begin(RN_PROF_CHAIN_TC, st, a.algo_flops);
+  double exec_flops = 0.0;
+  for (int l = 0; l < a.num_ops; ++l)
+    if (a.op[l].kind != 2) exec_flops += 2.0 * (double)a.m * a.op[l].n * (a.op[l].kb_act + a.op[l].kb_in) * kBK * a.w_planes;
+  rn_prof_begin(RN_PROF_CHAIN_TC, st, a.algo_flops, exec_flops);
   if (mode == 0 && !a.act_f16)
     chain_pair_kernel<0, 0><<<grid, 384, kSmemTotal, st>>>(maps, p);
   else if (mode == 0)

@@ -672,7 +672,10 @@ int launch_chain_x3(const ChainArgs& a, cudaStream_t st) {
     cudaMemsetAsync(trace_buf, 0, 64 * 8 * sizeof(long long), st);
     p.trace = trace_buf;
   }
-  rn_prof_begin(RN_PROF_CHAIN_TC, st, a.algo_flops);
+  double exec_flops = 0.0;   // three MMAs per K step
+  for (int l = 0; l < a.num_ops; ++l)
+    if (a.op[l].kind != 2) exec_flops += 3.0 * 2.0 * (double)a.m * a.op[l].n * (a.op[l].kb_act + a.op[l].kb_in) * kBK;
+  rn_prof_begin(RN_PROF_CHAIN_TC, st, a.algo_flops, exec_flops);
   if (mode == 0)
     chain_x3_kernel<0><<<grid, 384, kSmemTotal, st>>>(maps, p);
   else

@@ -22,7 +22,9 @@ int rn_set_error(int code, const char* msg);
 void rn_count_launch();
 // optional CUDA-event timing of kernel classes (bench.py roofline); no-ops unless rn_prof_enable(1)
 enum { RN_PROF_GEMM_TC = 0, RN_PROF_WGRAD_TC = 1, RN_PROF_GEMM_SIMT = 2, RN_PROF_CHAIN_TC = 3, RN_PROF_NUM = 4 };
-void rn_prof_begin(int cls, cudaStream_t st, double algo_flops);
+// algo_flops: algorithmic (dense, unpadded, 2*MAC) FLOPs of the launch; exec_flops: FLOPs the tensor pipe actually executes
+// for it (padded shapes x the number of MMAs per K step of the arithmetic mode)
+void rn_prof_begin(int cls, cudaStream_t st, double algo_flops, double exec_flops = 0.0);
 void rn_prof_end(int cls, cudaStream_t st);
 
 // ------------------------------------------------------------------------------------------

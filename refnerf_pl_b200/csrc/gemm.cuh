@@ -51,6 +51,8 @@ struct WgradArgs {
   int all_slabs = 0;          // bf16 tcgen05 only: cover every 128-wide slab of dY (n_real <= 256) in one launch
   float* bias_out = nullptr;  // tcgen05 kernels: also accumulate the bias gradient here, bias_out[c] += sum_r dY[r, c] for the
                               // dY columns this launch covers (all of them with all_slabs, else n0 .. n0+127)
+  float* partial = nullptr;   // with all_slabs: deterministic reduction -- every CTA writes its [256 x 256] partial tile (and
+                              // 256 bias partial sums) to partial + cta * (256 * 257) and a second kernel adds them in CTA order
   int x_f16 = 0, dy_f16 = 0;  // with all_slabs: the operands are fp16 instead of bf16 (both or neither: the MMA
                               // rejects mixed a/b formats with an illegal-instruction fault)
   double algo_flops = 0.0;
@@ -94,6 +96,7 @@ struct ChainArgs {
   ChainOpArgs op[12];
   GemmEpilogue gepi[2];
   double algo_flops = 0.0;
+  double exec_flops = 0.0;   // computed by the launchers: 2 * rows * n * k_padded * MMAs per K step, summed over the ops
 };
 int launch_chain(const ChainArgs& a, cudaStream_t st);      // chain_pair.cu: CTA pairs, cta_group::2, two row tiles in flight
 int launch_chain_x3(const ChainArgs& a, cudaStream_t st);   // chain_x3.cu: CTA pairs, split-bf16 operands, one row tile

@@ -15,6 +15,11 @@
 #include "chain_common.cuh"
 
 namespace rn {
+// fp16 mode: number of (wgrad launch, thread) observations of a SATURATED gradient element (|dY| = 65504 after
+// cvt.satfinite) since the last reset.  The dgrad chains scale every chain by one power of two chosen from its seed
+// tile (pointwise.cu); a gradient that grows more than 16x through a chain would be clamped silently.  The wgrad
+// kernels already visit every dY element in shared memory (bias column sums), so the check rides there for free.
+__device__ unsigned long long g_fp16_saturated = 0ull;
 namespace {
 using namespace tc;
 using chain::elect_one_sync;
@@ -413,7 +418,8 @@ wgrad_tc_kernel(const __grid_constant__ WgMaps maps, int64_t m, int64_t rows_per
 template <int NSLAB, int SPLIT>
 __global__ void __launch_bounds__(256, 1)
 wgrad2_tc_kernel(const __grid_constant__ WgMaps maps, int64_t m, int64_t rows_per_cta, int n_real, int kx, int k_real,
-                 int stages, float* __restrict__ out, int out_ld, float* __restrict__ bias_out, int f16) {
+                 int stages, float* __restrict__ out, int out_ld, float* __restrict__ bias_out, int f16,
+                 float* __restrict__ partial) {
   constexpr int kPlanes = SPLIT == 3 ? 2 : 1;
   constexpr int kRowBlk = SPLIT == 3 ? 32 : 64;
   constexpr int kBoxBytes = kRowBlk * 128;
@@ -519,6 +525,7 @@ wgrad2_tc_kernel(const __grid_constant__ WgMaps maps, int64_t m, int64_t rows_pe
         const int f = 2 * t;
         const int box = f >> 6, fi = f & 63;
         float s0 = 0.f, s1 = 0.f;
+        uint32_t sat = 0u;   // fp16: some |dY| reached the largest finite value (0x7bff), i.e. the conversion saturated
         int stage = 0;
         uint32_t phase = 0;
         for (int b = 0; b < nblk; ++b) {
@@ -534,6 +541,8 @@ wgrad2_tc_kernel(const __grid_constant__ WgMaps maps, int64_t m, int64_t rows_pe
                   const float2 f2 = unpack_f16x2(v);
                   s0 += f2.x;
                   s1 += f2.y;
+                  const uint32_t a = v & 0x7fff7fffu;
+                  sat |= (uint32_t)((a & 0xffffu) == 0x7bffu) | (uint32_t)((a >> 16) == 0x7bffu);
                 } else {
                   s0 += __uint_as_float(v << 16);
                   s1 += __uint_as_float(v & 0xffff0000u);
@@ -545,9 +554,16 @@ wgrad2_tc_kernel(const __grid_constant__ WgMaps maps, int64_t m, int64_t rows_pe
           if (lane == 0) mbar_arrive(&empty[stage]);
           if (++stage == stages) { stage = 0; phase ^= 1; }
         }
+        if (f16 && sat) atomicAdd(&g_fp16_saturated, 1ull);
         if (active) {
-          if (f < n_real) atomicAdd(bias_out + f, s0);
-          if (f + 1 < n_real) atomicAdd(bias_out + f + 1, s1);
+          if (partial) {   // deterministic mode: this CTA's bias partial sums, reduced in CTA order afterwards
+            float* pb = partial + (size_t)blockIdx.x * (256 * 257) + 256 * 256;
+            pb[f] = s0;
+            pb[f + 1] = s1;
+          } else {
+            if (f < n_real) atomicAdd(bias_out + f, s0);
+            if (f + 1 < n_real) atomicAdd(bias_out + f + 1, s1);
+          }
         }
       }
       mbar_wait(&tfull[0], 0);
@@ -560,7 +576,13 @@ wgrad2_tc_kernel(const __grid_constant__ WgMaps maps, int64_t m, int64_t rows_pe
           uint32_t r[32];
           tmem_ld32(taddr + (uint32_t)c0, r);
           tmem_ld_wait();
-          if (nrow < n_real) {
+          if (partial) {
+            float* ps = partial + (size_t)blockIdx.x * (256 * 257) + (size_t)nrow * 256 + c0;
+#pragma unroll
+            for (int e = 0; e < 32; e += 4)
+              *reinterpret_cast<float4*>(ps + e) = make_float4(__uint_as_float(r[e]), __uint_as_float(r[e + 1]),
+                                                               __uint_as_float(r[e + 2]), __uint_as_float(r[e + 3]));
+          } else if (nrow < n_real) {
 #pragma unroll
             for (int e = 0; e < 32; ++e) {
               const int j = c0 + e;
@@ -576,7 +598,40 @@ wgrad2_tc_kernel(const __grid_constant__ WgMaps maps, int64_t m, int64_t rows_pe
   if (warp == 2) tmem_dealloc(tmem_base, NSLAB * 256);
 }
 
+// deterministic mode, second pass: out[n, j] += sum over CTAs (in CTA order) of their partial tiles; same for the bias
+__global__ void __launch_bounds__(256)
+wgrad_reduce_kernel(const float* __restrict__ partial, int nctas, int n_real, int n_slab_rows, int k_real, float* __restrict__ out,
+                    int out_ld, float* __restrict__ bias_out) {
+  const int idx = blockIdx.x * 256 + threadIdx.x;
+  const int total = n_real * k_real;
+  if (idx < total) {
+    const int n = idx / k_real, j = idx - n * k_real;
+    float acc = 0.f;
+    for (int b = 0; b < nctas; ++b) acc += partial[(size_t)b * (256 * 257) + (size_t)n * 256 + j];
+    out[(size_t)n * out_ld + j] += acc;
+  } else if (bias_out && idx - total < n_real && idx - total < n_slab_rows) {
+    const int f = idx - total;
+    float acc = 0.f;
+    for (int b = 0; b < nctas; ++b) acc += partial[(size_t)b * (256 * 257) + 256 * 256 + f];
+    bias_out[f] += acc;
+  }
+}
+
 }  // namespace
+
+}  // namespace rn
+
+extern "C" int64_t rn_fp16_saturation_count(int reset) {
+  unsigned long long v = 0ull;
+  if (cudaMemcpyFromSymbol(&v, rn::g_fp16_saturated, sizeof(v)) != cudaSuccess) return -1;   // (synchronises the device)
+  if (reset && v) {
+    const unsigned long long z = 0ull;
+    cudaMemcpyToSymbol(rn::g_fp16_saturated, &z, sizeof(z));
+  }
+  return (int64_t)v;
+}
+
+namespace rn {
 
 int launch_gemm_tc(const GemmArgs& g, cudaStream_t st) {
   if (g.m <= 0) return RN_OK;
@@ -592,7 +647,7 @@ int launch_gemm_tc(const GemmArgs& g, cudaStream_t st) {
   if ((rc = make_map(&maps.b_lo, x3 ? g.b_lo : nullptr, g.n, g.k1 + g.k2, g.b_ld, g.n))) return rc;
   const int64_t tiles = (g.m + kBM - 1) / kBM;
   const unsigned grid = (unsigned)(tiles < num_sms() ? tiles : num_sms());
-  rn_prof_begin(RN_PROF_GEMM_TC, st, g.algo_flops);
+  rn_prof_begin(RN_PROF_GEMM_TC, st, g.algo_flops, (x3 ? 3.0 : 1.0) * 2.0 * (double)g.m * g.n * (g.k1 + g.k2));
   if (x3) {
     static bool once = false;
     if (!once) { if ((rc = set_smem(gemm_tc_kernel<3>, Cfg<3>::kSmemBytes))) return rc; once = true; }
@@ -638,8 +693,8 @@ int launch_wgrad2_tc(const WgradArgs& g, cudaStream_t st) {
     once = true;
   }
   const int f16 = (g.x_f16 && g.dy_f16) ? 1 : 0;
-  rn_prof_begin(RN_PROF_WGRAD_TC, st, g.algo_flops);
-#define RN_WG2(NS, SP) wgrad2_tc_kernel<NS, SP><<<grid, 256, smem, st>>>(maps, g.m, rows_per, g.n_real, g.kx, g.k_real, stages, g.out, g.out_ld, g.bias_out, f16)
+  rn_prof_begin(RN_PROF_WGRAD_TC, st, g.algo_flops, (x3 ? 3.0 : 1.0) * 2.0 * (double)g.m * (128.0 * nslab) * g.kx);
+#define RN_WG2(NS, SP) wgrad2_tc_kernel<NS, SP><<<grid, 256, smem, st>>>(maps, g.m, rows_per, g.n_real, g.kx, g.k_real, stages, g.out, g.out_ld, g.bias_out, f16, g.partial)
   if (x3) {
     if (nslab == 2) RN_WG2(2, 3); else RN_WG2(1, 3);
   } else {
@@ -648,6 +703,11 @@ int launch_wgrad2_tc(const WgradArgs& g, cudaStream_t st) {
 #undef RN_WG2
   rn_prof_end(RN_PROF_WGRAD_TC, st);
   RN_CUDA_CHECK_LAUNCH();
+  if (g.partial) {
+    const int total = g.n_real * g.k_real + (g.bias_out ? g.n_real : 0);
+    wgrad_reduce_kernel<<<(total + 255) / 256, 256, 0, st>>>(g.partial, (int)grid, g.n_real, 128 * nslab, g.k_real, g.out, g.out_ld, g.bias_out);
+    RN_CUDA_CHECK_LAUNCH();
+  }
   return RN_OK;
 }
 
@@ -671,7 +731,7 @@ int launch_wgrad_tc(const WgradArgs& g, cudaStream_t st) {
   if (ctas > blocks64) ctas = (int)blocks64;
   int64_t rows_per = ((blocks64 + ctas - 1) / ctas) * 64;
   const unsigned grid = (unsigned)((g.m + rows_per - 1) / rows_per);
-  rn_prof_begin(RN_PROF_WGRAD_TC, st, g.algo_flops);
+  rn_prof_begin(RN_PROF_WGRAD_TC, st, g.algo_flops, (x3 ? 3.0 : 1.0) * 2.0 * (double)g.m * 128.0 * g.kx);
   if (x3) {
     static bool once = false;
     if (!once) { if ((rc = set_smem(wgrad_tc_kernel<3>, Cfg<3>::kSmemBytes))) return rc; once = true; }

@@ -31,13 +31,14 @@ struct ProfClass {
   std::vector<cudaEvent_t> ev;  // pairs: start, stop
   size_t used = 0;
   double flops = 0.0;
+  double exec_flops = 0.0;
 };
 bool g_prof_on = false;
 ProfClass g_prof[RN_PROF_NUM];
 std::mutex g_prof_mu;
 }  // namespace
 
-void rn_prof_begin(int cls, cudaStream_t st, double algo_flops) {
+void rn_prof_begin(int cls, cudaStream_t st, double algo_flops, double exec_flops) {
   if (!g_prof_on) return;
   std::lock_guard<std::mutex> lk(g_prof_mu);
   ProfClass& p = g_prof[cls];
@@ -50,6 +51,7 @@ void rn_prof_begin(int cls, cudaStream_t st, double algo_flops) {
   }
   cudaEventRecord(p.ev[p.used], st);
   p.flops += algo_flops;
+  p.exec_flops += exec_flops;
 }
 void rn_prof_end(int cls, cudaStream_t st) {
   if (!g_prof_on) return;
@@ -65,7 +67,11 @@ extern "C" int rn_prof_enable(int on) {
   g_prof_on = on != 0;
   return RN_OK;
 }
+extern "C" int rn_prof_summary2(int cls, int64_t* launches, double* total_ms, double* algo_flops, double* exec_flops);
 extern "C" int rn_prof_summary(int cls, int64_t* launches, double* total_ms, double* algo_flops) {
+  return rn_prof_summary2(cls, launches, total_ms, algo_flops, nullptr);
+}
+extern "C" int rn_prof_summary2(int cls, int64_t* launches, double* total_ms, double* algo_flops, double* exec_flops) {
   if (cls < 0 || cls >= RN_PROF_NUM) return rn_set_error(RN_ERR_ARG, "rn_prof_summary: bad class");
   std::lock_guard<std::mutex> lk(g_prof_mu);
   ProfClass& p = g_prof[cls];
@@ -80,8 +86,10 @@ extern "C" int rn_prof_summary(int cls, int64_t* launches, double* total_ms, dou
   if (launches) *launches = (int64_t)(p.used / 2);
   if (total_ms) *total_ms = ms;
   if (algo_flops) *algo_flops = p.flops;
+  if (exec_flops) *exec_flops = p.exec_flops;
   p.used = 0;
   p.flops = 0.0;
+  p.exec_flops = 0.0;
   return RN_OK;
 }
 
@@ -157,6 +165,7 @@ struct Workspace {
   float *stage16, *scal;   // fp16 mode: f32 staging of the 16-wide chain seeds; amax / scale scalars (pointwise.cu)
   float* gW[kNumLayers];
   float* gB[kNumLayers];
+  float* wg_partial;           // deterministic wgrad: per-CTA partial tiles, num_sms x (256 x 257) floats
   int nsp, nvw;
   size_t bytes;
   ActBuf& a(int i) { return sp[(i - 1) % nsp]; }   // spatial activation a_i = relu(y_{i-1}), i = 1..8
@@ -199,8 +208,9 @@ ActBuf rows_from(ActBuf b, int prec, int64_t row0) {
 // hidden activations and raw head outputs live in a Saved region (see use_saved) instead of the workspace.
 // `x3chain`: fused split-bf16 chains -- chain inputs in two planes, hidden activations and every gradient tile in
 // one bf16 plane
-Workspace carve(void* base, int prec, int64_t rc, int mode, bool external = false, bool x3chain = false) {
+Workspace carve(void* base, int prec, int64_t rc, int mode, bool external = false, bool x3chain = false, bool det = false) {
   Workspace w;
+  w.wg_partial = nullptr;
   Carver c{reinterpret_cast<uint8_t*>(base)};
   const int hprec = x3chain ? RN_PREC_BF16 : prec;
   w.nsp = (mode == 0 && !external) ? 2 : 8;
@@ -242,6 +252,7 @@ Workspace carve(void* base, int prec, int64_t rc, int mode, bool external = fals
       w.gW[l] = (float*)c.take((size_t)d.n_pad * d.k_tot() * 4);
       w.gB[l] = (float*)c.take((size_t)d.n_pad * 4);
     }
+    if (det) w.wg_partial = (float*)c.take((size_t)256 * (256 * 257) * 4);   // up to 256 CTAs
   }
   w.bytes = c.off;
   return w;
@@ -547,6 +558,7 @@ int wgrad_layer(const Ctx& c, Workspace& w, int l, int64_t rows, ActBuf dy, int 
     g.dy = dy; g.dy_valid = dy_valid; g.n0 = 0; g.n_real = n_real_total;
     g.all_slabs = 1;
     g.x_f16 = g.dy_f16 = c.f16;
+    g.partial = w.wg_partial;
     g.bias_out = w.gB[l];
     g.x = x1; g.x_valid = d.k1_pad; g.kx = d.k1_pad; g.k_real = d.k1_real;
     g.out = w.gW[l]; g.out_ld = d.k_tot();
@@ -796,7 +808,7 @@ int make_ctx(Ctx& c, const RnMlpConfig* cfg, const void* packed, const float* td
 using namespace rn;
 
 extern "C" const char* rn_last_error(void) { return g_err; }
-extern "C" int rn_abi_version(void) { return 2; }
+extern "C" int rn_abi_version(void) { return 3; }
 extern "C" const char* rn_mlp_param_name(int i) { return (i >= 0 && i < RN_MLP_NUM_PARAMS) ? kParamNames[i] : nullptr; }
 extern "C" int64_t rn_mlp_param_numel(int i) { return (i >= 0 && i < RN_MLP_NUM_PARAMS) ? param_numel(i) : -1; }
 
@@ -808,7 +820,7 @@ extern "C" size_t rn_mlp_packed_bytes(int prec) {
 extern "C" size_t rn_mlp_workspace_bytes(const RnMlpConfig* cfg, int training) {
   if (!cfg || cfg->chunk_rows <= 0) return 0;
   const bool ext = training == 2;
-  size_t b = carve(nullptr, cfg->prec, cfg->chunk_rows, training ? 2 : 0, ext, cfg_x3chain(cfg)).bytes;
+  size_t b = carve(nullptr, cfg->prec, cfg->chunk_rows, training ? 2 : 0, ext, cfg_x3chain(cfg), cfg->deterministic_wgrad != 0).bytes;
   if (training) {
     size_t b1 = carve(nullptr, cfg->prec, cfg->chunk_rows, 1, ext, cfg_x3chain(cfg)).bytes;
     if (b1 > b) b = b1;
@@ -922,7 +934,8 @@ extern "C" int rn_mlp_backward(const RnMlpConfig* cfg, const void* packed, const
   if (!g || !grads) return rn_set_error(RN_ERR_ARG, "rn_mlp_backward: null gradients");
   const int64_t rows_total = n_rays * s;
   const int64_t rc = cfg->chunk_rows;
-  Workspace w = carve(workspace, cfg->prec, rc, 2, saved != nullptr, c.x3);
+  if (cfg->deterministic_wgrad && !c.chain) return rn_set_error(RN_ERR_UNSUPPORTED, "rn_mlp_backward: deterministic_wgrad needs the fused-chain modes (gemm_impl 0, bf16 / fp16 / bf16x3)");
+  Workspace w = carve(workspace, cfg->prec, rc, 2, saved != nullptr, c.x3, cfg->deterministic_wgrad != 0);
   Saved sv;
   if (saved) {
     sv = carve_saved(const_cast<void*>(saved), cfg->prec, c.hprec(), rows_total);

@@ -80,6 +80,7 @@ class MLP(nn.Module):
             precision: str = 'bf16x3',
             chunk_rows: int = 0,
             gemm_impl: int = 0,
+            deterministic_wgrad: bool = False,
     ):
         super().__init__()
         for k, v in list(locals().items()):
@@ -184,7 +185,8 @@ class MLP(nn.Module):
                               flat(g.radii, 1), self.ordered_params(), self.packed_weights(), training,
                               _lib.PREC_BY_NAME[self.precision], self.srgb_mapping, self.srgb_mapping_normalization,
                               float(self.density_bias), float(self.roughness_bias), float(self.rgb_premultiplier),
-                              float(self.rgb_bias), float(self.rgb_padding), int(self.chunk_rows), int(self.gemm_impl),
+                              float(self.rgb_bias), float(self.rgb_padding), int(self.chunk_rows),
+                              int(self.gemm_impl) | (256 if self.deterministic_wgrad else 0),
                               bool(training and torch.is_grad_enabled()))
         density, rgb, normals, npred, gpred, tint, diffuse, spec, rough, _saved = out
         v3 = lambda t: t.reshape(lead + (s, 3))
@@ -263,7 +265,12 @@ class Model(nn.Module):
             raise NotImplementedError('raydist_fn / disable_integration / opaque_background / use_viewdirs=False are '
                                       'not used by the Ref-NeRF configs and are not implemented on the CUDA path')
         self.nerf_mlp = NerfMLP()
-        self.prop_mlp = self.nerf_mlp if self.single_mlp else PropMLP()
+        if not self.single_mlp:
+            # (the reference's PropMLP() takes the MLP defaults -- icosahedron basis, no reflections -- which none of the
+            # Ref-NeRF configs uses: they all bind Model.single_mlp = True)
+            raise NotImplementedError('Model.single_mlp=False (a separate PropMLP) is not part of the Ref-NeRF configurations '
+                                      'this package implements on CUDA; bind Model.single_mlp = True as configs/*_refnerf*.gin do')
+        self.prop_mlp = self.nerf_mlp
 
     @property
     def device(self):
@@ -337,7 +344,9 @@ class Model(nn.Module):
                 rendering['normals_pred'] = shp(ex[:, 3:6], 3)
                 rendering['tint'] = shp(ex[:, 6:9], 3)
                 rendering['roughness'] = shp(ex[:, 9], 1)
-                rendering['distance_mean'] = shp(comp[:, 11])
+                # (rn_composite_bwd propagates no gradient through distance_mean / the percentiles: they are visualisation
+                # outputs that no loss of the reference reads; detached so that autograd shows the absence)
+                rendering['distance_mean'] = shp(comp[:, 11]).detach()
                 rendering['distance_percentile_5'] = shp(pct[:, 0])
                 rendering['distance_median'] = shp(pct[:, 1])
                 rendering['distance_percentile_95'] = shp(pct[:, 2])

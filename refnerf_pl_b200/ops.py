@@ -362,8 +362,9 @@ def ide(dirs: Tensor, kappa_inv: Tensor) -> Tensor:
 # ------------------------------------------------------------------------------------------
 def _mlp_config(prec, srgb_mapping, srgb_norm, density_bias, roughness_bias, rgb_premultiplier, rgb_bias, rgb_padding,
                 chunk_rows, gemm_impl):
+    # bit 8 of `gemm_impl` carries NerfMLP.deterministic_wgrad through the op schema
     return _lib.RnMlpConfig(prec, int(srgb_mapping), int(srgb_norm), density_bias, roughness_bias, rgb_premultiplier,
-                            rgb_bias, rgb_padding, chunk_rows, gemm_impl)
+                            rgb_bias, rgb_padding, chunk_rows, gemm_impl & 0xff, (gemm_impl >> 8) & 1)
 
 
 def default_chunk_rows(n_rows, training=False):
@@ -570,3 +571,11 @@ def _(pix_x, pix_y, cam_idx, pixtocams, camtoworlds, pixtocam_ndc):
     n = pix_x.numel()
     f = lambda *shape: pixtocams.new_empty(shape)
     return [f(n, 3), f(n, 3), f(n, 3), f(n, 1), f(n, 2)]
+
+
+def fp16_saturation_count(reset=True):
+    """fp16 precision mode: number of saturated (clamped to +-65504) gradient-tile observations since the last reset
+    (`rn_fp16_saturation_count`).  0 means the per-chain power-of-two gradient scales had enough head-room; anything else
+    means some weight gradients of the steps since the last reset are biased -- skip those steps or switch the model to
+    `precision='bf16x3'` / `'bf16'`.  Synchronises the device, so poll it every few hundred steps, not every step."""
+    return int(_lib.load().rn_fp16_saturation_count(int(bool(reset))))

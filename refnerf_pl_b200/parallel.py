@@ -67,8 +67,38 @@ class GradAllReducer:
             p.grad = v
         return self
 
+    def _grads_as_one_buffer(self):
+        """`ops.mlp_backward` returns every parameter gradient of a call as a view of ONE flat fp32 buffer, and autograd
+        keeps those views as `.grad` (later calls accumulate into them in place).  If the gradients tile one contiguous
+        range of one storage, return that range as a 1-D tensor: the collective then runs on it directly -- no
+        per-parameter copies into `self.flat`.  None if the layout is anything else."""
+        gs = [p.grad for p in self.params]
+        if any(g is None or g.dtype != torch.float32 or not g.is_contiguous() for g in gs):
+            return None
+        st = gs[0].untyped_storage()
+        if any(g.untyped_storage().data_ptr() != st.data_ptr() for g in gs):
+            return None
+        spans = sorted((g.storage_offset(), g.numel()) for g in gs)
+        off = spans[0][0]
+        for o, n in spans:
+            if o != off:
+                return None
+            off += n
+        return torch.empty(0, dtype=torch.float32, device=gs[0].device).set_(st, spans[0][0], (off - spans[0][0],))
+
     def allreduce(self, async_op=False):
         world = dist.get_world_size(self.group) if dist.is_initialized() else 1
+        direct = self._grads_as_one_buffer()
+        if direct is not None:
+            if world == 1:
+                return None
+            if dist.get_backend(self.group) == 'nccl':     # the mean is taken inside the collective
+                return dist.all_reduce(direct, op=dist.ReduceOp.AVG, group=self.group, async_op=async_op)
+            work = dist.all_reduce(direct, op=dist.ReduceOp.SUM, group=self.group, async_op=async_op)
+            if async_op:
+                return work
+            direct.div_(world)
+            return None
         for p, v in zip(self.params, self.views):
             if p.grad is None:
                 v.zero_()

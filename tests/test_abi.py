@@ -30,7 +30,7 @@ def test_header_symbols_exported(lib):
 def test_metadata_calls(lib):
     from refnerf_pl_b200 import _lib
     from oracle import refnerf_oracle as O
-    assert lib.rn_abi_version() == 2
+    assert lib.rn_abi_version() == 3
     names = _lib.param_names()
     assert len(names) == 46 and names[0] == 'spatial_net.0.weight' and names[-1] == 'rgb.bias'
     shapes = O.param_shapes()

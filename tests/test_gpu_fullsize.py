@@ -20,7 +20,7 @@ from tests._gpu import DEV, build_model, load_params, rays_obj
 pytestmark = pytest.mark.gpu
 
 N = 16384
-PRECISIONS = ['fp16', 'bf16']
+PRECISIONS = ['bf16x3', 'fp16', 'bf16']
 
 
 def _model(precision, **mlp_kwargs):
@@ -114,3 +114,57 @@ def test_backward_linearity_and_ray_additivity(precision):
     ga = _grads(model, cfg, _take(rays, slice(0, half)), gt[:half])
     gb = _grads(model, cfg, _take(rays, slice(half, N)), gt[half:])
     assert rel((ga + gb) / 2.0, g1) <= (5e-3 if precision == 'fp16' else 3e-2)
+
+
+def test_config1_size_against_oracle():
+    """BASELINE config 1 size: one 4 096-ray Blender-shaped batch (near 2, far 6), the CUDA path in the parity arithmetic
+    against the CPU oracle on the SAME rays and weights -- eval forward (compute_extras) and training forward + losses +
+    backward.  Gates are north_star's: per-sample density within 1e-3 relative (99.9th percentile; a ReLU flip moves single
+    samples), composited rgb / acc within 1e-3 absolute, depth within 5e-3, every parameter gradient within 1e-2 (norm-wise).
+    About a minute of host time for the oracle."""
+    import os
+    n = 4096
+    torch.set_num_threads(os.cpu_count() or 1)
+    p = O.init_params(seed=7, bias_std=0.1, weight_scale=1.5)
+    rays = synthetic.blender_rays(n, seed=77)
+    gt_np = synthetic.gt_rgb(n, 77)
+    model, cfg = build_model('bf16x3')
+    load_params(model, p)
+    r = rays_obj(rays)
+    rt = {k: torch.tensor(v) for k, v in rays.items()}
+
+    def rel(a, b):
+        a, b = a.double(), b.double()
+        return (a - b).abs() / (b.abs() + 1e-3 * b.abs().max())
+
+    model.eval()
+    with torch.no_grad():
+        rend, hist = model(r, 1.0, True)
+        orend, ohist = O.model_forward(p, rt, 1.0, True, False)
+    for lvl in range(2):
+        assert float(torch.quantile(rel(hist[lvl]['density'].cpu(), ohist[lvl]['density']).flatten()[::7], 0.999)) <= 1e-3 * (8 if lvl else 1)
+        assert float((rend[lvl]['rgb'].cpu() - orend[lvl]['rgb']).abs().max()) <= 1e-3
+        assert float((rend[lvl]['acc'].cpu() - orend[lvl]['acc']).abs().max()) <= 1e-3
+        assert float((rend[lvl]['distance'].cpu() - orend[lvl]['distance']).abs().max()) <= 5e-3
+    model.train(True)
+    rend, hist = model(r, 1.0, True)
+    loss, _ = train_utils.total_loss(model, r.viewdirs, r.lossmult, torch.tensor(gt_np, device=DEV), rend, hist, cfg)
+    loss.backward()
+    pp = {k: v.clone().requires_grad_(True) for k, v in p.items()}
+    orend, ohist = O.model_forward(pp, rt, 1.0, True, True)
+    oloss = O.total_loss(orend, ohist, rt, torch.tensor(gt_np))
+    oloss.backward()
+    assert abs(float(loss.detach()) - float(oloss.detach())) <= 1e-4 * abs(float(oloss.detach()))
+    nrm = (hist[1]['normals'].cpu() - ohist[1]['normals']).abs()
+    assert float(nrm.mean()) <= 5e-3
+    worst = {}
+    for k, q in model.nerf_mlp.named_parameters():
+        a, b = q.grad.cpu().double(), pp[k].grad.double()
+        worst[k] = float((a - b).norm() / b.norm().clamp(min=1e-30))
+    bad = {k: v for k, v in worst.items() if v > 1e-2}
+    import json
+    os.makedirs('gpurun_out', exist_ok=True)
+    with open('gpurun_out/parity_report.jsonl', 'a') as f:
+        f.write(json.dumps({'case': 'config1_4096rays/bf16x3', 'grad_worst': max(worst.values()), 'grad_median': float(np.median(list(worst.values()))),
+                            'normals_mean_abs': float(nrm.mean())}) + '\n')
+    assert not bad, bad

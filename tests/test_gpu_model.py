@@ -443,3 +443,55 @@ def test_training_mode_forward_under_no_grad_keeps_no_activations():
     with torch.no_grad():
         rend2, _ = model(r, 1.0, False)
     assert float((rend2[1]['rgb'] - before).abs().max()) > 1e-4   # new weights are in use
+
+
+def test_deterministic_wgrad_is_bit_reproducible_and_agrees():
+    """NerfMLP.deterministic_wgrad: weight / bias gradients reduced over the row-split CTAs in a fixed order (per-CTA
+    partial tiles + one reduction pass) instead of with floating-point atomics.  Two identical steps give bit-identical
+    gradients, and they agree with the atomic path to fp32 summation noise."""
+    from refnerf_pl_b200 import synthetic, train_utils
+    p = O.init_params(seed=15, bias_std=0.1, weight_scale=1.2)
+    rays = synthetic.blender_rays(3000, seed=51)       # several CTAs' worth of rows per wgrad launch
+    gt = torch.tensor(synthetic.gt_rgb(3000, 51), device=DEV)
+    grads = {}
+    for key, det in (('det_a', True), ('det_b', True), ('atomic', False)):
+        model, cfg = build_model('bf16x3', mlp_kwargs=dict(deterministic_wgrad=det))
+        load_params(model, p)
+        model.train(True)
+        r = rays_obj(rays)
+        rend, hist = model(r, 1.0, True)
+        loss, _ = train_utils.total_loss(model, r.viewdirs, r.lossmult, gt, rend, hist, cfg)
+        loss.backward()
+        grads[key] = torch.cat([q.grad.reshape(-1) for q in model.nerf_mlp.parameters()]).clone()
+    assert torch.equal(grads['det_a'], grads['det_b'])
+    a, b = grads['det_a'].double(), grads['atomic'].double()
+    assert float((a - b).norm()) <= 1e-5 * float(b.norm())
+
+
+def test_fp16_gradient_saturation_is_reported():
+    """the fp16 mode scales each dgrad chain by ONE power of two chosen from its seed tile; a gradient
+    that grows > 16x through the chain is clamped by the saturating conversion.  The clamp must not be silent:
+    ops.fp16_saturation_count() stays 0 on a healthy step and fires when the later layers amplify the gradient."""
+    from refnerf_pl_b200 import ops, synthetic, train_utils
+    rays = synthetic.blender_rays(600, seed=61)
+    gt = torch.tensor(synthetic.gt_rgb(600, 61), device=DEV)
+
+    def step(p):
+        model, cfg = build_model('fp16')
+        load_params(model, p)
+        model.train(True)
+        r = rays_obj(rays)
+        rend, hist = model(r, 1.0, True)
+        loss, _ = train_utils.total_loss(model, r.viewdirs, r.lossmult, gt, rend, hist, cfg)
+        loss.backward()
+        torch.cuda.synchronize()
+
+    ops.fp16_saturation_count(reset=True)
+    step(O.init_params(seed=16, bias_std=0.1, weight_scale=1.2))
+    assert ops.fp16_saturation_count(reset=True) == 0
+    p = O.init_params(seed=16, bias_std=0.0, weight_scale=1.0)
+    for i in range(1, 8):
+        p[f'viewdir_mlp.{i}.weight'] = p[f'viewdir_mlp.{i}.weight'] * 10.0     # the backward grows ~4x per layer
+    step(p)
+    assert ops.fp16_saturation_count(reset=True) > 0
+    assert ops.fp16_saturation_count(reset=False) == 0

@@ -145,3 +145,17 @@ def test_geometry_losses_and_noisy_rays_match_reference_fixture():
     assert train_utils.consistency_warmup_ratio(cfg, 0) == 0.0
     assert abs(train_utils.consistency_warmup_ratio(cfg, 75000) - 0.5) < 1e-12
     assert train_utils.consistency_warmup_ratio(cfg, 200000) == 1.0
+
+
+def test_contract_follows_reference_formula():
+    """coord.contract / inv_contract (coord.py:20-35; the reference function itself raises TypeError)."""
+    import torch
+    from oracle import refnerf_oracle as O
+    from refnerf_pl_b200 import coord
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(1000, 3, generator=g) * 3
+    z = coord.contract(x)
+    assert torch.equal(z, O.contract(x))
+    inside = (x ** 2).sum(-1) <= 1
+    assert torch.equal(z[inside], x[inside]) and float(z.norm(dim=-1).max()) < 2.0
+    assert float((coord.inv_contract(z) - x).abs().max()) < 1e-3 * float(x.abs().max())

@@ -49,6 +49,20 @@ def _worker(rank, world, port, out_dir):
     red.allreduce()
     if rank == 0:
         np.save(os.path.join(out_dir, 'flat.npy'), red.flat.numpy())
+    # gradients that are views of ONE flat buffer (what ops.mlp_backward hands to autograd): reduced in place, no copies
+    one = torch.cat([v.grad.reshape(-1) for v in params]).clone() * world   # undo nothing: fresh un-averaged stand-in
+    off = 0
+    for v in params:
+        v.grad = one[off:off + v.numel()].view_as(v)
+        off += v.numel()
+    before = one.clone()
+    red2 = parallel.GradAllReducer(params)
+    assert red2._grads_as_one_buffer() is not None and red2._grads_as_one_buffer().data_ptr() == one.data_ptr()
+    red2.allreduce()
+    assert all(v.grad.data_ptr() != w_.data_ptr() for v, w_ in zip(params, red2.views))   # .grad still points into `one`
+    if rank == 0:
+        np.save(os.path.join(out_dir, 'direct.npy'), one.numpy())
+        np.save(os.path.join(out_dir, 'direct_before.npy'), before.numpy())
     g = parallel.gather_rows(torch.full((2, 3), float(rank)))
     assert g.shape == (2 * world, 3) and float(g[-1, 0]) == world - 1
     dist.barrier()
@@ -76,3 +90,6 @@ def test_two_rank_allreduce_matches_single_process(tmp_path):
     ref = torch.cat([v.grad.reshape(-1) for v in pp.values()]).numpy()
     # equal shards + per-rank means => the rank-average equals the full-batch gradient
     assert np.linalg.norm(flat - ref) <= 1e-5 * np.linalg.norm(ref)
+    # direct path: every rank fed (its averaged gradient x world) -> the mean over ranks is world x the averaged gradient
+    direct = np.load(tmp_path / 'direct.npy')
+    assert np.linalg.norm(direct - 2 * flat) <= 1e-5 * np.linalg.norm(2 * flat)

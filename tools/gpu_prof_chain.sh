@@ -17,5 +17,5 @@ torch.cuda.synchronize()
 PY
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:chain_kernel -s 4 -c 2 -f -o gpurun_out/chain_eval_r01 python /tmp/render_only.py > gpurun_out/ncu_chain_eval.log 2>&1
 tail -n 3 gpurun_out/ncu_chain_eval.log
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:wgrad2_tc -s 10 -c 2 -f -o gpurun_out/wgrad2_r01 python bench.py --steps 1 --warmup 1 --precision bf16 --no-render --no-cpu --no-parity > gpurun_out/ncu_wgrad2.log 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:wgrad2_tc -s 10 -c 2 -f -o gpurun_out/wgrad2_r01 python bench.py --steps 1 --warmup 1 --precision bf16 --no-render --no-cpu --no-extra > gpurun_out/ncu_wgrad2.log 2>&1
 tail -n 3 gpurun_out/ncu_wgrad2.log

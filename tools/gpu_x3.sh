@@ -7,5 +7,5 @@ TAILN=4 run x3_debug_small python tools/x3_debug.py 3
 TAILN=6 run x3_model python -m pytest tests/test_gpu_model.py -q -m gpu -x -k "bf16x3 or fused or tiny or saved"
 PREC=bf16x3 RN_CHAIN_TRACE=3 TAILN=2 run trace_x3_train python tools/chain_trace.py train
 TAILN=3 run x3_bench python bench.py --precision bf16x3 --no-cpu --no-render --no-hbm --steps 5 --warmup 3
-TAILN=3 run fp16_bench python bench.py --precision fp16 --no-cpu --no-render --no-hbm --no-parity --steps 5 --warmup 3
+TAILN=3 run fp16_bench python bench.py --precision fp16 --no-cpu --no-render --no-hbm --steps 5 --warmup 3
 (cd tools/micro && nvcc -arch=sm_100a -O3 -o cvt_bw cvt_bw.cu) && TAILN=12 run cvt_bw tools/micro/cvt_bw

@@ -1,5 +1,11 @@
 """2k-step training parity run (north_star: "a 2k-step Blender training run must land within 0.1 dB PSNR").
 
+Arms: `ref_fp32` = the REFERENCE ARITHMETIC: the oracle port of the reference (unfused fp32 torch ops + autograd,
+oracle/refnerf_oracle.py -- pinned against the unmodified reference) running on the same GPU, same optimiser recipe
+(train_utils.py:448-467, math.py:46-78), same ray stream, same initial weights; `bf16x3` / `fp16` / `bf16` = this package.
+Training is chaotic (1e-7 perturbations grow to visible PSNR differences within 2k steps), so the comparison is made per
+ray-stream seed and reported as the mean paired difference with its spread.
+
 There is no dataset in this environment, so the scene is analytic: a Phong-shaded unit sphere with a procedural
 albedo in front of a white background, seen from Blender-shaped cameras (synthetic.blender_rays).  The SAME ray
 stream, ground truth and initial weights train the throughput modes (fp16 / bf16 tensor-core chains) and the parity mode
@@ -41,13 +47,57 @@ def shade(rays):
     return np.where(hit[:, None], col, 1.0).astype(np.float32)
 
 
-def run(precision, steps, n_rays, dev):
+def run_reference(steps, n_rays, dev, stream_seed=0):
+    """The reference arithmetic (oracle port, fp32, autograd) on the GPU: same stream, weights, optimiser, schedule."""
+    from oracle import refnerf_oracle as O
+    model, cfg = build_everything('fp32', dev)          # only for the initial weights and the optimiser recipe
+    params = {k: v.detach().clone().requires_grad_(True) for k, v in model.nerf_mlp.state_dict().items()}
+    del model
+    opt, sched = train_utils.create_optimizer(cfg, list(params.values()))
+    loss_cfg = dict(data_loss_mult=cfg.data_loss_mult, data_coarse_loss_mult=cfg.data_coarse_loss_mult,
+                    orientation_loss_mult=cfg.orientation_loss_mult, orientation_coarse_loss_mult=cfg.orientation_coarse_loss_mult,
+                    predicted_normal_loss_mult=cfg.predicted_normal_loss_mult,
+                    predicted_normal_coarse_loss_mult=cfg.predicted_normal_coarse_loss_mult,
+                    interlevel_loss_mult=cfg.interlevel_loss_mult)
+    assert cfg.data_loss_type == 'mse'
+    t0 = time.time()
+    for step in range(steps):
+        r = synthetic.blender_rays(n_rays, seed=1000 + 100000 * stream_seed + step)
+        gt = torch.from_numpy(shade(r)).to(dev)
+        rays = {k: torch.from_numpy(v).to(dev) for k, v in r.items()}
+        rend, hist = O.model_forward(params, rays, min(1.0, step / steps), False, True)
+        loss = O.total_loss(rend, hist, rays, gt, loss_cfg)
+        opt.zero_grad(set_to_none=True)
+        loss.backward()
+        if cfg.grad_max_norm > 0:
+            torch.nn.utils.clip_grad_norm_(list(params.values()), cfg.grad_max_norm)
+        opt.step()
+        sched.step()
+        if step % 500 == 0:
+            print(f'  [ref_fp32] step {step} loss {float(loss.detach()):.5f}', flush=True)
+    torch.cuda.synchronize()
+    train_s = time.time() - t0
+    mse, cnt = 0.0, 0
+    with torch.no_grad():
+        for k in range(8):
+            r = synthetic.blender_rays(4096, seed=900000 + k)
+            gt = torch.from_numpy(shade(r)).to(dev)
+            rays = {k2: torch.from_numpy(v).to(dev) for k2, v in r.items()}
+            rend, _ = O.model_forward(params, rays, 1.0, False, False)
+            mse += float(((rend[-1]['rgb'] - gt) ** 2).sum())
+            cnt += gt.numel()
+    return -10 * np.log10(mse / cnt), train_s
+
+
+def run(precision, steps, n_rays, dev, stream_seed=0):
+    if precision == 'ref_fp32':
+        return run_reference(steps, n_rays, dev, stream_seed)
     model, cfg = build_everything(precision, dev)
     model.train(True)
     opt, sched = train_utils.create_optimizer(cfg, list(model.nerf_mlp.parameters()))
     t0 = time.time()
     for step in range(steps):
-        r = synthetic.blender_rays(n_rays, seed=1000 + step)
+        r = synthetic.blender_rays(n_rays, seed=1000 + 100000 * stream_seed + step)
         gt = torch.from_numpy(shade(r)).to(dev)
         rays = utils.Rays(**{k: torch.from_numpy(v).to(dev) for k, v in r.items()})
         rend, hist = model(rays, min(1.0, step / steps), False)
@@ -129,16 +179,21 @@ def main():
     n_rays = int(sys.argv[2]) if len(sys.argv) > 2 else 4096
     modes = tuple(sys.argv[3].split(',')) if len(sys.argv) > 3 else ('fp16', 'bf16', 'bf16x3')
     repeats = int(sys.argv[4]) if len(sys.argv) > 4 else 1
+    seeds = int(sys.argv[5]) if len(sys.argv) > 5 else 1       # ray-stream seeds (paired comparison per seed)
     dev = torch.device('cuda', 0)
     # identical initial weights and ray stream every run: repeats differ only through the order of the wgrad atomics,
     # i.e. they measure the run-to-run spread a precision mode has against ITSELF
     runs = []
-    for rep in range(repeats):
-        for prec in modes:
-            torch.manual_seed(0)
-            psnr, secs = run(prec, steps, n_rays, dev)
-            runs.append({'precision': prec, 'repeat': rep, 'psnr_db': psnr, 'train_seconds': secs})
-            print(f'{prec}[{rep}]: held-out PSNR {psnr:.3f} dB after {steps} steps of {n_rays} rays ({secs:.1f} s)', flush=True)
+    for seed in range(seeds):
+        for rep in range(repeats):
+            for prec in modes:
+                if prec == 'ref_fp32' and rep > 0:
+                    continue   # (cuBLAS fp32 + torch autograd on one stream: reruns are identical up to its own atomics)
+                torch.manual_seed(0)
+                psnr, secs = run(prec, steps, n_rays, dev, seed)
+                runs.append({'precision': prec, 'repeat': rep, 'stream_seed': seed, 'psnr_db': psnr, 'train_seconds': secs})
+                print(f'{prec}[seed {seed}, rep {rep}]: held-out PSNR {psnr:.3f} dB after {steps} steps of {n_rays} rays ({secs:.1f} s)',
+                      flush=True)
     res = {'runs': runs, 'steps': steps, 'rays_per_step': n_rays,
            'scene': 'analytic Phong sphere, white background, Blender-shaped cameras (tools/train_parity.py)'}
     for prec in modes:
@@ -147,6 +202,20 @@ def main():
     for prec in modes:
         if prec != 'bf16x3' and 'bf16x3' in res:
             res[f'delta_db_{prec}'] = res[prec]['mean_psnr_db'] - res['bf16x3']['mean_psnr_db']
+    if 'ref_fp32' in modes:   # paired per ray-stream seed against the reference arithmetic
+        for prec in modes:
+            if prec == 'ref_fp32':
+                continue
+            diffs = []
+            for seed in range(seeds):
+                ref = [r['psnr_db'] for r in runs if r['precision'] == 'ref_fp32' and r['stream_seed'] == seed]
+                mine = [r['psnr_db'] for r in runs if r['precision'] == prec and r['stream_seed'] == seed]
+                if ref and mine:
+                    diffs.append(float(np.mean(mine) - np.mean(ref)))
+            if diffs:
+                res[f'vs_reference_arithmetic_{prec}'] = {
+                    'paired_delta_db_per_seed': diffs, 'mean_delta_db': float(np.mean(diffs)),
+                    'stderr_db': float(np.std(diffs, ddof=1) / np.sqrt(len(diffs))) if len(diffs) > 1 else None}
     res['trained_scale_forward_parity_vs_bf16x3'] = trained_scale_parity(dev)
     print(json.dumps(res))
 
