@@ -159,19 +159,30 @@ chain_x3_kernel(const __grid_constant__ X3Maps maps, const __grid_constant__ Pai
     uint32_t tile_iter = 0;
     for (int64_t tile = cluster_id; tile < num_tiles; tile += num_clusters, ++tile_iter) {
       const int row0 = (int)(tile * 256 + (int64_t)rank * 128);
-      if (p.in_kb && tile + num_clusters < num_tiles && elect_one_sync()) {
-        // next tile's chain input -> L2 (its TMA load is issued at the tile boundary and sits on the critical path)
-        const int rown = (int)((tile + num_clusters) * 256 + (int64_t)rank * 128);
-        for (int kb = 0; kb < p.in_kb; ++kb) {
-          tma_prefetch_l2_2d(&maps.in_hi, kb * kBK, rown);
-          tma_prefetch_l2_2d(&maps.in_lo, kb * kBK, rown);
-        }
-      }
-      __syncwarp();
       for (int l = 0; l < p.num_ops; ++l) {
         const PairOp& L = p.op[l];
         if (L.kind == 2) continue;
         const int nhalf = L.n >= 256 ? 2 : 1;
+        // L2 prefetches, issued about one op (6 000+ cycles) ahead of the TMA loads they serve -- early enough to cover the
+        // HBM latency, late enough that the save traffic streaming through L2 has not evicted the lines again:
+        //   * the next op's ring-fed input K blocks (the skip layer re-reads the chain input 5 ops after the first op did);
+        //   * the NEXT tile's chain input, three ops before the tile boundary where its load sits on the critical path
+        if (p.in_kb && elect_one_sync()) {
+          if (l + 1 < p.num_ops && l + 1 > 0 && p.op[l + 1].kind != 2 && p.op[l + 1].kb_in) {
+            for (int kb = 0; kb < p.in_kb; ++kb) {
+              tma_prefetch_l2_2d(&maps.in_hi, kb * kBK, row0);
+              tma_prefetch_l2_2d(&maps.in_lo, kb * kBK, row0);
+            }
+          }
+          if (l == (p.num_ops >= 3 ? p.num_ops - 3 : 0) && tile + num_clusters < num_tiles) {
+            const int rown = (int)((tile + num_clusters) * 256 + (int64_t)rank * 128);
+            for (int kb = 0; kb < p.in_kb; ++kb) {
+              tma_prefetch_l2_2d(&maps.in_hi, kb * kBK, rown);
+              tma_prefetch_l2_2d(&maps.in_lo, kb * kBK, rown);
+            }
+          }
+        }
+        __syncwarp();
         if (l == 0 && direct_in) {
           // the first weight items first, then the input tile (it has to wait for the previous tile), then the rest
           const int early = L.kb_in < 3 ? L.kb_in : 3;

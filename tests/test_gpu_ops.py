@@ -56,7 +56,7 @@ def test_resample_golden(ops, gold):
                             'mismatching_indices': int((idx.numpy() != gold['rs_idx']).sum()), 'indices': int(idx.numel()),
                             'cdf_max_abs_diff_in_ulp_of_1': cw_ulp,
                             'sdist_max_abs_diff': float(np.abs(so.numpy() - gold['rs_sdist']).max())}) + '\n')
-    assert mism <= 5e-4, mism
+    assert mism <= 1e-4, mism   # measured on the B200: 0 of 12 288 (profiles/r02_parity_report.jsonl)
     assert np.abs(so.numpy() - gold['rs_sdist']).max() <= 1e-5   # few-ulp CDF differences / narrow CDF steps
 
 

@@ -47,11 +47,17 @@ def shade(rays):
     return np.where(hit[:, None], col, 1.0).astype(np.float32)
 
 
-def run_reference(steps, n_rays, dev, stream_seed=0):
-    """The reference arithmetic (oracle port, fp32, autograd) on the GPU: same stream, weights, optimiser, schedule."""
+def run_reference(steps, n_rays, dev, stream_seed=0, perturb=0):
+    """The reference arithmetic (oracle port, fp32, autograd) on the GPU: same stream, weights, optimiser, schedule.
+    `perturb` > 0 multiplies every initial weight by (1 + 1e-6 N(0,1)) -- a perturbation of the size of an fp32
+    re-ordering: repeats of this arm then measure the chaotic spread the REFERENCE arithmetic has against itself."""
     from oracle import refnerf_oracle as O
     model, cfg = build_everything('fp32', dev)          # only for the initial weights and the optimiser recipe
-    params = {k: v.detach().clone().requires_grad_(True) for k, v in model.nerf_mlp.state_dict().items()}
+    params = {k: v.detach().clone() for k, v in model.nerf_mlp.state_dict().items()}
+    if perturb:
+        g = torch.Generator(device='cpu').manual_seed(777 + perturb)
+        params = {k: v * (1 + 1e-6 * torch.randn(v.shape, generator=g).to(v.device)) for k, v in params.items()}
+    params = {k: v.requires_grad_(True) for k, v in params.items()}
     del model
     opt, sched = train_utils.create_optimizer(cfg, list(params.values()))
     loss_cfg = dict(data_loss_mult=cfg.data_loss_mult, data_coarse_loss_mult=cfg.data_coarse_loss_mult,
@@ -89,9 +95,9 @@ def run_reference(steps, n_rays, dev, stream_seed=0):
     return -10 * np.log10(mse / cnt), train_s
 
 
-def run(precision, steps, n_rays, dev, stream_seed=0):
+def run(precision, steps, n_rays, dev, stream_seed=0, rep=0):
     if precision == 'ref_fp32':
-        return run_reference(steps, n_rays, dev, stream_seed)
+        return run_reference(steps, n_rays, dev, stream_seed, perturb=rep)
     model, cfg = build_everything(precision, dev)
     model.train(True)
     opt, sched = train_utils.create_optimizer(cfg, list(model.nerf_mlp.parameters()))
@@ -180,6 +186,9 @@ def main():
     modes = tuple(sys.argv[3].split(',')) if len(sys.argv) > 3 else ('fp16', 'bf16', 'bf16x3')
     repeats = int(sys.argv[4]) if len(sys.argv) > 4 else 1
     seeds = int(sys.argv[5]) if len(sys.argv) > 5 else 1       # ray-stream seeds (paired comparison per seed)
+    # optional "mode:first_rep" entries: start a mode at a later repeat (to add perturbed reference runs to an earlier log)
+    first_rep = {}
+    modes = tuple(m.split(':')[0] for m in modes if not first_rep.update({m.split(':')[0]: int(m.split(':')[1])} if ':' in m else {}))
     dev = torch.device('cuda', 0)
     # identical initial weights and ray stream every run: repeats differ only through the order of the wgrad atomics,
     # i.e. they measure the run-to-run spread a precision mode has against ITSELF
@@ -187,10 +196,10 @@ def main():
     for seed in range(seeds):
         for rep in range(repeats):
             for prec in modes:
-                if prec == 'ref_fp32' and rep > 0:
-                    continue   # (cuBLAS fp32 + torch autograd on one stream: reruns are identical up to its own atomics)
+                if rep < first_rep.get(prec, 0):
+                    continue
                 torch.manual_seed(0)
-                psnr, secs = run(prec, steps, n_rays, dev, seed)
+                psnr, secs = run(prec, steps, n_rays, dev, seed, rep)
                 runs.append({'precision': prec, 'repeat': rep, 'stream_seed': seed, 'psnr_db': psnr, 'train_seconds': secs})
                 print(f'{prec}[seed {seed}, rep {rep}]: held-out PSNR {psnr:.3f} dB after {steps} steps of {n_rays} rays ({secs:.1f} s)',
                       flush=True)
