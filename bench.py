@@ -275,14 +275,14 @@ def load_profile_json(name):
     return json.load(open(p)) if os.path.exists(p) else {}
 
 
-def time_hbm_kernels(dev, peaks):
+def time_hbm_kernels(dev, peaks, iters=20):
     """Achieved HBM GB/s of the warp-per-ray kernels (SURVEY 8(d) algorithmic bytes), inputs larger than L2."""
     from refnerf_pl_b200 import ops
     out = {}
     g = torch.Generator(device=dev).manual_seed(0)
     rnd = lambda *s: torch.rand(*s, device=dev, generator=g)
 
-    def timeit(fn, iters=20):
+    def timeit(fn):
         fn()
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -434,6 +434,7 @@ def run_b200(args):
     ms_prof_total = timed(wl.step, args.steps)
     prof = prof_read()
     lib.rn_prof_enable(0)
+    allreduce_path = wl.reducer.last_path if wl.reducer is not None else None
     # ---- end-to-end: pinned host rays -> H2D every step, loss read back every step ----
     wl.e2e_step()
     ms_e2e = timed(wl.e2e_step, args.steps) / args.steps
@@ -580,7 +581,8 @@ def run_b200(args):
                                'both levels (single_mlp), fwd (incl. density-gradient normals) + losses + bwd + Adam',
                    'rays_per_gpu': n, 'levels': 2, 'samples_per_level': 128, 'precision': args.precision,
                    'l2': 'no explicit flush: per-step activation working set (>2 GB) exceeds the 126 MB L2',
-                   'parallelism': f'ray-sharded dp{world}, one NCCL gradient all-reduce per step' if world > 1 else 'single GPU'},
+                   'parallelism': (f'ray-sharded dp{world}, one NCCL gradient all-reduce per step; ' + str(allreduce_path))
+                                  if world > 1 else 'single GPU'},
         'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': wl.h2d_bytes, 'd2h_bytes_per_step': 4,
                 'ms_per_step': ms_e2e},
         'gpu_launches': int(launches),

@@ -53,6 +53,7 @@ class GradAllReducer:
                 seen.add(id(p))
                 self.params.append(p)
         self.group = group
+        self.last_path = None
         n = sum(p.numel() for p in self.params)
         self.flat = torch.zeros(n, dtype=torch.float32, device=self.params[0].device)
         self.views, off = [], 0
@@ -89,6 +90,7 @@ class GradAllReducer:
     def allreduce(self, async_op=False):
         world = dist.get_world_size(self.group) if dist.is_initialized() else 1
         direct = self._grads_as_one_buffer()
+        self.last_path = 'direct (collective on the backward\'s flat buffer)' if direct is not None else 'copy into a flat buffer'
         if direct is not None:
             if world == 1:
                 return None
