@@ -356,10 +356,13 @@ class Workload:
         else:
             rend, hist = model(rays, 1.0, True)
             loss, _ = tu.total_loss(model, rays.viewdirs, rays.lossmult, gt, rend, hist, cfg)
-        self.opt.zero_grad(set_to_none=True)
-        loss.backward()
         if self.reducer is not None:
+            self.reducer.attach()     # .grad = zeroed slices of ONE flat buffer: backward accumulates in place, and the
+            loss.backward()           # collective runs on that buffer directly (no per-parameter copies, no div_)
             self.reducer.allreduce()
+        else:
+            self.opt.zero_grad(set_to_none=True)
+            loss.backward()
         if cfg.grad_max_norm > 0:
             torch.nn.utils.clip_grad_norm_(model.nerf_mlp.parameters(), cfg.grad_max_norm)
         self.opt.step()
@@ -478,8 +481,11 @@ def run_b200(args):
 
             with torch.no_grad():
                 render_once()
+                smp = ClockSampler(local_rank).start() if rank == 0 else None
                 fms = timed(render_once, 2) / 2
+                clk = smp.stop() if smp else None
             render['by_chunk'][str(chunk)] = {
+                'sm_mhz': clk['sm_mhz'] if clk else None,
                 'ms_per_frame': fms, 'rays_per_s': 640000 / (fms * 1e-3),
                 'mlp_tflops': FLOP_PER_SAMPLE_EVAL * SAMPLES_PER_RAY * 640000 / (fms * 1e-3) / 1e12,
                 'driver': 'CUDA graph of one chunk replayed per chunk, outputs written into the frame buffers'
@@ -490,17 +496,20 @@ def run_b200(args):
         wl.model.train(True)
     wl.free()
 
-    def short_run(gin, precision, rays_np, gt_np, geometry=False, steps=5, warm=3):
+    def short_run(gin, precision, rays_np, gt_np, geometry=False, steps=8, warm=3):
         w = Workload(gin, precision, rays_np, gt_np, dev, world, geometry)
         for _ in range(warm):
             w.step()
+        smp = ClockSampler(local_rank).start() if rank == 0 else None
         ms = timed(w.step, steps) / steps
+        clk = smp.stop() if smp else None
         w.e2e_step()
         ms_e = timed(w.e2e_step, steps) / steps
         nn = w.n
         w.free()
         return {'ms_per_step': ms, 'value': world * nn / (ms * 1e-3), 'unit': UNIT, 'rays_per_gpu': nn, 'precision': precision,
-                'e2e_value': world * nn / (ms_e * 1e-3), 'steps': steps}
+                'e2e_value': world * nn / (ms_e * 1e-3), 'steps': steps,
+                'sm_mhz': clk['sm_mhz'] if clk else None}   # (the part is power-capped: later legs of a long run see lower clocks)
 
     extra = {}
     if not args.no_extra:
