@@ -511,6 +511,22 @@ def run_b200(args):
                 'e2e_value': world * nn / (ms_e * 1e-3), 'steps': steps,
                 'sm_mhz': clk['sm_mhz'] if clk else None}   # (the part is power-capped: later legs of a long run see lower clocks)
 
+    def render_ms(precision, chunk=4096):
+        """ms per 800x800 eval frame (compute_extras) of this rank's ray slice in another arithmetic mode"""
+        from refnerf_pl_b200 import models
+        m, c = build_everything(precision, dev)
+        m.eval()
+        frame = synthetic.blender_rays(None, seed=7)
+        lo, hi = parallel.shard_range(640000, rank, world)
+        fr = utils.Rays(**{k: torch.from_numpy(v[lo:hi]).to(dev).reshape(hi - lo, 1, -1) for k, v in frame.items()})
+        c.render_chunk_size = chunk
+        with torch.no_grad():
+            models.render_image(lambda r: m(r, 1.0, True), fr, c)
+            ms = timed(lambda: models.render_image(lambda r: m(r, 1.0, True), fr, c), 2) / 2
+        del m, fr
+        torch.cuda.empty_cache()
+        return ms
+
     extra = {}
     if not args.no_extra:
         # ---- the fp16 throughput mode (a stated-error mode, see DESIGN.md section 2), same step ----
@@ -519,6 +535,8 @@ def run_b200(args):
                                                            synthetic.gt_rgb(n, seed=100 + rank)),
                                                  note='fp16 operands (11-bit): misses the 1e-2 gradient and the trained-scale per-sample '
                                                       'tolerances of north_star; reported beside the headline, never as it')
+            if not args.no_render:
+                extra['throughput_mode_fp16']['render_800x800_ms_per_frame_chunk_4096'] = render_ms('fp16')
         # ---- configs 4 / 5: LLFF-shaped NDC rays (1008x756, near 0, far 1), ray-sharded, one all-reduce per step ----
         llff = synthetic.llff_rays(n, seed=200 + rank)
         extra['llff_refnerf'] = dict(short_run('llff_refnerf.gin', args.precision, llff, synthetic.gt_rgb(n, seed=200 + rank)),

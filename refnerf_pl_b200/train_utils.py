@@ -283,6 +283,25 @@ def training_losses(model, rays, batch_rgb, config, train_frac=1.0, global_step=
     return loss, losses, stats, renderings, ray_history
 
 
+def collect_param_stats(model):
+    """The per-parameter statistics of `RefNeRFSystem.on_after_backward` (nerf_system.py:212-217: squared weight norm,
+    gradient norm, gradient max-abs for every parameter) without its 2 x 92 `.cpu()` round trips per step: three
+    multi-tensor reductions on the device and no synchronisation at all -- the dict holds 0-dim DEVICE tensors (slices of
+    three small vectors), which is what `on_train_batch_end` stacks and logs every `print_every` steps
+    (nerf_system.py:220-271); call `.cpu()` on the stacked result there, once per logging interval.
+    Same keys as the reference ('.' -> '/'), parameters without a gradient are reported as 0."""
+    named = [(k, p) for k, p in model.named_parameters()]
+    params = [p.detach() for _, p in named]
+    grads = [p.grad.detach() if p.grad is not None else torch.zeros_like(p) for _, p in named]
+    with torch.no_grad():
+        w_l2 = torch.stack(torch._foreach_norm(params)) ** 2
+        g_norm = torch.stack(torch._foreach_norm(grads))
+        g_max = torch.stack(torch._foreach_norm(grads, float('inf')))
+    keys = [k.replace('.', '/') for k, _ in named]
+    return {'weights_l2s': dict(zip(keys, w_l2.unbind())), 'grad_norms': dict(zip(keys, g_norm.unbind())),
+            'grad_maxes': dict(zip(keys, g_max.unbind()))}
+
+
 def learning_rate_decay(step, lr_init, lr_final, max_steps, lr_delay_steps=0, lr_delay_mult=1):
     """math.py:46-78."""
     if lr_delay_steps > 0:

@@ -159,3 +159,31 @@ def test_contract_follows_reference_formula():
     inside = (x ** 2).sum(-1) <= 1
     assert torch.equal(z[inside], x[inside]) and float(z.norm(dim=-1).max()) < 2.0
     assert float((coord.inv_contract(z) - x).abs().max()) < 1e-3 * float(x.abs().max())
+
+
+def test_collect_param_stats_matches_reference_definition():
+    """train_utils.collect_param_stats == the per-parameter loop of nerf_system.py:212-217 (weights_l2s, grad_norms,
+    grad_maxes), computed as three multi-tensor reductions without host round trips."""
+    import torch
+    from refnerf_pl_b200 import train_utils
+
+    class Tiny(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.a = torch.nn.Linear(5, 7)
+            self.b = torch.nn.Linear(7, 3)
+
+    torch.manual_seed(0)
+    m = Tiny()
+    m.b(m.a(torch.randn(11, 5))).square().sum().backward()
+    m.b.bias.grad = None                       # a parameter without gradient
+    st = train_utils.collect_param_stats(m)
+    params = dict(m.named_parameters())
+    for k, p in params.items():
+        kk = k.replace('.', '/')
+        assert torch.allclose(st['weights_l2s'][kk], p.detach().norm() ** 2)
+        if p.grad is None:
+            assert float(st['grad_norms'][kk]) == 0.0 and float(st['grad_maxes'][kk]) == 0.0
+        else:
+            assert torch.allclose(st['grad_norms'][kk], p.grad.norm())
+            assert torch.allclose(st['grad_maxes'][kk], p.grad.abs().max())
