@@ -481,15 +481,11 @@ def run_b200(args):
 
             with torch.no_grad():
                 render_once()
-                smp = ClockSampler(local_rank).start() if rank == 0 else None
                 fms = timed(render_once, 2) / 2
-                clk = smp.stop() if smp else None
             render['by_chunk'][str(chunk)] = {
-                'sm_mhz': clk['sm_mhz'] if clk else None,
                 'ms_per_frame': fms, 'rays_per_s': 640000 / (fms * 1e-3),
                 'mlp_tflops': FLOP_PER_SAMPLE_EVAL * SAMPLES_PER_RAY * 640000 / (fms * 1e-3) / 1e12,
-                'driver': 'CUDA graph of one chunk replayed per chunk, outputs written into the frame buffers'
-                          if (hi - lo) // chunk >= 2 else 'eager (fewer than two full chunks)'}
+                'driver': 'chunk loop without host synchronisation, outputs written straight into the frame buffers'}
         best = min(render['by_chunk'].values(), key=lambda d: d['ms_per_frame'])
         render.update(ms_per_frame=best['ms_per_frame'], rays_per_s=best['rays_per_s'], mlp_tflops=best['mlp_tflops'],
                       ms_per_frame_reference_chunk_4096=render['by_chunk']['4096']['ms_per_frame'])

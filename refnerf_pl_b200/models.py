@@ -388,17 +388,18 @@ def _write_chunk(buffers, chunk_renderings, idx0, n, num_rays):
             buffers.setdefault(k, []).append([r[k].detach().clone() for r in chunk_renderings])
 
 
-def render_image(render_fn, rays, config, verbose=True, device=None, use_graph=None):
+def render_image(render_fn, rays, config, verbose=True, device=None, use_graph=False):
     """models.py:763-825: chunked full-image render in eval mode -> dict of [H, W, ...] tensors (+ ray_* bundles).
 
-    Same chunking contract as the reference (`config.render_chunk_size` rays per `render_fn` call), but the per-chunk
-    Python / launch overhead of its loop (157 iterations x ~60 launches for an 800x800 frame at the reference's chunk of
-    4096, models.py:788-803) is taken off the critical path:
+    Same chunking contract as the reference (`config.render_chunk_size` rays per `render_fn` call):
       * every chunk's outputs are written straight into pre-sized [H*W, ...] frame buffers (no list of chunk dicts, no
-        `merge_chunks` concatenation, utils.py:192-204);
-      * when the frame has at least two full chunks and runs on CUDA without autograd, ONE chunk's forward is captured
-        into a CUDA graph over static ray buffers and replayed for every full chunk (`use_graph=False` disables it;
-        a ragged last chunk runs eagerly).  The graph replays exactly the kernels of the eager call.
+        `merge_chunks` concatenation, utils.py:192-204), and nothing in the loop synchronises, so the host runs ahead of
+        the GPU: measured on a B200, an 800x800 frame at the reference's chunk of 4096 (157 iterations) takes 903 ms
+        against 895 ms at 65536 in the parity arithmetic and 361 vs 347 ms in fp16 -- the loop is GPU-bound;
+      * `use_graph=True` (opt-in) captures ONE chunk's forward into a CUDA graph over static ray buffers and replays it
+        for every full chunk (a ragged last chunk runs eagerly).  It replays exactly the kernels of the eager call, but
+        capturing per frame costs 0.1-0.3 s, more than the launch overhead it removes at any chunk size measured
+        (tools/render_test.py), so it only pays for chunks far smaller than the reference's.
     """
     height, width = rays.origins.shape[:2]
     num_rays = height * width
@@ -406,8 +407,8 @@ def render_image(render_fn, rays, config, verbose=True, device=None, use_graph=N
     chunk = int(config.render_chunk_size)
     on_cuda = isinstance(rays.origins, torch.Tensor) and rays.origins.is_cuda
     n_full = num_rays // chunk
-    if use_graph is None:
-        use_graph = on_cuda and n_full >= 2 and not torch.is_grad_enabled()
+    if use_graph and not (on_cuda and n_full >= 2 and not torch.is_grad_enabled()):
+        use_graph = False   # needs CUDA rays, at least two full chunks and no autograd
     buffers = {}
     start_eager = 0
     if use_graph:

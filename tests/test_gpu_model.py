@@ -398,7 +398,7 @@ def test_render_image_graph_and_eager_match_oracle():
     fn = lambda r: model(r, 1.0, True)
     outs = {}
     with torch.no_grad():
-        for name, chunk, graph in (('graph', 96, True), ('ragged', 100, True), ('eager', 96, False), ('one', 4096, None)):
+        for name, chunk, graph in (('graph', 96, True), ('ragged', 100, True), ('eager', 96, False), ('one', 4096, False)):
             cfg.render_chunk_size = chunk
             outs[name] = models.render_image(fn, frame, cfg, use_graph=graph)
     ref = outs['one']
