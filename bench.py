@@ -398,8 +398,10 @@ def run_b200(args):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
+        h0 = time.perf_counter()
         for _ in range(steps):
             fn()
+        timed.host_ms = (time.perf_counter() - h0) * 1e3 / max(1, steps)   # host time to ENQUEUE one step (no sync inside fn)
         e1.record()
         barrier()
         ms = e0.elapsed_time(e1)
@@ -430,6 +432,7 @@ def run_b200(args):
     launches = lib.rn_launch_count() - l0
     clocks = sampler.stop() if sampler else None
     ms_step = ms_total / args.steps
+    host_enqueue_ms = timed.host_ms
     value = world * n / (ms_step * 1e-3)
     # ---- the same K steps once more with per-kernel-class CUDA events around every GEMM-class launch (roofline) ----
     lib.rn_prof_enable(1)
@@ -442,6 +445,11 @@ def run_b200(args):
     wl.e2e_step()
     ms_e2e = timed(wl.e2e_step, args.steps) / args.steps
     e2e_value = world * n / (ms_e2e * 1e-3)
+    e2e_step_ms = []          # diagnostic: host wall clock of individual e2e steps (each ends with the loss read-back)
+    for _ in range(min(args.steps, 8)):
+        h0 = time.perf_counter()
+        wl.e2e_step()
+        e2e_step_ms.append(round((time.perf_counter() - h0) * 1e3, 2))
 
     # ---- training strong scaling: the 16384-ray batch split over the ranks (beside the weak-scaling value) ----
     strong = None
@@ -607,7 +615,8 @@ def run_b200(args):
                    'parallelism': (f'ray-sharded dp{world}, one NCCL gradient all-reduce per step; ' + str(allreduce_path))
                                   if world > 1 else 'single GPU'},
         'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': wl.h2d_bytes, 'd2h_bytes_per_step': 4,
-                'ms_per_step': ms_e2e},
+                'ms_per_step': ms_e2e, 'host_wall_ms_of_single_steps': e2e_step_ms},
+        'host_enqueue_ms_per_step': host_enqueue_ms,
         'gpu_launches': int(launches),
         'clocks': clocks,
         'roofline': roofline,

@@ -38,22 +38,11 @@ __device__ __forceinline__ uint32_t map_to_cta(uint32_t local_addr, uint32_t cta
 __device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
-__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
-  const uint32_t addr = smem_u32(bar);
-#pragma unroll 1
-  for (int spin = 0; spin < kSpinLimit; ++spin) {
-    uint32_t done;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done)
-        : "r"(addr), "r"(parity)
-        : "memory");
-    if (done) return;
-  }
-  __trap();
-}
+// Wait on a barrier of THIS CTA that threads / TMA / tcgen05.commit of either CTA of the pair arrive on.  Default semantics
+// (acquire at CTA scope), as CUTLASS' ClusterBarrier::wait: what the waiter consumes is shared memory / TMEM read through the
+// async proxy, ordered by the writers' fence.proxy.async / tcgen05.fence before their arrive.  (An `.acquire.cluster` wait
+// compiles to SYNCS.PHASECHK + CCTL.IVALL -- an L1 invalidate on the MMA warp's critical path, five times per op.)
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) { mbar_wait(bar, parity); }
 __device__ __forceinline__ void tmem_alloc2(uint32_t* dst_smem, uint32_t cols) {
   asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(cols));
   asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
@@ -215,6 +204,7 @@ struct PairParams {
   int in2_sync_op;   // -1, or: the second input is a save of this launch; the op before its reader orders store -> load
   int a_f16, b_f16;  // operand formats of the MMAs (0 bf16, 1 fp16); the activation tile / outputs use a's
   int w_planes;      // chain_pair.cu: 2 = every weight K block arrives as a hi and a lo ring item (2 MMAs per K step)
+  int split_order;   // chain_x3.cu: issue order of the (column half, K block) pairs of a 256-wide op, see res_order()
   float seed_scale;  // seed ops: vec * seed_scale
   int64_t m;
   long long* trace;   // debug timeline (RN_CHAIN_TRACE=<launches>): written by CTA 0 only

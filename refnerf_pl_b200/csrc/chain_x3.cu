@@ -12,8 +12,8 @@
 //     tensor pipe the epilogue warps drain the first half (bias + ReLU / ReLU bit mask, hi/lo split) and write it back
 //     as K blocks 0 and 1 of the next A operand; each finished 64-column K block is handed to the MMA warp through its
 //     own mbarrier (act_ready[c]).  Op l+1 therefore starts on K blocks 0, 1 the moment op l's last MMA is issued and
-//     reaches K blocks 2, 3 (1 536 cycles later) after the epilogue of the second half has written them: in steady
-//     state the tensor pipe never waits for an epilogue.
+//     reaches K blocks 2, 3 (1 536 cycles later) after the epilogue of the second half has written them.
+//     (RN_X3_ORDER=1 selects the alternative issue order of res_order(): K blocks 0, 1 of both halves first.)
 //   * the chain input of the first op is loaded by TMA straight into the (then dead) activation tile, K block by K
 //     block, as soon as the previous tile's last MMA has retired, after an L2 prefetch issued one tile ahead; the skip
 //     layer's input K blocks stream through the ring and feed both column halves while they are resident.
@@ -39,6 +39,7 @@ using namespace tc;
 using namespace chain;
 
 constexpr int kStages = 6;
+constexpr int kTraceSlots = 32;   // RN_CHAIN_TRACE: 64-bit time stamps per (op, tile) of CTA 0
 constexpr int kItemPlane = 8192;               // [64 x 64] bf16: one plane of a weight item
 constexpr int kStageBytes = 2 * kItemPlane;    // hi | lo  (an input item is one [128 x 64] plane = the whole stage)
 constexpr int kPlaneBytes = 16384;             // [128 x 64] bf16, 128B swizzle: one K block of one activation plane
@@ -48,6 +49,21 @@ constexpr int kSmemBars = kSmemRing + kStages * kStageBytes;
 constexpr int kSmemBias = kSmemBars + 512;     // [op parity][column half h][4 K blocks x 32 floats]
 constexpr int kSmemTotal = kSmemBias + 2048;
 static_assert(kSmemTotal <= 232448, "shared memory budget");
+
+// Issue order of the (column half, resident K block) pairs of an op.  split = 0: half 0 (K blocks 0..3), then half 1.
+// split = 1: a 256-wide op over a full activation tile runs K blocks 0, 1 of BOTH column halves before K blocks 2, 3 --
+// the previous op's second-half epilogue (which writes blocks 2 and 3 once that op's last MMA has retired) then has
+// 3 072 / 3 840 cycles of tensor work to hide behind instead of 1 536 / 2 304, at the price of the first half completing
+// only 1 536 cycles before the op does.  Per accumulator element the K order is the same (bit-identical results).
+__device__ __forceinline__ void res_order(int split, int i, int kb_res, int nhalf, int& half, int& kb) {
+  if (split && nhalf == 2 && kb_res == 4) {
+    half = (i >> 1) & 1;
+    kb = (i & 1) | ((i >> 2) << 1);
+  } else {   // (no integer division on the MMA warp's critical path)
+    half = i >= kb_res ? 1 : 0;
+    kb = half ? i - kb_res : i;
+  }
+}
 
 struct X3Maps {
   CUtensorMap in_hi, in_lo;       // chain input [m, in_cols], box [128 x 64]
@@ -185,8 +201,13 @@ chain_x3_kernel(const __grid_constant__ X3Maps maps, const __grid_constant__ Pai
         __syncwarp();
         if (l == 0 && direct_in) {
           // the first weight items first, then the input tile (it has to wait for the previous tile), then the rest
-          const int early = L.kb_in < 3 ? L.kb_in : 3;
-          for (int kb = 0; kb < early; ++kb) load_w(l, L, kb, 0);
+          const int nres = nhalf * L.kb_in;
+          const int early = nres < 3 ? nres : 3;
+          int oh, ok;
+          for (int i = 0; i < early; ++i) {
+            res_order(p.split_order, i, L.kb_in, nhalf, oh, ok);
+            load_w(l, L, ok, oh);
+          }
           if (tile_iter) {
             // every MMA of the previous tile has retired (release of its last ring item) and its saves have been read
             mbar_wait(&ring_empty[(pos - early - 1) % kStages], ((pos - early - 1) / kStages) & 1u);
@@ -200,9 +221,10 @@ chain_x3_kernel(const __grid_constant__ X3Maps maps, const __grid_constant__ Pai
             }
           }
           __syncwarp();
-          for (int kb = early; kb < L.kb_in; ++kb) load_w(l, L, kb, 0);
-          for (int half = 1; half < nhalf; ++half)
-            for (int kb = 0; kb < L.kb_in; ++kb) load_w(l, L, kb, half);
+          for (int i = early; i < nres; ++i) {
+            res_order(p.split_order, i, L.kb_in, nhalf, oh, ok);
+            load_w(l, L, ok, oh);
+          }
           continue;
         }
         // ring-fed input K blocks (skip layers) feed both column halves while they are resident
@@ -211,8 +233,11 @@ chain_x3_kernel(const __grid_constant__ X3Maps maps, const __grid_constant__ Pai
           load_in(&maps.in_lo, kb, row0);
           for (int half = 0; half < nhalf; ++half) load_w(l, L, L.kb_act + kb, half);
         }
-        for (int half = 0; half < nhalf; ++half)
-          for (int kb = 0; kb < L.kb_act; ++kb) load_w(l, L, kb, half);
+        for (int i = 0; i < nhalf * L.kb_act; ++i) {
+          int oh, ok;
+          res_order(p.split_order, i, L.kb_act, nhalf, oh, ok);
+          load_w(l, L, ok, oh);
+        }
       }
     }
   } else if (warp == 1 && rank == 0) {
@@ -254,11 +279,12 @@ chain_x3_kernel(const __grid_constant__ X3Maps maps, const __grid_constant__ Pai
         const int nhalf = L.n >= 256 ? 2 : 1;
         const uint32_t idesc = make_idesc2(nhalf == 2 ? 128 : L.n);
         const uint32_t buf = gemm_idx & 1u, use = gemm_idx >> 1;
+        const bool tr = p.trace && blockIdx.x == 0 && opcount < 64 && lane == 0;
+        if (tr) p.trace[opcount * kTraceSlots + 8] = clock64();
         mbar_wait_cluster(&acc_free[buf], (use & 1u) ^ 1u);   // epilogue of the op two before has drained this accumulator
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + buf * 256u;
-        const bool tr = p.trace && blockIdx.x == 0 && opcount < 64 && lane == 0;
-        if (tr) p.trace[opcount * 8 + 0] = clock64();
+        if (tr) p.trace[opcount * kTraceSlots + 0] = clock64();
         const bool direct = l == 0 && direct_in;
         const int kb_res = direct ? L.kb_in : L.kb_act;   // K blocks read from the activation tile
         const int blk0 = direct ? in_blk0 : 0;
@@ -280,15 +306,19 @@ chain_x3_kernel(const __grid_constant__ X3Maps maps, const __grid_constant__ Pai
             pos += 2 + nhalf;
           }
         }
-        for (int half = 0; half < nhalf; ++half) {
-          for (int kb = 0; kb < kb_res; ++kb) {
+        for (int i = 0; i < nhalf * kb_res; ++i) {
+          int half, kb;
+          res_order(p.split_order, i, kb_res, nhalf, half, kb);
+          {
             if (half == 0) {
               if (direct) mbar_wait_cluster(&in_full[kb], tile_iter & 1u);
               else if (need_acq) mbar_wait_cluster(&act_ready[kb], aver & 1u);
             }
             wait_full(pos);
             tc_fence_after();
-            if (tr && kb == 0 && half == 0) p.trace[opcount * 8 + 1] = clock64();
+            if (tr && kb == 0 && half == 0) p.trace[opcount * kTraceSlots + 1] = clock64();
+            if (tr && kb == kb_res - 1 && half == 0) p.trace[opcount * kTraceSlots + 7] = clock64();
+            if (tr && i < 8) p.trace[opcount * kTraceSlots + 9 + i] = clock64();   // item i: every wait passed
             const uint32_t sb = stage_addr(pos);
             // (one-half ops complete both half barriers of their accumulator so that the two phase counts stay in step)
             const bool last_kb = kb == kb_res - 1;
@@ -308,7 +338,7 @@ chain_x3_kernel(const __grid_constant__ X3Maps maps, const __grid_constant__ Pai
             ++pos;
           }
         }
-        if (tr) p.trace[opcount * 8 + 2] = clock64();
+        if (tr) p.trace[opcount * kTraceSlots + 2] = clock64();
         if (!direct && L.kb_act && need_acq) {
           ++aver;
           need_acq = false;
@@ -452,7 +482,7 @@ chain_x3_kernel(const __grid_constant__ X3Maps maps, const __grid_constant__ Pai
         const uint32_t buf = gemm_idx & 1u, use = gemm_idx >> 1;
         ++gemm_idx;
         const bool tr = p.trace && blockIdx.x == 0 && warp == 4 && lane == 0 && opcount < 64;
-        if (tr) p.trace[opcount * 8 + 3] = clock64();
+        if (tr) p.trace[opcount * kTraceSlots + 3] = clock64();
         const uint32_t taddr = tmem_base + buf * 256u + ((uint32_t)(q * 32) << 16);
         if (L.kind == 0) {
           uint32_t bits_out[4];
@@ -460,7 +490,7 @@ chain_x3_kernel(const __grid_constant__ X3Maps maps, const __grid_constant__ Pai
           for (int half = 0; half < 2; ++half) {
             mbar_wait(&acc_full[buf * 2 + half], use & 1u);
             tc_fence_after();
-            if (half == 0 && tr) p.trace[opcount * 8 + 4] = clock64();
+            if (half == 0 && tr) p.trace[opcount * kTraceSlots + 4] = clock64();
             wait_drained(half);
             uint32_t ra[32], rb[32];
             tmem_ld32(taddr + (uint32_t)(128 * half + 32 * h), ra);
@@ -500,7 +530,8 @@ chain_x3_kernel(const __grid_constant__ X3Maps maps, const __grid_constant__ Pai
                 if (cc == 1 && L.save) mbar_arrive(&written[half]);
                 mbar_arrive_cluster_addr(ready_addr0 + 8u * c);
               }
-              if (tr && c == 0) p.trace[opcount * 8 + 5] = clock64();
+              if (tr && c == 0) p.trace[opcount * kTraceSlots + 5] = clock64();
+              if (p.trace && blockIdx.x == 0 && lane == 0 && opcount < 64 && c == 3) p.trace[opcount * kTraceSlots + 18 + (warp - 4)] = clock64();
             }
           }
           ++nhid;
@@ -521,7 +552,7 @@ chain_x3_kernel(const __grid_constant__ X3Maps maps, const __grid_constant__ Pai
           ge.out.hi = nullptr;
           mbar_wait(&acc_full[buf * 2], use & 1u);
           tc_fence_after();
-          if (tr) p.trace[opcount * 8 + 4] = clock64();
+          if (tr) p.trace[opcount * kTraceSlots + 4] = clock64();
           // dgrad chains: the next row tile's seed only needs the activation tile, which this op's MMAs have released
           if (MODE == 1 && l == p.num_ops - 1 && p.op[0].kind == 2 && tile + num_clusters < num_tiles) {
             do_seed(p.op[0], tile + num_clusters, bias_half + ((opcount + 1) & 1u) * 1024u);
@@ -571,7 +602,7 @@ chain_x3_kernel(const __grid_constant__ X3Maps maps, const __grid_constant__ Pai
           }
           if (staged) save_outstanding[0] = true;
         }
-        if (tr) p.trace[opcount * 8 + 6] = clock64();
+        if (tr) p.trace[opcount * kTraceSlots + 6] = clock64();
       }
     }
   }
@@ -600,6 +631,10 @@ int launch_chain_x3(const ChainArgs& a, cudaStream_t st) {
   if ((rc = tc::make_map(&maps.in_hi, a.in.hi, a.m, a.in_valid, a.in.ld, kBM))) return rc;
   if ((rc = tc::make_map(&maps.in_lo, a.in.lo, a.m, a.in_valid, a.in.ld, kBM))) return rc;
   p.in2_sync_op = -1;
+  // (measured on the B200: both orders run the 16 384-ray step within 0.5 % of each other -- the chains are paced by the
+  // weight ring's L2 latency and the power cap, not by the epilogue hand-over -- so the plain order stays the default)
+  static const int split_order = getenv("RN_X3_ORDER") ? atoi(getenv("RN_X3_ORDER")) : 0;
+  p.split_order = split_order;
   p.seed_scale = a.seed_scale;
   p.num_ops = a.num_ops;
   p.in_kb = a.in.hi ? a.in_cols / kBK : 0;
@@ -679,8 +714,8 @@ int launch_chain_x3(const ChainArgs& a, cudaStream_t st) {
   static int trace_left = getenv("RN_CHAIN_TRACE") ? atoi(getenv("RN_CHAIN_TRACE")) : 0;
   p.trace = nullptr;
   if (trace_left > 0) {
-    if (!trace_buf) cudaMalloc(&trace_buf, 64 * 8 * sizeof(long long));
-    cudaMemsetAsync(trace_buf, 0, 64 * 8 * sizeof(long long), st);
+    if (!trace_buf) cudaMalloc(&trace_buf, 64 * kTraceSlots * sizeof(long long));
+    cudaMemsetAsync(trace_buf, 0, 64 * kTraceSlots * sizeof(long long), st);
     p.trace = trace_buf;
   }
   double exec_flops = 0.0;   // three MMAs per K step
@@ -696,19 +731,21 @@ int launch_chain_x3(const ChainArgs& a, cudaStream_t st) {
   if (p.trace) {
     --trace_left;
     cudaStreamSynchronize(st);
-    static long long hbuf[64 * 8];
+    static long long hbuf[64 * kTraceSlots];
     cudaMemcpy(hbuf, trace_buf, sizeof(hbuf), cudaMemcpyDeviceToHost);
     long long t0 = 0;
-    for (int i = 0; i < 64 * 8 && !t0; ++i) t0 = hbuf[i];
-    for (int i = 0; i < 64 * 8; ++i)
+    for (int i = 0; i < 64 * kTraceSlots && !t0; ++i) t0 = hbuf[i];
+    for (int i = 0; i < 64 * kTraceSlots; ++i)
       if (hbuf[i] && hbuf[i] < t0) t0 = hbuf[i];
-    printf("chain_x3 trace (mode %d, %d ops, m=%lld): per op: mma_acc_free first_blk_ready mma_issued | epi_begin acc_full(half 0) blk0_handed epi_end  [cycles since first event]\n",
-           mode, a.num_ops, (long long)a.m);
+    printf("chain_x3 trace (mode %d, %d ops, m=%lld, order %d): per op: mma_acc_free first_blk_ready mma_issued | epi_begin acc_full(half 0) blk0_handed epi_end | last_blk_ready(half 0)"
+           " || MMA warp: before acc_free wait, waits of items 0..7 passed || block 3 handed by epilogue warps 4..11  [cycles since first event]\n",
+           mode, a.num_ops, (long long)a.m, p.split_order);
     for (int i = 0; i < 44; ++i) {
       printf("  op %2d:", i);
-      for (int j = 0; j < 7; ++j) {
-        if (j == 3) printf(" |");
-        if (hbuf[i * 8 + j]) printf(" %8lld", hbuf[i * 8 + j] - t0); else printf("        -");
+      for (int j = 0; j < 26; ++j) {
+        if (j == 3 || j == 7) printf(" |");
+        if (j == 8 || j == 18) printf(" ||");
+        if (hbuf[i * kTraceSlots + j]) printf(" %7lld", hbuf[i * kTraceSlots + j] - t0); else printf("       -");
       }
       printf("\n");
     }

@@ -419,7 +419,7 @@ template <int NSLAB, int SPLIT>
 __global__ void __launch_bounds__(256, 1)
 wgrad2_tc_kernel(const __grid_constant__ WgMaps maps, int64_t m, int64_t rows_per_cta, int n_real, int kx, int k_real,
                  int stages, float* __restrict__ out, int out_ld, float* __restrict__ bias_out, int f16,
-                 float* __restrict__ partial) {
+                 float* __restrict__ partial, int coalesced) {
   constexpr int kPlanes = SPLIT == 3 ? 2 : 1;
   constexpr int kRowBlk = SPLIT == 3 ? 32 : 64;
   constexpr int kBoxBytes = kRowBlk * 128;
@@ -568,6 +568,49 @@ wgrad2_tc_kernel(const __grid_constant__ WgMaps maps, int64_t m, int64_t rows_pe
       }
       mbar_wait(&tfull[0], 0);
       tc_fence_after();
+      if (!partial && coalesced) {
+        // The accumulator leaves TMEM with one dW row per lane; adding it to global memory from there touches 32 different
+        // lines per warp instruction (65 536 scalar reductions per CTA, all CTAs at once at the end of the launch: ~12 % of
+        // the kernel).  Transpose through the (now idle) ring instead -- 32 rows x kx floats per warp, 16-byte groups
+        // XOR-swizzled by the row so that both the row-per-lane writes and the row-contiguous reads are conflict-free --
+        // and add whole rows with red.v4: 512 contiguous bytes per warp instruction.
+        asm volatile("bar.sync 1, 128;" ::: "memory");   // every epilogue warp is done with the staged dY tiles (bias sums)
+        const uint32_t stg = smem_u32(smem) + (uint32_t)q * (uint32_t)(32 * kx * 4);
+        const uint32_t row_pitch = (uint32_t)kx * 4u;
+#pragma unroll 1
+        for (int sl = 0; sl < NSLAB; ++sl) {
+          const uint32_t taddr = tmem_base + sl * 256 + ((uint32_t)(q * 32) << 16);
+          for (int c0 = 0; c0 < kx; c0 += 32) {
+            uint32_t r[32];
+            tmem_ld32(taddr + (uint32_t)c0, r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int e4 = 0; e4 < 8; ++e4) {
+              const uint32_t g = (uint32_t)(c0 >> 2) + e4;
+              sts128(stg + lane * row_pitch + (((g & ~7u) | ((g ^ (uint32_t)lane) & 7u)) << 4), r[4 * e4], r[4 * e4 + 1], r[4 * e4 + 2],
+                     r[4 * e4 + 3]);
+            }
+          }
+          __syncwarp();
+          for (int rr = 0; rr < 32; ++rr) {
+            const int nrow = sl * 128 + q * 32 + rr;
+            if (nrow >= n_real) break;
+            float* orow = out + (size_t)nrow * out_ld;
+            for (int g = lane; 4 * g < k_real; g += 32) {
+              const float4 v = lds128f(stg + rr * row_pitch + ((((uint32_t)g & ~7u) | (((uint32_t)g ^ (uint32_t)rr) & 7u)) << 4));
+              if (4 * g + 3 < k_real) {
+                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(orow + 4 * g), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+                             : "memory");
+              } else {
+                atomicAdd(orow + 4 * g, v.x);
+                if (4 * g + 1 < k_real) atomicAdd(orow + 4 * g + 1, v.y);
+                if (4 * g + 2 < k_real) atomicAdd(orow + 4 * g + 2, v.z);
+              }
+            }
+          }
+          __syncwarp();
+        }
+      } else
 #pragma unroll
       for (int sl = 0; sl < NSLAB; ++sl) {
         const int nrow = sl * 128 + q * 32 + lane;
@@ -694,7 +737,11 @@ int launch_wgrad2_tc(const WgradArgs& g, cudaStream_t st) {
   }
   const int f16 = (g.x_f16 && g.dy_f16) ? 1 : 0;
   rn_prof_begin(RN_PROF_WGRAD_TC, st, g.algo_flops, (x3 ? 3.0 : 1.0) * 2.0 * (double)g.m * (128.0 * nslab) * g.kx);
-#define RN_WG2(NS, SP) wgrad2_tc_kernel<NS, SP><<<grid, 256, smem, st>>>(maps, g.m, rows_per, g.n_real, g.kx, g.k_real, stages, g.out, g.out_ld, g.bias_out, f16, g.partial)
+  // row-coalesced red.v4 epilogue: needs 16-byte aligned dW rows and 128 x kx floats of staging in the ring
+  static const bool scalar_red = getenv("RN_WGRAD_SCALAR_RED") != nullptr;   // (A/B switch for the profiles)
+  const int coalesced = (!scalar_red && (reinterpret_cast<uintptr_t>(g.out) & 15u) == 0 && (g.out_ld & 3) == 0 &&
+                         (size_t)128 * g.kx * 4 <= (size_t)stages * stage_bytes) ? 1 : 0;
+#define RN_WG2(NS, SP) wgrad2_tc_kernel<NS, SP><<<grid, 256, smem, st>>>(maps, g.m, rows_per, g.n_real, g.kx, g.k_real, stages, g.out, g.out_ld, g.bias_out, f16, g.partial, coalesced)
   if (x3) {
     if (nslab == 2) RN_WG2(2, 3); else RN_WG2(1, 3);
   } else {

@@ -1066,7 +1066,7 @@ extern "C" int rn_gemm_test(const float* a, const float* b, const float* bias, i
 
 extern "C" int rn_wgrad_test(const float* dy, const float* x, int64_t m, int n, int k, int prec, int impl, float* cmat,
                              void* scratch, size_t scratch_bytes, void* stream) {
-  if (n % 8 || n > 128 || k % 64 || k > 256) return rn_set_error(RN_ERR_ARG, "rn_wgrad_test: need n%8==0, n<=128, k%64==0, k<=256");
+  if (n % 8 || n > 256 || k % 64 || k > 256) return rn_set_error(RN_ERR_ARG, "rn_wgrad_test: need n%8==0, n<=256, k%64==0, k<=256");
   if (scratch_bytes < rn_gemm_scratch_bytes(m, n, k)) return rn_set_error(RN_ERR_ARG, "rn_wgrad_test: scratch too small");
   cudaStream_t st = (cudaStream_t)stream;
   Carver c{reinterpret_cast<uint8_t*>(scratch)};
@@ -1081,7 +1081,18 @@ extern "C" int rn_wgrad_test(const float* dy, const float* x, int64_t m, int n, 
   g.dy = ybuf; g.dy_valid = n; g.n0 = 0; g.n_real = n;
   g.x = xbuf; g.x_valid = k; g.kx = k; g.k_real = k;
   g.out = cmat; g.out_ld = k;
-  return launch_wgrad(g, st);
+  if (n <= 128) return launch_wgrad(g, st);
+  // wider dY: the tcgen05 kernels cover both 128-feature slabs in ONE launch (the training path's wgrad2 kernel with
+  // its row-coalesced red.v4 epilogue), the SIMT kernel takes one launch per slab
+  if (impl == 0 && prec != RN_PREC_FP32) {
+    g.all_slabs = 1;
+    return launch_wgrad(g, st);
+  }
+  for (int n0 = 0; n0 < n; n0 += 128) {
+    g.n0 = n0;
+    RN_TRY(launch_wgrad(g, st));
+  }
+  return RN_OK;
 }
 
 extern "C" int rn_gemm_bench(int64_t m, int prec, int impl, int iters, float* ms_out, void* scratch, size_t scratch_bytes,

@@ -418,10 +418,13 @@ def mlp_forward(tdist: Tensor, origins: Tensor, dirs: Tensor, viewdirs: Tensor, 
     if saved_bytes > SAVED_BYTES_CAP:
         saved_bytes = 0
     if saved_bytes:   # bound by what is actually free as well (the backward then recomputes chunk by chunk)
-        free_b, _ = torch.cuda.mem_get_info(dev)
         cached = torch.cuda.memory_reserved(dev) - torch.cuda.memory_allocated(dev)
-        if saved_bytes > 0.8 * (free_b + cached):
-            saved_bytes = 0
+        if saved_bytes > cached:
+            # not served from the caching allocator's pool (first steps only): ask the driver.  cudaMemGetInfo costs 3 ms
+            # and more of host time -- at the head of a step that is GPU idle time whenever the host is not running ahead
+            free_b, _ = torch.cuda.mem_get_info(dev)
+            if saved_bytes > 0.8 * (free_b + cached):
+                saved_bytes = 0
     saved = torch.empty((saved_bytes,), device=dev, dtype=torch.uint8)
     ws_bytes = lib.rn_mlp_workspace_bytes(ctypes.byref(cfg), (2 if saved_bytes else 1) if training else 0)
     ws = torch.empty((ws_bytes,), device=dev, dtype=torch.uint8)

@@ -45,7 +45,8 @@ def test_gemm(prec, impl, shape):
 
 @pytest.mark.parametrize('impl', [1, 0], ids=['simt', 'tc'])
 @pytest.mark.parametrize('prec', ['fp32', 'bf16', 'bf16x3'])
-@pytest.mark.parametrize('shape', [(512, 128, 256), (4096, 128, 128), (3000, 16, 256), (40000, 128, 256)])
+@pytest.mark.parametrize('shape', [(512, 128, 256), (4096, 128, 128), (3000, 16, 256), (40000, 128, 256),
+                                   (3000, 256, 256), (20000, 144, 128), (70000, 256, 192)])
 def test_wgrad(prec, impl, shape):
     from refnerf_pl_b200 import ops
     m, n, k = shape
