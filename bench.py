@@ -356,13 +356,10 @@ class Workload:
         else:
             rend, hist = model(rays, 1.0, True)
             loss, _ = tu.total_loss(model, rays.viewdirs, rays.lossmult, gt, rend, hist, cfg)
-        if self.reducer is not None:
-            self.reducer.attach()     # .grad = zeroed slices of ONE flat buffer: backward accumulates in place, and the
-            loss.backward()           # collective runs on that buffer directly (no per-parameter copies, no div_)
+        self.opt.zero_grad(set_to_none=True)
+        loss.backward()               # every .grad is a view of ONE flat buffer (ops.param_carrier): the sum over the
+        if self.reducer is not None:  # step's fused MLP calls, so the collective runs on it directly (no copies, no div_)
             self.reducer.allreduce()
-        else:
-            self.opt.zero_grad(set_to_none=True)
-            loss.backward()
         if cfg.grad_max_norm > 0:
             torch.nn.utils.clip_grad_norm_(model.nerf_mlp.parameters(), cfg.grad_max_norm)
         self.opt.step()

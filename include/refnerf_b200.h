@@ -113,6 +113,17 @@ RN_API int rn_normal_losses_bwd(const float* weights, const float* normals, cons
                          const float* g_ori, const float* g_pred, int64_t n_rays, int s, int ori_target_is_pred,
                          float* d_weights, float* d_normals_pred, void* stream);
 
+/* train_utils.compute_data_loss (train_utils.py:33-88) of one level, the loss epilogue of SURVEY 8(f) rank 2: ONE launch
+ * instead of ~10 elementwise / reduction launches over [N,3] tensors.  rgb, gt [N,3]; lossmult [N] (the reference
+ * broadcasts rays.lossmult over the channels) or NULL (= 1, config.disable_multiscale_loss).  sums_out[3] =
+ * { sum lm (rgb-gt)^2,  sum lm term(rgb-gt),  sum lm } with term = r^2 (charb == 0, data_loss_type 'mse') or
+ * sqrt(r^2 + charb_padding^2) ('charb'); fp64 accumulation in a fixed order (bit-reproducible).  The caller divides
+ * (mse = s0 / s2, data loss = s1 / s2) and applies data_(coarse_)loss_mult.  Backward w.r.t. rgb given g_sums[0..1]. */
+RN_API int rn_data_loss_fwd(const float* rgb, const float* gt, const float* lossmult, int64_t n_rays, int charb,
+                     float charb_padding, float* sums_out, void* stream);
+RN_API int rn_data_loss_bwd(const float* rgb, const float* gt, const float* lossmult, const float* g_sums, int64_t n_rays,
+                     int charb, float charb_padding, float* d_rgb, void* stream);
+
 /* ---- K1 / K2 unit-level entry points (the fused MLP uses the same device code) -------------
  * rn_encode: render.cast_rays (render.py:105-129, cone, full cov) + coord.lift_and_diagonalize
  * (coord.py:129-133, octahedron-1 basis) + coord.integrated_pos_enc (coord.py:107-126, degrees

@@ -40,6 +40,8 @@ _SIGNATURES = {
     'rn_distortion_bwd': (c_int, [_P, _P, _P, c_int64, c_int, _P, _P]),
     'rn_normal_losses_fwd': (c_int, [_P, _P, _P, _P, c_int64, c_int, c_int, _P, _P, _P]),
     'rn_normal_losses_bwd': (c_int, [_P, _P, _P, _P, _P, _P, c_int64, c_int, c_int, _P, _P, _P]),
+    'rn_data_loss_fwd': (c_int, [_P, _P, _P, c_int64, c_int, c_float, _P, _P]),
+    'rn_data_loss_bwd': (c_int, [_P, _P, _P, _P, c_int64, c_int, c_float, _P, _P]),
     'rn_encode': (c_int, [_P, _P, _P, _P, c_int64, c_int, _P, _P]),
     'rn_ide': (c_int, [_P, _P, c_int64, _P, _P]),
     'rn_pixels_to_rays': (c_int, [_P, _P, _P, _P, _P, _P, c_int64, _P, _P, _P, _P, _P, _P]),

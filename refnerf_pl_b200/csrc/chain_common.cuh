@@ -205,6 +205,8 @@ struct PairParams {
   int a_f16, b_f16;  // operand formats of the MMAs (0 bf16, 1 fp16); the activation tile / outputs use a's
   int w_planes;      // chain_pair.cu: 2 = every weight K block arrives as a hi and a lo ring item (2 MMAs per K step)
   int split_order;   // chain_x3.cu: issue order of the (column half, K block) pairs of a 256-wide op, see res_order()
+  int whatif;        // chain_x3.cu, RN_X3_WHATIF (TIMING EXPERIMENTS ONLY, results are garbage): bit 0 = the epilogue skips its
+                     // shared-memory stores, bit 1 = the producer skips the weight loads, bit 2 = no TMA save stores
   float seed_scale;  // seed ops: vec * seed_scale
   int64_t m;
   long long* trace;   // debug timeline (RN_CHAIN_TRACE=<launches>): written by CTA 0 only

@@ -155,6 +155,11 @@ chain_x3_kernel(const __grid_constant__ X3Maps maps, const __grid_constant__ Pai
     auto load_w = [&](int l, const PairOp& L, int kblk, int half) {
       const uint32_t s = acquire();
       const int rows = L.n >= 256 ? 64 : (L.n >> 1);
+      if (p.whatif & 2) {   // timing experiment: no weight traffic at all
+        if (rank == 0 && elect_one_sync()) mbar_arrive(&ring_full[s]);
+        __syncwarp();
+        return;
+      }
       if (elect_one_sync()) {
         if (rank == 0) mbar_arrive_expect_tx(&ring_full[s], (uint32_t)rows * 512u);   // 2 planes x 2 CTAs x rows x 128 B
         const uint32_t dst = smem_base + kSmemRing + s * kStageBytes;
@@ -236,7 +241,13 @@ chain_x3_kernel(const __grid_constant__ X3Maps maps, const __grid_constant__ Pai
         for (int i = 0; i < nhalf * L.kb_act; ++i) {
           int oh, ok;
           res_order(p.split_order, i, L.kb_act, nhalf, oh, ok);
+          const bool trp = p.trace && blockIdx.x == 0 && lane == 0 && (i == 0 || i == 4) && tile_iter * p.num_ops + l < 64;
+          if (trp) {   // (debug timeline) when this item's ring stage became free / when its TMA loads were issued
+            mbar_wait(&ring_empty[pos % kStages], ((pos / kStages) & 1u) ^ 1u);
+            p.trace[(tile_iter * p.num_ops + l) * kTraceSlots + 26 + (i ? 2 : 0)] = clock64();
+          }
           load_w(l, L, ok, oh);
+          if (trp) p.trace[(tile_iter * p.num_ops + l) * kTraceSlots + 27 + (i ? 2 : 0)] = clock64();
         }
       }
     }
@@ -314,6 +325,7 @@ chain_x3_kernel(const __grid_constant__ X3Maps maps, const __grid_constant__ Pai
               if (direct) mbar_wait_cluster(&in_full[kb], tile_iter & 1u);
               else if (need_acq) mbar_wait_cluster(&act_ready[kb], aver & 1u);
             }
+            if (tr && (i == 0 || i == 4)) p.trace[opcount * kTraceSlots + (i ? 31 : 30)] = clock64();   // before the weight wait
             wait_full(pos);
             tc_fence_after();
             if (tr && kb == 0 && half == 0) p.trace[opcount * kTraceSlots + 1] = clock64();
@@ -362,7 +374,7 @@ chain_x3_kernel(const __grid_constant__ X3Maps maps, const __grid_constant__ Pai
           mbar_wait(&written[ch], nw[ch] & 1u);
           ++nw[ch];
           if (elect_one_sync()) {
-            if (row_c < p.m) {
+            if (row_c < p.m && !(p.whatif & 4)) {
               if (sv) {
 #pragma unroll
                 for (int c = 2 * ch; c < 2 * ch + 2; ++c) tma_store_2d(&maps.save[l], smem_base + c * kPlaneBytes, c * 64, (int)row_c);
@@ -413,6 +425,14 @@ chain_x3_kernel(const __grid_constant__ X3Maps maps, const __grid_constant__ Pai
     // write this thread's 32 columns (half h of K block c) of both planes
     auto store_block = [&](int c, const uint32_t* hi, const uint32_t* lo) {
       const uint32_t bh = act_row_hi + (uint32_t)(c * kPlaneBytes), bl = act_row_lo + (uint32_t)(c * kPlaneBytes);
+      if (p.whatif & 1) {   // timing experiment: keep the arithmetic alive, skip the stores
+        uint32_t x = 0;
+#pragma unroll
+        for (int u = 0; u < 16; ++u) x ^= hi[u] ^ lo[u];
+        if (x == 0x12345u) sts128(bh, x, x, x, x);
+        fence_proxy_async();
+        return;
+      }
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         const uint32_t pos16 = ((uint32_t)(h * 4 + u) ^ swz) * 16u;
@@ -635,6 +655,13 @@ int launch_chain_x3(const ChainArgs& a, cudaStream_t st) {
   // weight ring's L2 latency and the power cap, not by the epilogue hand-over -- so the plain order stays the default)
   static const int split_order = getenv("RN_X3_ORDER") ? atoi(getenv("RN_X3_ORDER")) : 0;
   p.split_order = split_order;
+  static const int whatif = getenv("RN_X3_WHATIF") ? atoi(getenv("RN_X3_WHATIF")) : 0;
+  p.whatif = whatif;
+  if (whatif) {
+    static bool warned = false;
+    if (!warned) fprintf(stderr, "refnerf_b200: RN_X3_WHATIF=%d -- TIMING EXPERIMENT, the chain kernels skip work and their results are GARBAGE\n", whatif);
+    warned = true;
+  }
   p.seed_scale = a.seed_scale;
   p.num_ops = a.num_ops;
   p.in_kb = a.in.hi ? a.in_cols / kBK : 0;
@@ -738,13 +765,14 @@ int launch_chain_x3(const ChainArgs& a, cudaStream_t st) {
     for (int i = 0; i < 64 * kTraceSlots; ++i)
       if (hbuf[i] && hbuf[i] < t0) t0 = hbuf[i];
     printf("chain_x3 trace (mode %d, %d ops, m=%lld, order %d): per op: mma_acc_free first_blk_ready mma_issued | epi_begin acc_full(half 0) blk0_handed epi_end | last_blk_ready(half 0)"
-           " || MMA warp: before acc_free wait, waits of items 0..7 passed || block 3 handed by epilogue warps 4..11  [cycles since first event]\n",
+           " || MMA warp: before acc_free wait, waits of items 0..7 passed || block 3 handed by epilogue warps 4..11"
+           " || producer: stage free / TMA issued for items 0 and 4 || MMA warp: before the weight wait of items 0 and 4  [cycles since first event]\n",
            mode, a.num_ops, (long long)a.m, p.split_order);
     for (int i = 0; i < 44; ++i) {
       printf("  op %2d:", i);
-      for (int j = 0; j < 26; ++j) {
+      for (int j = 0; j < 32; ++j) {
         if (j == 3 || j == 7) printf(" |");
-        if (j == 8 || j == 18) printf(" ||");
+        if (j == 8 || j == 18 || j == 26 || j == 30) printf(" ||");
         if (hbuf[i * kTraceSlots + j]) printf(" %7lld", hbuf[i * kTraceSlots + j] - t0); else printf("       -");
       }
       printf("\n");

@@ -1217,6 +1217,82 @@ extern "C" int rn_distortion_bwd(const float* t, const float* w, const float* g_
   return RN_OK;
 }
 
+// ---------------------------------------------------------------------------------------------
+// train_utils.compute_data_loss (train_utils.py:33-88) of ONE level in one launch: the three sums the reference takes with
+// ~10 elementwise / reduction launches over [N,3] tensors.  One block, fp64 partial sums combined in a fixed order, so the
+// result is bit-reproducible (and closer to exact than the reference's own fp32 sum).
+//   out[0] = sum lm (rgb - gt)^2     (the 'mses' statistic)
+//   out[1] = sum lm term(rgb - gt)   term = r^2 ('mse') or sqrt(r^2 + pad^2) ('charb')
+//   out[2] = sum lm                  (lm broadcast over the 3 channels; lm == NULL: 1, disable_multiscale_loss)
+// backward: d_rgb = lm (g0 2 r + g1 dterm/dr).
+// ---------------------------------------------------------------------------------------------
+namespace {
+__device__ __forceinline__ double block_sum_1024(double v, double* sh) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  __syncthreads();
+  if (lane == 0) sh[warp] = v;
+  __syncthreads();
+  v = lane < (int)(blockDim.x >> 5) ? sh[lane] : 0.0;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__global__ void __launch_bounds__(1024)
+data_loss_fwd_kernel(const float* __restrict__ rgb, const float* __restrict__ gt, const float* __restrict__ lm, int64_t n,
+                     int charb, float pad2, float* __restrict__ out) {
+  __shared__ double sh[32];
+  double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+  for (int64_t i = threadIdx.x; i < 3 * n; i += blockDim.x) {
+    const float m = lm ? lm[i / 3] : 1.f;
+    const float r = rgb[i] - gt[i];
+    const float r2 = r * r;
+    s0 += (double)(m * r2);
+    s1 += (double)(m * (charb ? sqrtf(r2 + pad2) : r2));
+    s2 += (double)m;
+  }
+  s0 = block_sum_1024(s0, sh);
+  s1 = block_sum_1024(s1, sh);
+  s2 = block_sum_1024(s2, sh);
+  if (threadIdx.x == 0) {
+    out[0] = (float)s0;
+    out[1] = (float)s1;
+    out[2] = (float)s2;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+data_loss_bwd_kernel(const float* __restrict__ rgb, const float* __restrict__ gt, const float* __restrict__ lm,
+                     const float* __restrict__ g, int64_t n, int charb, float pad2, float* __restrict__ d_rgb) {
+  const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (i >= 3 * n) return;
+  const float m = lm ? lm[i / 3] : 1.f;
+  const float r = rgb[i] - gt[i];
+  const float dterm = charb ? r / sqrtf(r * r + pad2) : 2.f * r;
+  d_rgb[i] = m * (g[0] * 2.f * r + g[1] * dterm);
+}
+}  // namespace
+
+extern "C" int rn_data_loss_fwd(const float* rgb, const float* gt, const float* lossmult, int64_t n_rays, int charb,
+                                float charb_padding, float* sums_out, void* stream) {
+  if (!rgb || !gt || !sums_out || n_rays < 0) return rn_set_error(RN_ERR_ARG, "rn_data_loss_fwd: bad arguments");
+  data_loss_fwd_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(rgb, gt, lossmult, n_rays, charb, charb_padding * charb_padding, sums_out);
+  RN_CUDA_CHECK_LAUNCH();
+  return RN_OK;
+}
+
+extern "C" int rn_data_loss_bwd(const float* rgb, const float* gt, const float* lossmult, const float* g_sums, int64_t n_rays,
+                                int charb, float charb_padding, float* d_rgb, void* stream) {
+  if (n_rays == 0) return RN_OK;
+  if (!rgb || !gt || !g_sums || !d_rgb || n_rays < 0) return rn_set_error(RN_ERR_ARG, "rn_data_loss_bwd: bad arguments");
+  data_loss_bwd_kernel<<<(unsigned)((3 * n_rays + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      rgb, gt, lossmult, g_sums, n_rays, charb, charb_padding * charb_padding, d_rgb);
+  RN_CUDA_CHECK_LAUNCH();
+  return RN_OK;
+}
+
 extern "C" int rn_normal_losses_fwd(const float* weights, const float* normals, const float* normals_pred,
                                     const float* viewdirs, int64_t n_rays, int s, int ori_target_is_pred, float* ori_out,
                                     float* pred_out, void* stream) {

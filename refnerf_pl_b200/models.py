@@ -144,6 +144,12 @@ class MLP(nn.Module):
         named = dict(self.named_parameters())
         return [named[n] for n in _lib.param_names()]
 
+    def param_carrier(self):
+        """The differentiable stand-in for the parameters that every fused call of ONE step shares (ops.param_carrier).
+        `Model.__call__` opens one per call of the level loop; a stand-alone MLP call makes its own."""
+        c = self.__dict__.get('_carrier')
+        return c if c is not None else ops.param_carrier(self.ordered_params())
+
     def invalidate_packed(self):
         """Drop the packed-weight cache.  It is keyed on (data_ptr, _version) of every parameter, which in-place updates
         through `.data` (EMA, manual weight surgery) do not change: call this after such an update."""
@@ -182,7 +188,7 @@ class MLP(nn.Module):
         flat = lambda t, c: ops._f32c(t.reshape(-1, c))
         training = self.training
         out = ops.mlp_forward(flat(g.tdist, s + 1), flat(g.origins, 3), flat(g.directions, 3), flat(viewdirs, 3),
-                              flat(g.radii, 1), self.ordered_params(), self.packed_weights(), training,
+                              flat(g.radii, 1), self.param_carrier(), self.packed_weights(), training,
                               _lib.PREC_BY_NAME[self.precision], self.srgb_mapping, self.srgb_mapping_normalization,
                               float(self.density_bias), float(self.roughness_bias), float(self.rgb_premultiplier),
                               float(self.rgb_bias), float(self.rgb_padding), int(self.chunk_rows),
@@ -308,6 +314,20 @@ class Model(nn.Module):
             bg = float(self.bg_intensity_range[0] + self.bg_intensity_range[1]) / 2
         mapping = self.config.srgb_mapping_type if self.config.srgb_mapping_when_rendering else 'none'
         renderings, ray_history = [], []
+        # one autograd edge to the parameters for every fused MLP call of this level loop (ops.param_carrier)
+        mlps = {id(m): m for m in (self.nerf_mlp, self.prop_mlp) if m is not None}
+        for m in mlps.values():
+            m.__dict__['_carrier'] = ops.param_carrier(m.ordered_params())
+        try:
+            return self._levels(lead, r, n, near, far, sdist, weights, prod_num_samples, bg, mapping, train_frac,
+                                compute_extras, renderings, ray_history)
+        finally:
+            for m in mlps.values():
+                m.__dict__['_carrier'] = None
+
+    def _levels(self, lead, r, n, near, far, sdist, weights, prod_num_samples, bg, mapping, train_frac, compute_extras,
+                renderings, ray_history):
+        from . import render  # noqa: PLC0415 (function-level surface built on the same ops)
         for i_level in range(self.num_levels):
             is_prop = i_level < (self.num_levels - 1)
             num_samples = self.num_prop_samples if is_prop else self.num_nerf_samples

@@ -337,6 +337,52 @@ torch.library.register_autograd(f'{NS}::normal_losses', _nl_backward, setup_cont
 
 
 # ------------------------------------------------------------------------------------------
+# data loss of one level (train_utils.py:33-88; the loss epilogue of SURVEY 8(f) rank 2)
+# ------------------------------------------------------------------------------------------
+@torch.library.custom_op(f'{NS}::data_loss_sums', mutates_args=(), device_types='cuda')
+def data_loss_sums(rgb: Tensor, gt: Tensor, lossmult: Tensor, charb: bool, charb_padding: float) -> Tensor:
+    """rgb, gt [N,3]; lossmult [N] (empty = 1) -> [3] = (sum lm r^2, sum lm term(r), sum lm), r = rgb - gt."""
+    lib = _lib.load()
+    out = torch.empty((3,), device=rgb.device, dtype=torch.float32)
+    _lib.check(lib.rn_data_loss_fwd(_ptr(rgb), _ptr(gt), _ptr(lossmult) if lossmult.numel() else None, rgb.shape[0],
+                                    int(charb), charb_padding, _ptr(out), _stream()))
+    return out
+
+
+@data_loss_sums.register_fake
+def _(rgb, gt, lossmult, charb, charb_padding):
+    return rgb.new_empty((3,))
+
+
+@torch.library.custom_op(f'{NS}::data_loss_sums_bwd', mutates_args=(), device_types='cuda')
+def data_loss_sums_bwd(rgb: Tensor, gt: Tensor, lossmult: Tensor, g: Tensor, charb: bool, charb_padding: float) -> Tensor:
+    lib = _lib.load()
+    d_rgb = torch.empty_like(rgb)
+    _lib.check(lib.rn_data_loss_bwd(_ptr(rgb), _ptr(gt), _ptr(lossmult) if lossmult.numel() else None, _ptr(g), rgb.shape[0],
+                                    int(charb), charb_padding, _ptr(d_rgb), _stream()))
+    return d_rgb
+
+
+@data_loss_sums_bwd.register_fake
+def _(rgb, gt, lossmult, g, charb, charb_padding):
+    return torch.empty_like(rgb)
+
+
+def _dl_setup(ctx, inputs, output):
+    rgb, gt, lossmult, charb, pad = inputs
+    ctx.save_for_backward(rgb, gt, lossmult)
+    ctx.charb, ctx.pad = charb, pad
+
+
+def _dl_backward(ctx, g):
+    rgb, gt, lossmult = ctx.saved_tensors
+    return data_loss_sums_bwd(rgb, gt, lossmult, _f32c(g), ctx.charb, ctx.pad), None, None, None, None
+
+
+torch.library.register_autograd(f'{NS}::data_loss_sums', _dl_backward, setup_context=_dl_setup)
+
+
+# ------------------------------------------------------------------------------------------
 # unit-level encoders
 # ------------------------------------------------------------------------------------------
 @torch.library.custom_op(f'{NS}::encode', mutates_args=(), device_types='cuda')
@@ -393,15 +439,42 @@ def mlp_pack(params: Sequence[Tensor], prec: int) -> Tensor:
     return blob
 
 
+@torch.library.custom_op(f'{NS}::param_carrier', mutates_args=(), device_types='cuda')
+def param_carrier(params: Sequence[Tensor]) -> Tensor:
+    """The autograd edge from the 46 parameters to the fused MLP calls of one step, as ONE flat fp32 tensor (its VALUES are
+    never read -- the kernels read the packed weights).  Every `mlp_forward` of the step takes the same carrier, so
+    autograd sums the per-call flat parameter gradients with one add, and the carrier's backward hands every parameter
+    a view of that sum: no per-parameter accumulation kernels, and all `.grad`s tile one buffer (what
+    `parallel.GradAllReducer` runs its collective on)."""
+    return torch.empty((sum(_param_sizes()),), device=params[0].device, dtype=torch.float32)
+
+
+@param_carrier.register_fake
+def _(params):
+    return params[0].new_empty((sum(p.numel() for p in params),))
+
+
+def _pc_setup(ctx, inputs, output):
+    ctx.param_shapes = [p.shape for p in inputs[0]]
+
+
+def _pc_backward(ctx, g):
+    g = _f32c(g)
+    return ([t.view(shape) for t, shape in zip(g.split(_param_sizes()), ctx.param_shapes)],)
+
+
+torch.library.register_autograd(f'{NS}::param_carrier', _pc_backward, setup_context=_pc_setup)
+
+
 @torch.library.custom_op(f'{NS}::mlp_forward', mutates_args=(), device_types='cuda')
-def mlp_forward(tdist: Tensor, origins: Tensor, dirs: Tensor, viewdirs: Tensor, radii: Tensor, params: Sequence[Tensor],
+def mlp_forward(tdist: Tensor, origins: Tensor, dirs: Tensor, viewdirs: Tensor, radii: Tensor, carrier: Tensor,
                 packed: Tensor, training: bool, prec: int, srgb_mapping: bool, srgb_norm: bool, density_bias: float,
                 roughness_bias: float, rgb_premultiplier: float, rgb_bias: float, rgb_padding: float, chunk_rows: int,
                 gemm_impl: int, keep_saved: bool) -> List[Tensor]:
     """-> [density [N,S], rgb, normals (empty in eval), normals_pred, grad_pred, tint, diffuse, specular [N,S,3],
     roughness [N,S,1], saved (uint8: activations kept for the backward; empty in eval / when over the cap / when
     `keep_saved` is False, e.g. a training-mode forward under torch.no_grad())].
-    `params` only carries autograd edges; the arithmetic reads `packed`."""
+    `carrier` (ops.param_carrier) only carries the autograd edge to the parameters; the arithmetic reads `packed`."""
     lib = _lib.load()
     n, s1 = tdist.shape
     s = s1 - 1
@@ -438,7 +511,7 @@ def mlp_forward(tdist: Tensor, origins: Tensor, dirs: Tensor, viewdirs: Tensor, 
 
 
 @mlp_forward.register_fake
-def _(tdist, origins, dirs, viewdirs, radii, params, packed, training, prec, srgb_mapping, srgb_norm, density_bias,
+def _(tdist, origins, dirs, viewdirs, radii, carrier, packed, training, prec, srgb_mapping, srgb_norm, density_bias,
       roughness_bias, rgb_premultiplier, rgb_bias, rgb_padding, chunk_rows, gemm_impl, keep_saved):
     n, s1 = tdist.shape
     s = s1 - 1
@@ -447,9 +520,14 @@ def _(tdist, origins, dirs, viewdirs, radii, params, packed, training, prec, srg
             f(n, s, 3), f(n, s, 1), tdist.new_empty((0,), dtype=torch.uint8)]
 
 
+_PARAM_SIZES = []
+
+
 def _param_sizes():
-    lib = _lib.load()
-    return [int(lib.rn_mlp_param_numel(i)) for i in range(_lib.NUM_PARAMS)]
+    if not _PARAM_SIZES:
+        lib = _lib.load()
+        _PARAM_SIZES.extend(int(lib.rn_mlp_param_numel(i)) for i in range(_lib.NUM_PARAMS))
+    return _PARAM_SIZES
 
 
 @torch.library.custom_op(f'{NS}::mlp_backward', mutates_args=(), device_types='cuda')
@@ -490,10 +568,9 @@ def _(tdist, origins, dirs, viewdirs, radii, packed, saved, grads, prec, srgb_ma
 
 
 def _mlp_setup(ctx, inputs, output):
-    (tdist, origins, dirs, viewdirs, radii, params, packed, training, *scalars) = inputs
+    (tdist, origins, dirs, viewdirs, radii, carrier, packed, training, *scalars) = inputs
     ctx.save_for_backward(tdist, origins, dirs, viewdirs, radii, packed, output[9])
     ctx.scalars = scalars[:-1]   # (keep_saved belongs to the forward only)
-    ctx.param_shapes = [p.shape for p in params]
     ctx.mark_non_differentiable(output[2], output[9])  # density-gradient normals are a constant
     ctx.set_materialize_grads(False)
 
@@ -504,8 +581,7 @@ def _mlp_backward(ctx, grads):
     order = (0, 1, 3, 4, 5, 6, 7, 8)  # density, rgb, normals_pred, grad_pred, tint, diffuse, specular, roughness
     g = [grads[i] if grads[i] is not None else empty for i in order]
     flat = mlp_backward(tdist, origins, dirs, viewdirs, radii, packed, saved, g, *ctx.scalars)
-    pg = [t.view(shape) for t, shape in zip(flat.split(_param_sizes()), ctx.param_shapes)]
-    return (None, None, None, None, None, pg, None, None) + (None,) * (len(ctx.scalars) + 1)
+    return (None, None, None, None, None, flat, None, None) + (None,) * (len(ctx.scalars) + 1)
 
 
 torch.library.register_autograd(f'{NS}::mlp_forward', _mlp_backward, setup_context=_mlp_setup)

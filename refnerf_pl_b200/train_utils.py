@@ -15,6 +15,26 @@ def compute_data_loss(batch_rgb, renderings, lossmult, config):
     if config.supervised_by_linear_rgb:                      # train_utils.py:40-41
         from . import image
         gt = image.srgb_to_linear(gt)
+    if config.data_loss_type not in ('mse', 'charb'):
+        assert False
+    if renderings[0]['rgb'].is_cuda and renderings[0]['rgb'].dtype == torch.float32:
+        # loss epilogue: the three sums of a level in one launch (rn_data_loss_fwd / _bwd)
+        gt2 = gt.reshape(-1, 3).float().contiguous()
+        n = gt2.shape[0]
+        if config.disable_multiscale_loss:
+            lm1 = gt2.new_empty((0,))
+        else:
+            lm1 = torch.broadcast_to(torch.as_tensor(lossmult, device=gt2.device, dtype=torch.float32), gt.shape[:-1] + (1,))
+            lm1 = lm1.reshape(n).contiguous()
+        losses, mses = [], []
+        for rendering in renderings:
+            sums = ops.data_loss_sums(rendering['rgb'].reshape(-1, 3).contiguous(), gt2, lm1,
+                                      config.data_loss_type == 'charb', float(config.charb_padding))
+            mses.append(sums[0] / sums[2])
+            losses.append(sums[1] / sums[2])
+        losses = torch.stack(losses)
+        loss = config.data_coarse_loss_mult * torch.sum(losses[:-1]) + config.data_loss_mult * losses[-1]
+        return loss, {'mses': torch.stack(mses).detach()}
     lm = torch.broadcast_to(lossmult, gt.shape)
     if config.disable_multiscale_loss:
         lm = torch.ones_like(lm)

@@ -495,3 +495,45 @@ def test_fp16_gradient_saturation_is_reported():
     step(p)
     assert ops.fp16_saturation_count(reset=True) > 0
     assert ops.fp16_saturation_count(reset=False) == 0
+
+
+def test_parameter_gradients_of_a_step_tile_one_flat_buffer():
+    """ops.param_carrier: both levels' fused calls share one autograd edge to the parameters, so a step's parameter
+    gradients are views of ONE flat buffer (their sum over the calls) -- what parallel.GradAllReducer reduces in place --
+    and they equal the gradients of per-call carriers (stand-alone MLP calls accumulate per parameter)."""
+    from refnerf_pl_b200 import parallel, synthetic, train_utils
+    p = O.init_params(seed=4, bias_std=0.1, weight_scale=1.2)
+    rays = synthetic.blender_rays(200, seed=9)
+    gt = torch.tensor(synthetic.gt_rgb(200, 9), device=DEV)
+    model, cfg = build_model('bf16x3', mlp_kwargs=dict(deterministic_wgrad=True))
+    load_params(model, p)
+    model.train(True)
+    r = rays_obj(rays)
+
+    def step():
+        for q in model.nerf_mlp.parameters():
+            q.grad = None
+        rend, hist = model(r, 1.0, True)
+        loss, _ = train_utils.total_loss(model, r.viewdirs, r.lossmult, gt, rend, hist, cfg)
+        loss.backward()
+
+    step()
+    red = parallel.GradAllReducer(model.nerf_mlp.parameters())
+    one = red._grads_as_one_buffer()
+    assert one is not None and one.numel() == sum(q.numel() for q in model.nerf_mlp.parameters())
+    shared = torch.cat([q.grad.reshape(-1) for q in model.nerf_mlp.parameters()]).clone()
+    assert model.nerf_mlp.__dict__.get('_carrier') is None          # closed again after the level loop
+    # the same step with one carrier per MLP call (per-parameter accumulation by autograd)
+    orig = type(model.nerf_mlp).param_carrier
+    try:
+        type(model.nerf_mlp).param_carrier = lambda self: ops_mod().param_carrier(self.ordered_params())
+        step()
+    finally:
+        type(model.nerf_mlp).param_carrier = orig
+    separate = torch.cat([q.grad.reshape(-1) for q in model.nerf_mlp.parameters()])
+    assert float((shared.double() - separate.double()).norm()) <= 1e-6 * float(separate.double().norm())
+
+
+def ops_mod():
+    from refnerf_pl_b200 import ops
+    return ops

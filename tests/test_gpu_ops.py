@@ -314,3 +314,38 @@ def test_max_dilate_weights_golden_and_oracle(ops, gold):
             assert torch.equal(kt.cpu(), rt), (s, dil)
             scale = max(1.0, float(rw.abs().max()))
             assert float((kw.cpu() - rw).abs().max()) <= 2e-7 * scale, (s, dil, renorm)
+
+
+@pytest.mark.parametrize('kind', ['mse', 'charb'])
+@pytest.mark.parametrize('n,multiscale', [(1, True), (37, True), (4096, True), (300, False)])
+def test_data_loss_epilogue_matches_reference_formula(ops, kind, n, multiscale):
+    """rn_data_loss_fwd / _bwd (one launch per level) vs train_utils.compute_data_loss's torch formula
+    (reference train_utils.py:33-88) in fp64: loss, the 'mses' statistic and d loss / d rgb of both levels."""
+    from types import SimpleNamespace
+    from refnerf_pl_b200 import train_utils
+    g = torch.Generator().manual_seed(n + len(kind))
+    gt = torch.rand(n, 3, generator=g)
+    lm = torch.rand(n, 1, generator=g) + 0.25
+    rgbs = [torch.rand(n, 3, generator=g) for _ in range(2)]
+    cfg = SimpleNamespace(supervised_by_linear_rgb=False, disable_multiscale_loss=not multiscale, data_loss_type=kind,
+                          charb_padding=0.001, data_coarse_loss_mult=0.5, data_loss_mult=1.0)
+    # fp64 statement of the reference formula
+    ref_in = [r.double().requires_grad_(True) for r in rgbs]
+    lmb = torch.broadcast_to(lm.double(), gt.shape) if multiscale else torch.ones_like(gt, dtype=torch.float64)
+    terms, mses = [], []
+    for r in ref_in:
+        r2 = (r - gt.double()) ** 2
+        mses.append((lmb * r2).sum() / lmb.sum())
+        terms.append((lmb * (r2 if kind == 'mse' else torch.sqrt(r2 + cfg.charb_padding ** 2))).sum() / lmb.sum())
+    ref_loss = cfg.data_coarse_loss_mult * terms[0] + cfg.data_loss_mult * terms[1]
+    ref_loss.backward()
+    dev_in = [r.to(DEV).requires_grad_(True) for r in rgbs]
+    loss, stats = train_utils.compute_data_loss(gt.to(DEV), [{'rgb': r} for r in dev_in], lm.to(DEV), cfg)
+    loss.backward()
+    assert abs(float(loss) - float(ref_loss)) <= 2e-6 * max(1.0, abs(float(ref_loss)))
+    assert np.abs(stats['mses'].cpu().numpy() - np.array([float(m) for m in mses])).max() <= 2e-6
+    for a, b in zip(dev_in, ref_in):
+        assert (a.grad.cpu().double() - b.grad).abs().max() <= 2e-6 * max(1e-3, float(b.grad.abs().max()))
+    # bit-reproducible (fixed summation order)
+    loss2, _ = train_utils.compute_data_loss(gt.to(DEV), [{'rgb': r.detach()} for r in dev_in], lm.to(DEV), cfg)
+    assert float(loss2) == float(loss.detach())
