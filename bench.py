@@ -410,7 +410,8 @@ def run_b200(args):
 
     def prof_read():
         prof = {}
-        for c, name in enumerate(('gemm_tc', 'wgrad_tc', 'gemm_simt', 'chain_tc')):
+        for c, name in enumerate(('gemm_tc', 'wgrad_tc', 'gemm_simt', 'chain_tc', 'encode', 'heads_prologue_fwd', 'heads_prologue_bwd',
+                                  'ipe_grad_normals', 'color', 'glue', 'ray_kernels')):
             nl, tms, fl, ef = ctypes.c_int64(0), ctypes.c_double(0), ctypes.c_double(0), ctypes.c_double(0)
             lib.rn_prof_summary2(c, ctypes.byref(nl), ctypes.byref(tms), ctypes.byref(fl), ctypes.byref(ef))
             prof[name] = dict(launches=nl.value, ms=tms.value, flops=fl.value, exec_flops=ef.value)

@@ -229,8 +229,10 @@ RN_API int64_t rn_fp16_saturation_count(int reset);
  * rn_launch_count: kernels launched by this library since load (process-wide).
  * rn_prof_enable(1) makes the GEMM launchers bracket every launch with CUDA events on the launching
  * stream; rn_prof_summary(cls, ...) synchronises the recorded events and returns, for kernel class
- * cls (0 = tcgen05 fwd/dgrad GEMM, 1 = tcgen05 wgrad, 2 = SIMT GEMMs, 3 = fused tcgen05 forward chain), the number of launches, their
- * summed device time in ms and the algorithmic FLOPs they carried, then clears the class. */
+ * cls (0 = tcgen05 fwd/dgrad GEMM, 1 = tcgen05 wgrad, 2 = SIMT GEMMs, 3 = fused tcgen05 chains; time only: 4 = encode,
+ * 5 / 6 = heads prologue forward / backward, 7 = IPE-gradient normals, 8 = colour combine, 9 = pack / unpack / conversion
+ * glue, 10 = the ray kernels: resample, compositing, losses), the number of launches, their summed device time in ms and
+ * the algorithmic FLOPs they carried, then clears the class. */
 RN_API int64_t rn_launch_count(void);
 RN_API int rn_prof_enable(int on);
 RN_API int rn_prof_summary(int cls, int64_t* launches, double* total_ms, double* algo_flops);

@@ -21,11 +21,21 @@ int rn_set_cuda_error(cudaError_t e, const char* file, int line);
 int rn_set_error(int code, const char* msg);
 void rn_count_launch();
 // optional CUDA-event timing of kernel classes (bench.py roofline); no-ops unless rn_prof_enable(1)
-enum { RN_PROF_GEMM_TC = 0, RN_PROF_WGRAD_TC = 1, RN_PROF_GEMM_SIMT = 2, RN_PROF_CHAIN_TC = 3, RN_PROF_NUM = 4 };
+enum { RN_PROF_GEMM_TC = 0, RN_PROF_WGRAD_TC = 1, RN_PROF_GEMM_SIMT = 2, RN_PROF_CHAIN_TC = 3,
+       // the non-GEMM kernels of a step (time only, no FLOP accounting)
+       RN_PROF_ENCODE = 4, RN_PROF_HEADS_FWD = 5, RN_PROF_HEADS_BWD = 6, RN_PROF_IPE_GRAD = 7, RN_PROF_COLOR = 8,
+       RN_PROF_GLUE = 9 /* pack / unpack / column sums / format conversions */, RN_PROF_RAY = 10 /* raymarch.cu entry points */,
+       RN_PROF_NUM = 11 };
 // algo_flops: algorithmic (dense, unpadded, 2*MAC) FLOPs of the launch; exec_flops: FLOPs the tensor pipe actually executes
 // for it (padded shapes x the number of MMAs per K step of the arithmetic mode)
 void rn_prof_begin(int cls, cudaStream_t st, double algo_flops, double exec_flops = 0.0);
 void rn_prof_end(int cls, cudaStream_t st);
+struct RnProfScope {   // brackets everything launched on `st` during its lifetime
+  int cls;
+  cudaStream_t st;
+  RnProfScope(int c, cudaStream_t s) : cls(c), st(s) { rn_prof_begin(c, s, 0.0); }
+  ~RnProfScope() { rn_prof_end(cls, st); }
+};
 
 // ------------------------------------------------------------------------------------------
 // Activation buffers: [rows, ld] matrices that feed / leave the GEMMs.

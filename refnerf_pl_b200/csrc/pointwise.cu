@@ -766,6 +766,7 @@ inline unsigned nblk(int64_t n, int per) { return (unsigned)((n + per - 1) / per
 
 int launch_encode(int prec, const float* tdist, const float* origins, const float* dirs, const float* radii, int s,
                   int64_t row0, int64_t rows, ActBuf out, int ncols, cudaStream_t st) {
+  RnProfScope prof_scope(RN_PROF_ENCODE, st);
   if (rows <= 0) return RN_OK;
   DISPATCH_PREC(prec, (encode_kernel<PREC><<<nblk(rows, kEncRows), 256, 0, st>>>(tdist, origins, dirs, radii, s, row0, rows, out, ncols)));
   RN_CUDA_CHECK_LAUNCH();
@@ -775,6 +776,7 @@ int launch_encode(int prec, const float* tdist, const float* origins, const floa
 int launch_ipe_grad_normals(const float* gx0, const float* gx0b, int ld, const float* tdist, const float* origins, const float* dirs,
                             const float* radii, int s, int64_t row0, int64_t rows, float* normals_out, float gscale,
                             cudaStream_t st) {
+  RnProfScope prof_scope(RN_PROF_IPE_GRAD, st);
   if (rows <= 0) return RN_OK;
   ipe_grad_normals_kernel<<<nblk(rows, kEncRows), 256, 0, st>>>(gx0, gx0b, ld, tdist, origins, dirs, radii, s, row0, rows, normals_out, gscale);
   RN_CUDA_CHECK_LAUNCH();
@@ -782,6 +784,7 @@ int launch_ipe_grad_normals(const float* gx0, const float* gx0b, int ld, const f
 }
 
 int launch_density_grad_seed(int prec, ActBuf a8, const float* wd, ActBuf out, int64_t rows, cudaStream_t st) {
+  RnProfScope prof_scope(RN_PROF_GLUE, st);
   if (rows <= 0) return RN_OK;
   DISPATCH_PREC(prec, (density_grad_seed_kernel<PREC><<<nblk(rows * 32, 256), 256, 0, st>>>(a8, wd, out, rows)));
   RN_CUDA_CHECK_LAUNCH();
@@ -791,6 +794,7 @@ int launch_density_grad_seed(int prec, ActBuf a8, const float* wd, ActBuf out, i
 int launch_heads_prologue_fwd(int prec, const float* heads_raw, const float* viewdirs, int s, int64_t row0, int64_t rows,
                               MlpScalars sc, ActBuf v0, float* density, float* normals_pred, float* grad_pred,
                               float* roughness, float* tint, cudaStream_t st) {
+  RnProfScope prof_scope(RN_PROF_HEADS_FWD, st);
   if (rows <= 0) return RN_OK;
   DISPATCH_PREC(prec, (heads_prologue_fwd_kernel<PREC><<<nblk(rows, kProRows), kProRows, 0, st>>>(
                           heads_raw, viewdirs, s, row0, rows, sc, v0, density, normals_pred, grad_pred, roughness, tint)));
@@ -802,6 +806,7 @@ int launch_heads_prologue_bwd(int prec, const float* heads_raw, const float* vie
                               MlpScalars sc, const float* dv0f, const float* dcolor, const float* g_density,
                               const float* g_normals_pred, const float* g_grad_pred, const float* g_roughness,
                               const float* g_tint, ActBuf d_scal, const float* dv0_unscale, cudaStream_t st) {
+  RnProfScope prof_scope(RN_PROF_HEADS_BWD, st);
   if (rows <= 0) return RN_OK;
   DISPATCH_PREC(prec, (heads_prologue_bwd_kernel<PREC><<<nblk(rows, kProRows), kProRows, 0, st>>>(
                           heads_raw, viewdirs, s, row0, rows, sc, dv0f, dcolor, g_density, g_normals_pred, g_grad_pred,
@@ -812,6 +817,7 @@ int launch_heads_prologue_bwd(int prec, const float* heads_raw, const float* vie
 
 int launch_color_fwd(const float* rgb_raw, const float* heads_raw, int64_t rows, MlpScalars sc, float* rgb,
                      float* diffuse, float* specular, cudaStream_t st) {
+  RnProfScope prof_scope(RN_PROF_COLOR, st);
   if (rows <= 0) return RN_OK;
   color_fwd_kernel<<<nblk(rows, 256), 256, 0, st>>>(rgb_raw, heads_raw, rows, sc, rgb, diffuse, specular);
   RN_CUDA_CHECK_LAUNCH();
@@ -821,6 +827,7 @@ int launch_color_fwd(const float* rgb_raw, const float* heads_raw, int64_t rows,
 int launch_color_bwd(int prec, const float* rgb_raw, const float* heads_raw, int64_t rows, MlpScalars sc,
                      const float* g_rgb, const float* g_diffuse, const float* g_specular, ActBuf d_rgb_raw,
                      float* dcolor, cudaStream_t st) {
+  RnProfScope prof_scope(RN_PROF_COLOR, st);
   if (rows <= 0) return RN_OK;
   DISPATCH_PREC(prec, (color_bwd_kernel<PREC><<<nblk(rows, 256), 256, 0, st>>>(rgb_raw, heads_raw, rows, sc, g_rgb, g_diffuse,
                                                                           g_specular, d_rgb_raw, dcolor)));
@@ -829,6 +836,7 @@ int launch_color_bwd(int prec, const float* rgb_raw, const float* heads_raw, int
 }
 
 int launch_colsum(int prec, ActBuf a, int64_t rows, int ncols, float* out, cudaStream_t st) {
+  RnProfScope prof_scope(RN_PROF_GLUE, st);
   if (rows <= 0) return RN_OK;
   if (ncols % 8 || ncols > 256) return rn_set_error(RN_ERR_ARG, "colsum: ncols must be a multiple of 8, <= 256");
   DISPATCH_PREC(prec, (colsum_kernel<PREC><<<nblk(rows, 128), 256, 0, st>>>(a, rows, ncols, out)));
@@ -837,6 +845,7 @@ int launch_colsum(int prec, ActBuf a, int64_t rows, int ncols, float* out, cudaS
 }
 
 int launch_f32_to_act(int prec, const float* src, int ld, int c0, int64_t rows, int ncols, ActBuf dst, cudaStream_t st) {
+  RnProfScope prof_scope(RN_PROF_GLUE, st);
   if (rows <= 0) return RN_OK;
   DISPATCH_PREC(prec, (f32_to_act_kernel<PREC><<<nblk(rows * (ncols >> 3), 256), 256, 0, st>>>(src, ld, c0, rows, ncols, dst)));
   RN_CUDA_CHECK_LAUNCH();
@@ -845,6 +854,7 @@ int launch_f32_to_act(int prec, const float* src, int ld, int c0, int64_t rows, 
 
 int launch_pack_segment(int prec, const float* src, int src_ld, int nr, int nc, int transpose, void* dst_hi, void* dst_lo,
                         int dst_ld, int r0, int c0, cudaStream_t st) {
+  RnProfScope prof_scope(RN_PROF_GLUE, st);
   DISPATCH_PREC(prec, (pack_segment_kernel<PREC><<<nblk((int64_t)nr * nc, 256), 256, 0, st>>>(src, src_ld, nr, nc, transpose, dst_hi,
                                                                                        dst_lo, dst_ld, r0, c0)));
   RN_CUDA_CHECK_LAUNCH();
@@ -853,12 +863,14 @@ int launch_pack_segment(int prec, const float* src, int src_ld, int nr, int nc, 
 
 int launch_unpack_add(const float* src, int src_ld, int r0, int c0, int nr, int nc, float* dst, int dst_ld,
                       const float* scale, cudaStream_t st) {
+  RnProfScope prof_scope(RN_PROF_GLUE, st);
   unpack_add_kernel<<<nblk((int64_t)nr * nc, 256), 256, 0, st>>>(src, src_ld, r0, c0, nr, nc, dst, dst_ld, scale);
   RN_CUDA_CHECK_LAUNCH();
   return RN_OK;
 }
 
 int launch_pack_batch(int prec, const PackTable& t, cudaStream_t st) {
+  RnProfScope prof_scope(RN_PROF_GLUE, st);
   if (t.n <= 0) return RN_OK;
   if (t.n > kMaxBatchSegs) return rn_set_error(RN_ERR_ARG, "pack_batch: too many segments");
   const dim3 grid(32, (unsigned)t.n);
@@ -867,6 +879,7 @@ int launch_pack_batch(int prec, const PackTable& t, cudaStream_t st) {
   return RN_OK;
 }
 int launch_unpack_add_batch(const UnpackTable& t, cudaStream_t st) {
+  RnProfScope prof_scope(RN_PROF_GLUE, st);
   if (t.n <= 0) return RN_OK;
   if (t.n > kMaxBatchSegs) return rn_set_error(RN_ERR_ARG, "unpack_add_batch: too many segments");
   const dim3 grid(32, (unsigned)t.n);
@@ -880,6 +893,7 @@ static unsigned reduce_grid(int64_t items) {
   return (unsigned)(b < 1 ? 1 : (b > 1184 ? 1184 : b));   // 8 CTAs per SM
 }
 int launch_amax_f32(const float* src, int64_t n, uint32_t* dst, cudaStream_t st) {
+  RnProfScope prof_scope(RN_PROF_GLUE, st);
   if (n <= 0) return RN_OK;
   if (n & 3) return rn_set_error(RN_ERR_ARG, "amax_f32: element count must be a multiple of 4");
   amax_f32_kernel<<<reduce_grid(n / 4), 256, 0, st>>>(src, n / 4, dst);
@@ -887,18 +901,21 @@ int launch_amax_f32(const float* src, int64_t n, uint32_t* dst, cudaStream_t st)
   return RN_OK;
 }
 int launch_amax_f16(const void* src, int ld, int ncols, int64_t rows, uint32_t* dst, cudaStream_t st) {
+  RnProfScope prof_scope(RN_PROF_GLUE, st);
   if (rows <= 0) return RN_OK;
   amax_f16_kernel<<<reduce_grid(rows * (ncols >> 3)), 256, 0, st>>>(reinterpret_cast<const uint16_t*>(src), ld, ncols, rows, dst);
   RN_CUDA_CHECK_LAUNCH();
   return RN_OK;
 }
 int launch_grad_scale(float* scal, int stage, cudaStream_t st) {
+  RnProfScope prof_scope(RN_PROF_GLUE, st);
   grad_scale_kernel<<<1, 1, 0, st>>>(scal, stage);
   RN_CUDA_CHECK_LAUNCH();
   return RN_OK;
 }
 int launch_scale_to_f16(const float* src, int ld_src, int64_t rows, int ncols, void* dst, int ld_dst, const float* scale,
                         cudaStream_t st) {
+  RnProfScope prof_scope(RN_PROF_GLUE, st);
   if (rows <= 0) return RN_OK;
   scale_to_f16_kernel<<<nblk(rows * (ncols >> 3), 256), 256, 0, st>>>(src, ld_src, rows, ncols, reinterpret_cast<uint16_t*>(dst),
                                                                      ld_dst, scale);
@@ -906,6 +923,7 @@ int launch_scale_to_f16(const float* src, int ld_src, int64_t rows, int ncols, v
   return RN_OK;
 }
 int launch_rescale_f16(void* buf, int ld, int ncols, int64_t rows, const float* ratio, cudaStream_t st) {
+  RnProfScope prof_scope(RN_PROF_GLUE, st);
   if (rows <= 0) return RN_OK;
   rescale_f16_kernel<<<nblk(rows * (ncols >> 3), 256), 256, 0, st>>>(reinterpret_cast<uint16_t*>(buf), ld, ncols, rows, ratio);
   RN_CUDA_CHECK_LAUNCH();

@@ -1095,6 +1095,7 @@ extern "C" int rn_resample(const float* sdist_in, const float* weights_in, const
                            const float* far_, int64_t n_rays, int s_in, int s_out, float padding, float anneal,
                            float dom_lo, float dom_hi, float* sdist_out, float* tdist_out, float* cw_out,
                            int32_t* idx_out, void* stream) {
+  RnProfScope prof_scope(RN_PROF_RAY, (cudaStream_t)stream);
   if (n_rays < 0 || s_in < 1 || s_out < 2) return rn_set_error(RN_ERR_ARG, "rn_resample: need s_in >= 1 and s_out >= 2");
   if (!weights_in && !cw_in) return rn_set_error(RN_ERR_ARG, "rn_resample: need weights or a CDF");
   if (n_rays == 0) return RN_OK;
@@ -1115,6 +1116,7 @@ extern "C" int rn_resample(const float* sdist_in, const float* weights_in, const
 
 extern "C" int rn_max_dilate_weights(const float* t, const float* w, int64_t n_rays, int s, float dilation, float dom_lo,
                                      float dom_hi, int renormalize, int trim, float* t_out, float* w_out, void* stream) {
+  RnProfScope prof_scope(RN_PROF_RAY, (cudaStream_t)stream);
   if (n_rays < 0 || s < 1 || s > 1024) return rn_set_error(RN_ERR_ARG, "rn_max_dilate_weights: need 1 <= s <= 1024");
   if (n_rays == 0) return RN_OK;
   int levels = 1;
@@ -1133,6 +1135,7 @@ extern "C" int rn_composite_fwd(const float* density, const float* tdist, const 
                                 const float* normals_pred, const float* roughness, const float* tint, int64_t n_rays,
                                 int s, float bg, float* weights_out, float* comp_out, float* extras_out,
                                 double* pct_out, void* stream) {
+  RnProfScope prof_scope(RN_PROF_RAY, (cudaStream_t)stream);
   if (n_rays < 0 || s < 1) return rn_set_error(RN_ERR_ARG, "rn_composite_fwd: bad sizes");
   if (n_rays == 0) return RN_OK;
   if (s == 128) {
@@ -1158,6 +1161,7 @@ extern "C" int rn_composite_bwd(const float* density, const float* tdist, const 
                                 const float* g_extras, int64_t n_rays, int s, float bg, float* d_density, float* d_rgb,
                                 float* d_diffuse, float* d_specular, float* d_normals_pred, float* d_roughness,
                                 float* d_tint, void* stream) {
+  RnProfScope prof_scope(RN_PROF_RAY, (cudaStream_t)stream);
   if (n_rays < 0 || s < 1) return rn_set_error(RN_ERR_ARG, "rn_composite_bwd: bad sizes");
   if (n_rays == 0) return RN_OK;
   if (s == 128) {
@@ -1178,6 +1182,7 @@ extern "C" int rn_composite_bwd(const float* density, const float* tdist, const 
 
 extern "C" int rn_lossfun_outer_fwd(const float* t, const float* w, const float* t_env, const float* w_env,
                                     int64_t n_rays, int s, int se, float* loss_out, void* stream) {
+  RnProfScope prof_scope(RN_PROF_RAY, (cudaStream_t)stream);
   if (n_rays == 0) return RN_OK;
   size_t smem = (size_t)kWarps * 3 * (se + 1) * sizeof(float);
   if (int rc = ensure_smem(lossfun_outer_kernel<false>, smem)) return rc;
@@ -1189,6 +1194,7 @@ extern "C" int rn_lossfun_outer_fwd(const float* t, const float* w, const float*
 
 extern "C" int rn_lossfun_outer_bwd(const float* t, const float* w, const float* t_env, const float* w_env,
                                     const float* g_loss, int64_t n_rays, int s, int se, float* d_w_env, void* stream) {
+  RnProfScope prof_scope(RN_PROF_RAY, (cudaStream_t)stream);
   if (n_rays == 0) return RN_OK;
   size_t smem = (size_t)kWarps * 3 * (se + 1) * sizeof(float);
   if (int rc = ensure_smem(lossfun_outer_kernel<true>, smem)) return rc;
@@ -1199,6 +1205,7 @@ extern "C" int rn_lossfun_outer_bwd(const float* t, const float* w, const float*
 }
 
 extern "C" int rn_distortion_fwd(const float* t, const float* w, int64_t n_rays, int s, float* loss_out, void* stream) {
+  RnProfScope prof_scope(RN_PROF_RAY, (cudaStream_t)stream);
   if (n_rays == 0) return RN_OK;
   size_t smem = (size_t)kWarps * 2 * s * sizeof(float);
   if (int rc = ensure_smem(distortion_kernel<false>, smem)) return rc;
@@ -1209,6 +1216,7 @@ extern "C" int rn_distortion_fwd(const float* t, const float* w, int64_t n_rays,
 
 extern "C" int rn_distortion_bwd(const float* t, const float* w, const float* g_loss, int64_t n_rays, int s, float* d_w,
                                  void* stream) {
+  RnProfScope prof_scope(RN_PROF_RAY, (cudaStream_t)stream);
   if (n_rays == 0) return RN_OK;
   size_t smem = (size_t)kWarps * 2 * s * sizeof(float);
   if (int rc = ensure_smem(distortion_kernel<true>, smem)) return rc;
@@ -1277,6 +1285,7 @@ data_loss_bwd_kernel(const float* __restrict__ rgb, const float* __restrict__ gt
 
 extern "C" int rn_data_loss_fwd(const float* rgb, const float* gt, const float* lossmult, int64_t n_rays, int charb,
                                 float charb_padding, float* sums_out, void* stream) {
+  RnProfScope prof_scope(RN_PROF_RAY, (cudaStream_t)stream);
   if (!rgb || !gt || !sums_out || n_rays < 0) return rn_set_error(RN_ERR_ARG, "rn_data_loss_fwd: bad arguments");
   data_loss_fwd_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(rgb, gt, lossmult, n_rays, charb, charb_padding * charb_padding, sums_out);
   RN_CUDA_CHECK_LAUNCH();
@@ -1285,6 +1294,7 @@ extern "C" int rn_data_loss_fwd(const float* rgb, const float* gt, const float* 
 
 extern "C" int rn_data_loss_bwd(const float* rgb, const float* gt, const float* lossmult, const float* g_sums, int64_t n_rays,
                                 int charb, float charb_padding, float* d_rgb, void* stream) {
+  RnProfScope prof_scope(RN_PROF_RAY, (cudaStream_t)stream);
   if (n_rays == 0) return RN_OK;
   if (!rgb || !gt || !g_sums || !d_rgb || n_rays < 0) return rn_set_error(RN_ERR_ARG, "rn_data_loss_bwd: bad arguments");
   data_loss_bwd_kernel<<<(unsigned)((3 * n_rays + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
@@ -1296,6 +1306,7 @@ extern "C" int rn_data_loss_bwd(const float* rgb, const float* gt, const float* 
 extern "C" int rn_normal_losses_fwd(const float* weights, const float* normals, const float* normals_pred,
                                     const float* viewdirs, int64_t n_rays, int s, int ori_target_is_pred, float* ori_out,
                                     float* pred_out, void* stream) {
+  RnProfScope prof_scope(RN_PROF_RAY, (cudaStream_t)stream);
   if (n_rays == 0) return RN_OK;
   if (!weights || !normals_pred || !viewdirs || !ori_out || !pred_out || s < 1) return rn_set_error(RN_ERR_ARG, "rn_normal_losses_fwd: bad arguments");
   if (!ori_target_is_pred && !normals) return rn_set_error(RN_ERR_ARG, "rn_normal_losses_fwd: orientation target 'normals' needs the density-gradient normals");
@@ -1310,6 +1321,7 @@ extern "C" int rn_normal_losses_fwd(const float* weights, const float* normals, 
 extern "C" int rn_normal_losses_bwd(const float* weights, const float* normals, const float* normals_pred,
                                     const float* viewdirs, const float* g_ori, const float* g_pred, int64_t n_rays, int s,
                                     int ori_target_is_pred, float* d_weights, float* d_normals_pred, void* stream) {
+  RnProfScope prof_scope(RN_PROF_RAY, (cudaStream_t)stream);
   if (n_rays == 0) return RN_OK;
   if (!weights || !normals_pred || !viewdirs || !d_weights || !d_normals_pred || s < 1) return rn_set_error(RN_ERR_ARG, "rn_normal_losses_bwd: bad arguments");
   if (!ori_target_is_pred && !normals) return rn_set_error(RN_ERR_ARG, "rn_normal_losses_bwd: orientation target 'normals' needs the density-gradient normals");

@@ -12,6 +12,8 @@ for ln in open(sys.argv[1]):
         print('  value %.0f rays/s  %.2f ms  e2e %.0f (%.2f ms; single steps %s) | chains %.1f TF/s algo, exec frac %.3f, share %.3f | wgrad %.0f GB/s frac %.3f share %.3f | sm %s MHz' % (
             d['value'], d['ms_per_step'], d['e2e']['value'], d['e2e']['ms_per_step'], d['e2e'].get('host_wall_ms_of_single_steps'), r['achieved'], r['executed_mma']['frac'], r['kernel_share_of_step'],
             w['achieved'], w['frac'], w['kernel_share_of_step'], d['clocks']['sm_mhz']))
+        kc = d['kernel_classes']
+        print('  ms/step by class: ' + ', '.join('%s %.2f' % (k, v['ms'] / d['steps']) for k, v in kc.items() if v['launches']) + ' | profiled step %.2f' % r['profiled_pass_ms_per_step'])
 PY
 }
 if [ -z "$NOTEST" ]; then
