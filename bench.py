@@ -557,7 +557,7 @@ def run_b200(args):
     sec = d['ms'] * 1e-3
     achieved = d['flops'] / sec / 1e12 if sec > 0 else 0.0
     executed = d['exec_flops'] / sec / 1e12 if sec > 0 else 0.0
-    traffic = load_profile_json('r02_traffic.json')
+    traffic = load_profile_json('r02b_traffic.json') or load_profile_json('r02_traffic.json')
     roofline = {'bound': 'tensor', 'kernel': dom, 'achieved': achieved, 'peak': peaks['bf16_sustained'], 'unit': 'TFLOP/s',
                 'frac': achieved / peaks['bf16_sustained'], 'traffic': traffic.get(dom),
                 'peak_source': peaks['source'] + ' (sustained bf16: the chains are timed inside a long step)',

@@ -13,7 +13,7 @@ CSRC = os.path.join(HERE, 'csrc')
 ROOT = os.path.dirname(HERE)
 LIB = os.path.join(HERE, 'librefnerf_b200.so')
 OBJ_DIR = os.path.join(HERE, 'build')
-SOURCES = ['raymarch.cu', 'raygen.cu', 'pointwise.cu', 'gemm_simt.cu', 'gemm_tc.cu', 'chain_pair.cu', 'chain_x3.cu', 'mlp.cu']
+SOURCES = ['raymarch.cu', 'raygen.cu', 'pointwise.cu', 'gemm_simt.cu', 'gemm_tc.cu', 'chain_pair.cu', 'chain_x3.cu', 'chain_x3t.cu', 'mlp.cu']
 NVCC_FLAGS = ['-O3', '-std=c++17', '-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-Xcompiler', '-fPIC',
               '-Xcompiler', '-fvisibility=hidden', '--expt-relaxed-constexpr', '-Wno-deprecated-gpu-targets']
 

@@ -194,6 +194,7 @@ struct PairOp {
   int kind;        // 0: hidden (result -> activation tile [+ TMA save]); 1: global epilogue
   int gepi;        // kind 1: which global epilogue
   int save;        // hidden: TMA-store the result through maps.save[op]
+  int acc_half;    // chain_x3t.cu: the accumulator column half a one-half (global) op runs in
   const float* bias;       // forward hidden ops / global ops with a bias: [n] floats (padded to a multiple of 4)
   const uint32_t* mask_bits;   // backward hidden ops: ReLU bits (8 words per row, layout of relu_bits_index in gemm.cuh)
   uint32_t* save_bits;         // forward hidden ops: optional ReLU bits of the result
@@ -205,6 +206,7 @@ struct PairParams {
   int a_f16, b_f16;  // operand formats of the MMAs (0 bf16, 1 fp16); the activation tile / outputs use a's
   int w_planes;      // chain_pair.cu: 2 = every weight K block arrives as a hi and a lo ring item (2 MMAs per K step)
   int split_order;   // chain_x3.cu: issue order of the (column half, K block) pairs of a 256-wide op, see res_order()
+  int in_valid;      // chain_x3t.cu: valid (non-padding) columns of the chain input; K steps entirely beyond it are skipped
   int whatif;        // chain_x3.cu, RN_X3_WHATIF (TIMING EXPERIMENTS ONLY, results are garbage): bit 0 = the epilogue skips its
                      // shared-memory stores, bit 1 = the producer skips the weight loads, bit 2 = no TMA save stores
   float seed_scale;  // seed ops: vec * seed_scale

@@ -636,6 +636,9 @@ chain_x3_kernel(const __grid_constant__ X3Maps maps, const __grid_constant__ Pai
 
 int launch_chain_x3(const ChainArgs& a, cudaStream_t st) {
   if (a.m <= 0) return RN_OK;
+  // default: the tensor-memory-resident variant (chain_x3t.cu), same op list and results; RN_X3_TS=0 runs this file's kernel
+  static const int use_ts = getenv("RN_X3_TS") ? atoi(getenv("RN_X3_TS")) : 1;
+  if (use_ts) return launch_chain_x3t(a, st);
   if (a.act_f16 || a.w_f16) return rn_set_error(RN_ERR_UNSUPPORTED, "chain_x3: bf16 planes only");
   if (a.num_ops < 1 || a.num_ops > kMaxOps) return rn_set_error(RN_ERR_ARG, "chain_x3: 1..12 ops");
   if (a.in.hi && (!a.in.lo || a.in_cols % 64 || a.in_cols < 64 || a.in_cols > 256))

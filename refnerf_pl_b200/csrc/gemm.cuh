@@ -99,6 +99,7 @@ struct ChainArgs {
   double exec_flops = 0.0;   // computed by the launchers: 2 * rows * n * k_padded * MMAs per K step, summed over the ops
 };
 int launch_chain(const ChainArgs& a, cudaStream_t st);      // chain_pair.cu: CTA pairs, cta_group::2, two row tiles in flight
+int launch_chain_x3t(const ChainArgs& a, cudaStream_t st);  // chain_x3t.cu: the same chain with the activation in tensor memory (TS-form MMAs)
 int launch_chain_x3(const ChainArgs& a, cudaStream_t st);   // chain_x3.cu: CTA pairs, split-bf16 operands, one row tile
 // ReLU bit masks: 8 words per row (word w = columns [32w, 32w+32)), stored so that the 32 rows a warp owns are
 // contiguous per word: word index of (row, w) = ((row / 32) * 8 + w) * 32 + row % 32.  Buffers are sized for rows

@@ -378,7 +378,9 @@ int chain_layers(const Ctx& c, int l0, int lh, int64_t rows, ActBuf in, int in_c
   a.m = rows;
   a.in = in;
   a.in_cols = in_cols;
-  a.in_valid = in_cols;
+  // the real input width (96 IPE columns of 128, 201 view-net inputs of 256): the buffer is zero beyond it, the TMA loads
+  // zero-fill there and chain_x3t.cu skips the K steps that are padding only
+  a.in_valid = layer_def(l0).k1_real < in_cols ? layer_def(l0).k1_real : in_cols;
   a.act_f16 = a.w_f16 = c.f16;
   a.num_ops = 9;
   double flops = 0.0;
