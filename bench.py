@@ -430,8 +430,15 @@ def run_b200(args):
     launches = lib.rn_launch_count() - l0
     clocks = sampler.stop() if sampler else None
     ms_step = ms_total / args.steps
-    host_enqueue_ms = timed.host_ms
     value = world * n / (ms_step * 1e-3)
+    # host time to ENQUEUE one step, measured on an empty launch queue (over K steps the host runs ~5 steps ahead and then
+    # blocks in cudaLaunchKernel on the full queue, which would be counted as host time)
+    barrier()
+    h0 = time.perf_counter()
+    wl.step()
+    wl.step()
+    host_enqueue_ms = (time.perf_counter() - h0) * 1e3 / 2
+    barrier()
     # ---- the same K steps once more with per-kernel-class CUDA events around every GEMM-class launch (roofline) ----
     lib.rn_prof_enable(1)
     prof_read()

@@ -537,3 +537,19 @@ def test_parameter_gradients_of_a_step_tile_one_flat_buffer():
 def ops_mod():
     from refnerf_pl_b200 import ops
     return ops
+
+
+def test_shared_memory_chain_variant_still_matches():
+    """`RN_X3_TS=0` selects chain_x3.cu (activation tile in shared memory) instead of the default chain_x3t.cu (tensor
+    memory).  The switch is read once per process, so the fused-chain and trained-fixture parity tests are re-run in a
+    child process with it set."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, RN_X3_TS='0')
+    r = subprocess.run([sys.executable, '-m', 'pytest', os.path.join(root, 'tests', 'test_gpu_model.py'), '-q', '-m', 'gpu', '-x',
+                        '-k', 'fused or (fixture and trained and bf16x3) or tiny_and_ragged'], cwd=root, env=env,
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert ' passed' in r.stdout

@@ -1,5 +1,5 @@
 #!/bin/bash
-# Round-end GPU evidence: full test-suite, bench (both arms), memcheck, ncu captures of the small warp-per-ray kernels.
+# Round-end GPU evidence: full test-suite, smoke, bench (both arms), memcheck of every fused path.
 mkdir -p gpurun_out
 rm -f gpurun_out/parity_report.jsonl
 run() { name=$1; shift; echo "=== $name"; timeout ${TMO:-900} "$@" > gpurun_out/$name.log 2>&1; echo "rc=$?"; tail -n ${TAILN:-6} gpurun_out/$name.log | cut -c1-400; }
@@ -8,7 +8,3 @@ run smoke python __graft_entry__.py --smoke
 run bench_ref python bench.py --impl reference --steps 3 --warmup 1
 run bench_main python bench.py --steps 20 --warmup 5
 TMO=1200 run memcheck compute-sanitizer --tool memcheck --print-limit 5 python tools/memcheck_run.py 300 16384
-# the three instruction-bound warp-per-ray kernels (VERDICT r1 weak point 8): full ncu sections of one launch each
-timeout 600 ncu --set full --clock-control none -k regex:"resample128|lossfun_outer_kernel|distortion_kernel|max_dilate|composite_fwd128|composite_bwd128" -c 16 -f -o gpurun_out/rayk_r02 \
-    python tools/hbm_bench.py 1 > gpurun_out/ncu_rayk_r02.log 2>&1
-echo "ncu rayk rc=$?"
