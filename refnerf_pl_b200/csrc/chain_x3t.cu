@@ -205,6 +205,9 @@ chain_x3t_kernel(const __grid_constant__ X3Maps maps, const __grid_constant__ Pa
     uint32_t aver = 0;       // A-tile versions acquired so far (act_ready phases)
     bool need_acq = false;   // the A tile has been (is being) rewritten since it was last acquired
     uint32_t opcount = 0;
+    // (Moving an item's barrier waits one item ahead -- before the MMAs of the item in front of it -- was measured and is
+    // slower: a passing mbarrier.try_wait costs the MMA warp 150-250 cycles under load wherever it stands, and the tensor
+    // pipe's queue is too short to cover it; profiles/r02b_chain_x3t_trace_train.txt.)
     auto wait_full = [&](uint32_t q) { mbar_wait(&ring_full[q % kStages], (q / kStages) & 1u); };
     auto stage_addr = [&](uint32_t q) -> uint32_t { return smem_base + kSmemRing + (q % kStages) * kStageBytes; };
     // the 12 MMAs of one K block of one column half (hi*hi + lo*hi + hi*lo per K step), then up to four commits.
@@ -249,8 +252,9 @@ chain_x3t_kernel(const __grid_constant__ X3Maps maps, const __grid_constant__ Pa
         const int nhalf = L.n >= 256 ? 2 : 1;
         const uint32_t idesc = make_idesc2(nhalf == 2 ? 128 : L.n);
         const uint32_t rd_par = (gemm_idx & 1u) ^ 1u;   // acc_read phase of the previous GEMM op (passes at once for the first)
-        const bool tr = p.trace && blockIdx.x == 0 && opcount < 64 && lane == 0;
-        if (tr) p.trace[opcount * kTraceSlots + 0] = clock64();
+        const uint32_t top = opcount - (uint32_t)p.whatif;   // (RN_CHAIN_TRACE_SKIP ops of this CTA are not recorded)
+        const bool tr = p.trace && blockIdx.x == 0 && top < 64u && lane == 0;
+        if (tr) p.trace[top * kTraceSlots + 0] = clock64();
         bool acc_ok[2] = {false, false}, started[2] = {false, false};
         const int gh = nhalf == 1 ? L.acc_half : 0;   // one-half ops: the accumulator half they run in
         // column half `half` of the accumulator: the previous op's epilogue must have read it out
@@ -266,9 +270,10 @@ chain_x3t_kernel(const __grid_constant__ X3Maps maps, const __grid_constant__ Pa
           if (half == 0 && need_acq) mbar_wait(&act_ready[kb], aver & 1u);
           acc_acquire(half + gh);
           if (nhalf == 1 && kb == L.kb_act - 1) acc_acquire(gh ^ 1);   // (phase protection of the half this op does not use)
+          if (tr && kb == 0 && half == 0) p.trace[top * kTraceSlots + 7] = clock64();   // before the weight wait
           wait_full(pos);
           tc_fence_after();
-          if (tr && kb == 0 && half == 0) p.trace[opcount * kTraceSlots + 1] = clock64();
+          if (tr && kb == 0 && half == 0) p.trace[top * kTraceSlots + 1] = clock64();
           const uint32_t sb = stage_addr(pos);
           const bool last = kb == L.kb_act - 1 && (half > 0 || L.kb_in == 0);   // last item of this column half
           uint64_t* c1 = last ? &acc_full[half] : nullptr;
@@ -315,7 +320,7 @@ chain_x3t_kernel(const __grid_constant__ X3Maps maps, const __grid_constant__ Pa
         }
         for (int half = 1; half < nhalf; ++half)
           for (int kb = 0; kb < L.kb_act; ++kb) act_item(half, kb);
-        if (tr) p.trace[opcount * kTraceSlots + 2] = clock64();
+        if (tr) p.trace[top * kTraceSlots + 2] = clock64();
         if (L.kb_act && need_acq) {
           ++aver;
           need_acq = false;
@@ -464,8 +469,9 @@ chain_x3t_kernel(const __grid_constant__ X3Maps maps, const __grid_constant__ Pa
         }
         const uint32_t full_par = gemm_idx & 1u;
         ++gemm_idx;
-        const bool tr = p.trace && blockIdx.x == 0 && warp == 4 && lane == 0 && opcount < 64;
-        if (tr) p.trace[opcount * kTraceSlots + 3] = clock64();
+        const uint32_t top = opcount - (uint32_t)p.whatif;
+        const bool tr = p.trace && blockIdx.x == 0 && warp == 4 && lane == 0 && top < 64u;
+        if (tr) p.trace[top * kTraceSlots + 3] = clock64();
         const uint32_t taddr = tmem_base + kAccCol + lane_sel;
         if (L.kind == 0) {
           uint32_t bits_out[4];
@@ -473,7 +479,7 @@ chain_x3t_kernel(const __grid_constant__ X3Maps maps, const __grid_constant__ Pa
           for (int half = 0; half < 2; ++half) {
             mbar_wait(&acc_full[half], full_par);
             tc_fence_after();
-            if (half == 0 && tr) p.trace[opcount * kTraceSlots + 4] = clock64();
+            if (half == 0 && tr) p.trace[top * kTraceSlots + 4] = clock64();
             if (L.save) wait_drained(half);
             uint32_t ra[32], rb[32];
             tmem_ld32(taddr + (uint32_t)(128 * half + 32 * h), ra);
@@ -522,7 +528,7 @@ chain_x3t_kernel(const __grid_constant__ X3Maps maps, const __grid_constant__ Pa
                 if (cc == 1 && L.save) mbar_arrive(&written[half]);
                 mbar_arrive_cluster_addr(ready_addr0 + 8u * c);
               }
-              if (tr && c == 0) p.trace[opcount * kTraceSlots + 5] = clock64();
+              if (tr && c == 0) p.trace[top * kTraceSlots + 5] = clock64();
             }
           }
           ++nhid;
@@ -545,7 +551,7 @@ chain_x3t_kernel(const __grid_constant__ X3Maps maps, const __grid_constant__ Pa
           // op's MMAs are done (not earlier: the MMA warp acquires both barriers of the PREVIOUS op before this op's last K
           // block, so acc_full also tells that every warp's arrivals of the previous phase are in)
           if (lane == 0) mbar_arrive_cluster_addr(read_addr0 + 8u * (gh ^ 1));
-          if (tr) p.trace[opcount * kTraceSlots + 4] = clock64();
+          if (tr) p.trace[top * kTraceSlots + 4] = clock64();
           // this warp's (up to two) 32-column groups: read them out, hand the accumulator back, then process
           uint32_t rg[2][32];
 #pragma unroll
@@ -601,7 +607,7 @@ chain_x3t_kernel(const __grid_constant__ X3Maps maps, const __grid_constant__ Pa
           if (staged && lane == 0) mbar_arrive(&written[sch]);
           if (staged) save_outstanding[sch] = true;
         }
-        if (tr) p.trace[opcount * kTraceSlots + 6] = clock64();
+        if (tr) p.trace[top * kTraceSlots + 6] = clock64();
       }
     }
   }
@@ -633,6 +639,8 @@ int launch_chain_x3t(const ChainArgs& a, cudaStream_t st) {
   static const int x3t_opt = getenv("RN_X3T_OPT") ? atoi(getenv("RN_X3T_OPT")) : 3;   // bit 0: global ops in accumulator half 1,
   p.split_order = (x3t_opt >> 1) & 1;                                                 // bit 1: staged outputs on store channel 1
   p.seed_scale = a.seed_scale;
+  static const int trace_skip = getenv("RN_CHAIN_TRACE_SKIP") ? atoi(getenv("RN_CHAIN_TRACE_SKIP")) : 0;
+  p.whatif = trace_skip;   // (chain_x3t.cu uses this field as the number of ops the debug timeline skips)
   p.num_ops = a.num_ops;
   p.in_kb = a.in.hi ? a.in_cols / kBK : 0;
   p.in_valid = a.in_valid > 0 ? a.in_valid : a.in_cols;
@@ -743,12 +751,12 @@ int launch_chain_x3t(const ChainArgs& a, cudaStream_t st) {
     for (int i = 0; i < 64 * kTraceSlots && !t0; ++i) t0 = hbuf[i];
     for (int i = 0; i < 64 * kTraceSlots; ++i)
       if (hbuf[i] && hbuf[i] < t0) t0 = hbuf[i];
-    printf("chain_x3t trace (mode %d, %d ops, m=%lld): per op: mma_begin first_item_ready mma_issued | epi_begin acc_full(half 0) blk0_handed epi_end  [cycles since first event]\n",
+    printf("chain_x3t trace (mode %d, %d ops, m=%lld): per op: mma_begin first_item_ready mma_issued | epi_begin acc_full(half 0) blk0_handed epi_end | first item: A block + accumulator acquired (then the weight wait)  [cycles since first event]\n",
            mode, a.num_ops, (long long)a.m);
     for (int i = 0; i < 44; ++i) {
       printf("  op %2d:", i);
-      for (int j = 0; j < 7; ++j) {
-        if (j == 3) printf(" |");
+      for (int j = 0; j < 8; ++j) {
+        if (j == 3 || j == 7) printf(" |");
         if (hbuf[i * kTraceSlots + j]) printf(" %8lld", hbuf[i * kTraceSlots + j] - t0); else printf("        -");
       }
       printf("\n");
