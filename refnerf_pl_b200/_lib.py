@@ -8,7 +8,8 @@ import os
 from ctypes import POINTER, Structure, c_char_p, c_double, c_float, c_int, c_int32, c_int64, c_size_t, c_void_p
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, 'librefnerf_b200.so')
+# (REFNERF_B200_LIB: another build of the same library, for A/B measurements of kernel variants on one box)
+LIB_PATH = os.environ.get('REFNERF_B200_LIB') or os.path.join(HERE, 'librefnerf_b200.so')
 
 PREC_FP32, PREC_BF16, PREC_BF16X3, PREC_FP16 = 0, 1, 2, 3
 PREC_BY_NAME = {'fp32': PREC_FP32, 'bf16': PREC_BF16, 'bf16x3': PREC_BF16X3, 'fp16': PREC_FP16}

@@ -176,18 +176,28 @@ chain_pair_kernel(const __grid_constant__ PairMaps maps, const __grid_constant__
       }
       __syncwarp();
     };
+    // The op descriptor of op l+1 is fetched while op l is issued (as in chain_x3t.cu): read at the op boundary and inside
+    // the K loops, the dependent constant-bank loads (run-time op index) sit on the MMA warp's critical path.
+    struct OpLite { int n, kb_act, kb_in, kind; };
+    auto fetch = [&](int l) -> OpLite {
+      const PairOp& o = p.op[l];
+      return OpLite{o.n, o.kb_act, o.kb_in, o.kind};
+    };
+    OpLite nxt = fetch(0);
+    const int w_planes = p.w_planes, a_f16 = p.a_f16, b_f16 = p.b_f16;
     for (int64_t st = cluster_id; st < num_super; st += num_clusters) {
       for (int l = 0; l < p.num_ops; ++l, ++opcount) {
-        const PairOp& L = p.op[l];
+        const OpLite L = nxt;
+        nxt = fetch(l + 1 < p.num_ops ? l + 1 : 0);
         if (L.kind == 2) {           // seed op: the epilogue warps generate the activation tile, no MMA
           ++nseed;
           seed_pending = true;
           continue;
         }
-        const uint32_t idesc = make_idesc2(L.n, p.a_f16, p.b_f16);
+        const uint32_t idesc = make_idesc2(L.n, a_f16, b_f16);
         const uint32_t free_parity = (nreal & 1u) ^ 1u;   // epilogue of the previous GEMM op on this tile done
         ++nreal;
-        if (p.w_planes == 2) {
+        if (w_planes == 2) {
           // split-bf16 weights against one-plane activations: every K block is a (hi, lo) pair of ring items and
           // both row tiles consume it before the next one (eight resident items would not fit the ring), so the two
           // accumulators fill side by side: dY * W_hi + dY * W_lo

@@ -280,9 +280,17 @@ chain_x3_kernel(const __grid_constant__ X3Maps maps, const __grid_constant__ Pai
       __syncwarp();
     };
     uint32_t tile_iter = 0;
+    // (the op descriptor of op l+1 is fetched while op l is issued, as in chain_x3t.cu)
+    struct OpLite { int n, kb_act, kb_in, kind; };
+    auto fetch = [&](int l) -> OpLite {
+      const PairOp& o = p.op[l];
+      return OpLite{o.n, o.kb_act, o.kb_in, o.kind};
+    };
+    OpLite nxt = fetch(0);
     for (int64_t tile = cluster_id; tile < num_tiles; tile += num_clusters, ++tile_iter) {
       for (int l = 0; l < p.num_ops; ++l, ++opcount) {
-        const PairOp& L = p.op[l];
+        const OpLite L = nxt;
+        nxt = fetch(l + 1 < p.num_ops ? l + 1 : 0);
         if (L.kind == 2) {   // seed op: the epilogue warps generate the activation tile, no MMA
           need_acq = true;
           continue;

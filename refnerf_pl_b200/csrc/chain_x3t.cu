@@ -242,9 +242,18 @@ chain_x3t_kernel(const __grid_constant__ X3Maps maps, const __grid_constant__ Pa
       }
       __syncwarp();
     };
+    // The op descriptor of op l+1 is fetched while op l is issued: read at the op boundary, the dependent constant-bank
+    // loads (run-time op index) sit on the MMA warp's critical path while the tensor pipe's queue runs dry.
+    struct OpLite { int n, kb_act, kb_in, kind, acc_half; };
+    auto fetch = [&](int l) -> OpLite {
+      const PairOp& o = p.op[l];
+      return OpLite{o.n, o.kb_act, o.kb_in, o.kind, o.acc_half};
+    };
+    OpLite nxt = fetch(0);
     for (int64_t tile = cluster_id; tile < num_tiles; tile += num_clusters) {
       for (int l = 0; l < p.num_ops; ++l, ++opcount) {
-        const PairOp& L = p.op[l];
+        const OpLite L = nxt;
+        nxt = fetch(l + 1 < p.num_ops ? l + 1 : 0);
         if (L.kind == 2) {   // seed op: the epilogue warps generate the A tile, no MMA
           need_acq = true;
           continue;
