@@ -21,6 +21,9 @@
 //     half it does not use back at once, so neither the second heads op nor the hidden op after a global op waits for a
 //     global epilogue; an activation-format global output is staged in hi-plane blocks 2, 3 + the lo-plane blocks (store
 //     channel 1), which the next row tile overwrites 3 000 cycles later than blocks 0, 1.
+//   * K steps of the chain input that are zero padding are not issued (96 of 128 IPE columns, 201 of 256 view-net
+//     inputs hold data), and the MMA warp fetches the descriptor of op l+1 while it issues op l (constant-bank loads with
+//     a run-time op index on the issue path of every item cost 1-2 % of the step).
 //   * an op that reads both the activation and the chain input (the skip layer) is issued as: half 0 over the activation K
 //     blocks, then the input K blocks for both halves, then half 1 over the activation K blocks -- half 1 of the
 //     accumulator is then first touched 3 072 cycles into the op, when the previous op's half-1 epilogue is long done.
@@ -486,10 +489,12 @@ chain_x3t_kernel(const __grid_constant__ X3Maps maps, const __grid_constant__ Pa
           uint32_t bits_out[4];
 #pragma unroll
           for (int half = 0; half < 2; ++half) {
+            // (the drain of the previous save does not depend on this op: waited for BEFORE the accumulator, so that the
+            // passing wait's latency is not on the path from acc_full to the first hand-over)
+            if (L.save) wait_drained(half);
             mbar_wait(&acc_full[half], full_par);
             tc_fence_after();
             if (half == 0 && tr) p.trace[top * kTraceSlots + 4] = clock64();
-            if (L.save) wait_drained(half);
             uint32_t ra[32], rb[32];
             tmem_ld32(taddr + (uint32_t)(128 * half + 32 * h), ra);
 #pragma unroll
