@@ -616,6 +616,10 @@ def run_b200(args):
         'config': {'workload': f'configs/blender_refnerf.gin single training step, {n}-ray batch per GPU, NerfMLP at '
                                'both levels (single_mlp), fwd (incl. density-gradient normals) + losses + bwd + Adam',
                    'rays_per_gpu': n, 'levels': 2, 'samples_per_level': 128, 'precision': args.precision,
+                   'chain_kernel': ('chain_x3t (split-bf16 chains, running activation in tensor memory)'
+                                    if os.environ.get('RN_X3_TS', '1') != '0' else 'chain_x3 (activation tile in shared memory)')
+                                   if args.precision == 'bf16x3' else 'chain_pair',
+                   'board': 'power-capped (clocks.reasons): executed-MMA throughput, not pipe utilisation, is what the step is bound by',
                    'l2': 'no explicit flush: per-step activation working set (>2 GB) exceeds the 126 MB L2',
                    'parallelism': (f'ray-sharded dp{world}, one NCCL gradient all-reduce per step; ' + str(allreduce_path))
                                   if world > 1 else 'single GPU'},
